@@ -1,0 +1,591 @@
+// pe_sphere.cu -- per-atom sphere enumeration, density gather-sum and voxel lists.
+//
+// Replaces (batched over atoms, one warp per atom):
+//   getSphereCrsFromXyz / getSphereCrsFromXyzList        pdb_eda/cutils.pyx:220-271
+//   _testXyzWithinDistance                               pdb_eda/cutils.pyx:205-218
+//   testValidXyz / testValidXyzList                      pdb_eda/cutils.pyx:273-313
+//   DensityMatrix.getTotalDensityFromXyz                 pdb_eda/ccp4.py:418-435
+//   findAberrantBlobs(atom) clustering (createCrsLists)  pdb_eda/ccp4.py:437-461, pdb_eda/cutils.pyx:44-70
+//
+// Design (B200): the work per in-sphere voxel is one 4-byte gather, so the kernel is bounded by instruction
+// issue long before HBM; everything is arranged to keep the per-candidate instruction count minimal:
+//   * lanes run along the column axis (the contiguous one in memory) so every gather of a warp is a few
+//     contiguous segments; small boxes pack several box rows into one warp (rows-per-iteration = 32 / pow2(D0));
+//   * in orthogonal cells the squared distance separates per axis:  d2 = fl(fl(X2 + Y2) + Z2)  where each term
+//     is the already-rounded square the reference forms, so the per-axis squares and the wrapped memory offsets
+//     are tabulated once per atom in shared memory and a candidate costs one DADD + one DSETP; the loop nest is
+//     ordered so that fl(X2 + Y2) is hoisted out of the innermost loop;
+//   * sqrt is never evaluated:  sqrt_rn(d2) <= r  <=>  d2 <= T(r)  (sphere_threshold);
+//   * gathers are predicated, not branched, and the inner loop is unrolled for memory-level parallelism;
+//   * warp-shuffle reductions in a fixed order make the float64 sums run-to-run deterministic.
+// Skewed cells (and boxes wider than kDMax) take a generic path that evaluates the reference's 3x3 mat-vec per
+// candidate in the host BLAS's accumulation order.
+#include "pe_common.cuh"
+
+namespace pe {
+
+constexpr int kDMax = 64;        // widest tabulated box edge (2R+2); wider boxes use the generic path
+constexpr int kSphereWarps = 4;  // warps (= atoms) per CTA
+
+struct AxisTab {
+    double sq[kDMax];  // fl((coord - atom)^2) per index along this axis
+    int off[kDMax];    // wrapped element offset contribution, or kInvalidOff
+};
+
+struct AtomBox {
+    int lo[3];
+    int dim[3];
+};
+
+// Box of getSphereCrsFromXyz (pdb_eda/cutils.pyx:238-243) and the distance threshold.
+__device__ __forceinline__ void atom_box(const pe_geom &g, double ax, double ay, double az, float radius, AtomBox &b,
+                                         double &thr) {
+    const double r = (double)radius;
+    int c0, r0, s0, rc, rr, rs;
+    xyz2crs(g, ax, ay, az, c0, r0, s0);
+    xyz2crs(g, __dadd_rn(g.origin[0], r), __dadd_rn(g.origin[1], r), __dadd_rn(g.origin[2], r), rc, rr, rs);
+    b.lo[0] = c0 - rc - 1;
+    b.lo[1] = r0 - rr - 1;
+    b.lo[2] = s0 - rs - 1;
+    b.dim[0] = max(2 * rc + 2, 0);
+    b.dim[1] = max(2 * rr + 2, 0);
+    b.dim[2] = max(2 * rs + 2, 0);
+    thr = sphere_threshold(r);
+}
+
+__global__ void sphere_params_kernel(pe_geom g, int n, const double *__restrict__ xyz, const float *__restrict__ radius,
+                                     int32_t *__restrict__ box, double *__restrict__ thr) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    AtomBox b;
+    double t;
+    atom_box(g, xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2], radius[a], b, t);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        box[6 * a + k] = b.lo[k];
+        box[6 * a + 3 + k] = b.dim[k];
+    }
+    thr[a] = t;
+}
+
+// Axis term of the separable squared distance for crs axis `axis`, index k (orthogonal cells only).
+__device__ __forceinline__ double axis_sq(const pe_geom &g, int axis, int k, double ax, double ay, double az) {
+    const int i = g.map2crs[axis];  // xyz axis carried by this crs axis
+    const double coord = __dadd_rn(__dmul_rn((double)k, g.grid_length[i]), g.origin[i]);
+    const double d = __dsub_rn(coord, sel3(ax, ay, az, i));
+    return __dmul_rn(d, d);
+}
+
+__device__ __forceinline__ int axis_off(const pe_geom &g, int axis, int k) {
+    const int w = wrap_index(k, g.ncrs[axis], g.crs_interval[axis]);
+    if (w < 0) return kInvalidOff;
+    return axis == 0 ? w : (axis == 1 ? w * g.ncrs[0] : w * g.ncrs[0] * g.ncrs[1]);
+}
+
+__device__ __forceinline__ void fill_tables(const pe_geom &g, const AtomBox &b, double ax, double ay, double az,
+                                            AxisTab *tab /* [2]: row axis, section axis */, int lane) {
+    for (int k = lane; k < b.dim[1]; k += 32) {
+        tab[0].sq[k] = axis_sq(g, 1, b.lo[1] + k, ax, ay, az);
+        tab[0].off[k] = axis_off(g, 1, b.lo[1] + k);
+    }
+    for (int k = lane; k < b.dim[2]; k += 32) {
+        tab[1].sq[k] = axis_sq(g, 2, b.lo[2] + k, ax, ay, az);
+        tab[1].off[k] = axis_off(g, 2, b.lo[2] + k);
+    }
+    __syncwarp();
+}
+
+// Is voxel (c, r, s) already owned by an earlier atom of the same group?  (set-union semantics)
+__device__ __forceinline__ bool claimed_by_earlier(const pe_geom &g, int first, int self, const int32_t *__restrict__ box,
+                                                   const double *__restrict__ thr, const double *__restrict__ xyz,
+                                                   int c, int r, int s) {
+    double vx, vy, vz;
+    crs2xyz(g, c, r, s, vx, vy, vz);
+    for (int e = first; e < self; ++e) {
+        const int32_t *b = box + 6 * e;
+        if (c < b[0] || c >= b[0] + b[3] || r < b[1] || r >= b[1] + b[4] || s < b[2] || s >= b[2] + b[5]) continue;
+        if (dist2(xyz[3 * e], xyz[3 * e + 1], xyz[3 * e + 2], vx, vy, vz) <= thr[e]) return true;
+    }
+    return false;
+}
+
+struct SphereAcc {
+    int n_all = 0, n_pos = 0, n_neg = 0, bad = 0;
+    double s_all = 0.0, s_pos = 0.0, s_neg = 0.0;
+    __device__ __forceinline__ void add(bool take, float v, float cp, float cn) {
+        n_all += take ? 1 : 0;
+        s_all += take ? (double)v : 0.0;
+        const bool p = take && cp > 0.f && v > cp;
+        const bool q = take && cn < 0.f && v < cn;
+        n_pos += p ? 1 : 0;
+        s_pos += p ? (double)v : 0.0;
+        n_neg += q ? 1 : 0;
+        s_neg += q ? (double)v : 0.0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ sums kernel
+// CASEB: the column axis carries z (the last term of the reference's sum), so fl(X2 + Y2) depends on (row, section).
+template <bool CASEB, bool GROUPED>
+__device__ __forceinline__ void sums_ortho(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
+                                           double ay, double az, double T, const AxisTab *tab, int lane, float cp,
+                                           float cn, int gfirst, int self, const int32_t *__restrict__ box,
+                                           const double *__restrict__ thr, const double *__restrict__ xyz,
+                                           SphereAcc &acc) {
+    // inner axis = the crs axis that carries z when that is the row or section axis; else sections.
+    const int inner = CASEB ? 2 : g.map2xyz[2];       // 1 (rows) or 2 (sections)
+    const int outer = 3 - inner;
+    const AxisTab &ti = tab[inner - 1];
+    const AxisTab &to = tab[outer - 1];
+    const int Di = sel3(b.dim[0], b.dim[1], b.dim[2], inner), Do = sel3(b.dim[0], b.dim[1], b.dim[2], outer), D0 = b.dim[0];
+    int d0p = 1;
+    while (d0p < D0 && d0p < 32) d0p <<= 1;
+    const int rpi = 32 / d0p;  // box rows handled per warp iteration
+    const int lrow = lane / d0p, lc = lane % d0p;
+    for (int cbase = 0; cbase < D0; cbase += 32) {
+        const int ic = cbase + lc;
+        const bool act = ic < D0;
+        const int c = b.lo[0] + ic;
+        const double sqc = act ? axis_sq(g, 0, c, ax, ay, az) : 0.0;
+        const int offc = act ? axis_off(g, 0, c) : kInvalidOff;
+        for (int ko = lrow; ko < Do; ko += rpi) {
+            const double sqo = to.sq[ko];
+            const int offo = to.off[ko];
+            const double P = __dadd_rn(sqc, sqo);  // fl(X2 + Y2) when !CASEB
+            const int offco = offc | offo;
+            const int sumco = (int)((unsigned)offc + (unsigned)offo);
+#pragma unroll 4
+            for (int ki = 0; ki < Di; ++ki) {
+                const double sqi = ti.sq[ki];
+                const int offi = ti.off[ki];
+                const double d2 = CASEB ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
+                bool inside = act && (d2 <= T);
+                const bool ok = (offco | offi) >= 0;
+                float v = 0.f;
+                if (inside && ok) v = __ldg(rho + (int)((unsigned)sumco + (unsigned)offi));
+                if (GROUPED) {
+                    if (inside && gfirst < self) {
+                        const int r = b.lo[1] + (inner == 1 ? ki : ko);
+                        const int s = b.lo[2] + (inner == 2 ? ki : ko);
+                        if (claimed_by_earlier(g, gfirst, self, box, thr, xyz, c, r, s)) inside = false;
+                    }
+                }
+                acc.bad |= (inside && !ok) ? 1 : 0;
+                acc.add(inside, v, cp, cn);
+            }
+        }
+    }
+}
+
+template <bool GROUPED>
+__device__ __forceinline__ void sums_generic(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
+                                             double ay, double az, double T, int lane, float cp, float cn, int gfirst,
+                                             int self, const int32_t *__restrict__ box, const double *__restrict__ thr,
+                                             const double *__restrict__ xyz, SphereAcc &acc) {
+    const int D0 = b.dim[0], D1 = b.dim[1], D2 = b.dim[2];
+    const int64_t vol = (int64_t)D0 * D1 * D2;
+    for (int64_t m = lane; m < vol; m += 32) {
+        const int ic = (int)(m % D0);
+        const int64_t t = m / D0;
+        const int ir = (int)(t % D1), is = (int)(t / D1);
+        const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+        double vx, vy, vz;
+        crs2xyz(g, c, r, s, vx, vy, vz);
+        bool inside = dist2(ax, ay, az, vx, vy, vz) <= T;
+        if (!inside) continue;
+        const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
+        const bool ok = (oc | orr | os) >= 0;
+        const float v = ok ? __ldg(rho + (oc + orr + os)) : 0.f;
+        if (GROUPED) {
+            if (gfirst < self && claimed_by_earlier(g, gfirst, self, box, thr, xyz, c, r, s)) inside = false;
+        }
+        acc.bad |= (inside && !ok) ? 1 : 0;
+        acc.add(inside, v, cp, cn);
+    }
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(kSphereWarps * 32)
+    sphere_sums_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
+                       const double *__restrict__ xyz, const int32_t *__restrict__ box, const double *__restrict__ thr,
+                       const int32_t *__restrict__ atom_first /* first atom of the atom's group (GROUPED) */, float cp,
+                       float cn, double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * kSphereWarps + warp;
+    if (a >= n_atoms) return;
+    AtomBox b;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.lo[k] = box[6 * a + k];
+        b.dim[k] = box[6 * a + 3 + k];
+    }
+    const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+    const double T = thr[a];
+    const int gfirst = GROUPED ? atom_first[a] : a;
+    SphereAcc acc;
+    const bool tabulated = g.orthogonal && b.dim[0] <= kDMax * 32 && b.dim[1] <= kDMax && b.dim[2] <= kDMax;
+    if (tabulated) {
+        fill_tables(g, b, ax, ay, az, tabs[warp], lane);
+        if (g.map2xyz[2] == 0)
+            sums_ortho<true, GROUPED>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, gfirst, a, box, thr, xyz, acc);
+        else
+            sums_ortho<false, GROUPED>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, gfirst, a, box, thr, xyz, acc);
+    } else {
+        sums_generic<GROUPED>(g, rho, b, ax, ay, az, T, lane, cp, cn, gfirst, a, box, thr, xyz, acc);
+    }
+    const int n_all = warp_sum(acc.n_all), n_pos = warp_sum(acc.n_pos), n_neg = warp_sum(acc.n_neg);
+    const int bad = warp_sum(acc.bad);
+    const double s_all = warp_sum(acc.s_all), s_pos = warp_sum(acc.s_pos), s_neg = warp_sum(acc.s_neg);
+    if (lane == 0) {
+        double *o = out + (int64_t)a * PE_SPHERE_NOUT;
+        o[0] = (double)n_all;
+        o[1] = s_all;
+        o[2] = (double)n_pos;
+        o[3] = s_pos;
+        o[4] = (double)n_neg;
+        o[5] = s_neg;
+        o[6] = bad ? 0.0 : 1.0;
+        o[7] = (double)b.dim[0] * (double)b.dim[1] * (double)b.dim[2];
+    }
+}
+
+__global__ void group_first_kernel(int n_groups, const int32_t *__restrict__ group_start, int32_t *__restrict__ atom_first) {
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= n_groups) return;
+    const int s = group_start[gidx], e = group_start[gidx + 1];
+    for (int a = s; a < e; ++a) atom_first[a] = s;
+}
+
+// Per-group totals from the per-atom partials, in atom order (deterministic).
+__global__ void group_reduce_kernel(int n_groups, const int32_t *__restrict__ group_start,
+                                    const double *__restrict__ partial, double *__restrict__ out) {
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= n_groups) return;
+    double acc[PE_SPHERE_NOUT];
+#pragma unroll
+    for (int k = 0; k < PE_SPHERE_NOUT; ++k) acc[k] = 0.0;
+    acc[6] = 1.0;
+    for (int a = group_start[gidx]; a < group_start[gidx + 1]; ++a) {
+        const double *p = partial + (int64_t)a * PE_SPHERE_NOUT;
+#pragma unroll
+        for (int k = 0; k < PE_SPHERE_NOUT; ++k) {
+            if (k == 6)
+                acc[k] = (p[k] != 0.0 && acc[k] != 0.0) ? 1.0 : 0.0;
+            else
+                acc[k] += p[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PE_SPHERE_NOUT; ++k) out[(int64_t)gidx * PE_SPHERE_NOUT + k] = acc[k];
+}
+
+// ------------------------------------------------------------------------------------------------ list kernels
+// Calls f(ic, ir, is, value_is_valid, rho) for every in-sphere voxel of the box, lanes in parallel.
+template <class F>
+__device__ __forceinline__ void for_each_inside(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b,
+                                                double ax, double ay, double az, double T, AxisTab *tab, int lane, F f) {
+    const int D0 = b.dim[0], D1 = b.dim[1], D2 = b.dim[2];
+    const bool tabulated = g.orthogonal && D1 <= kDMax && D2 <= kDMax;
+    if (tabulated) {
+        fill_tables(g, b, ax, ay, az, tab, lane);
+        const bool caseb = g.map2xyz[2] == 0;
+        const int inner = caseb ? 2 : g.map2xyz[2];
+        const int outer = 3 - inner;
+        const AxisTab &ti = tab[inner - 1];
+        const AxisTab &to = tab[outer - 1];
+        const int Di = sel3(b.dim[0], b.dim[1], b.dim[2], inner), Do = sel3(b.dim[0], b.dim[1], b.dim[2], outer);
+        int d0p = 1;
+        while (d0p < D0 && d0p < 32) d0p <<= 1;
+        const int rpi = 32 / d0p, lrow = lane / d0p, lc = lane % d0p;
+        for (int cbase = 0; cbase < D0; cbase += 32) {
+            const int ic = cbase + lc;
+            if (ic >= D0) continue;
+            const int c = b.lo[0] + ic;
+            const double sqc = axis_sq(g, 0, c, ax, ay, az);
+            const int offc = axis_off(g, 0, c);
+            for (int ko = lrow; ko < Do; ko += rpi) {
+                const double sqo = to.sq[ko];
+                const int offo = to.off[ko];
+                const double P = __dadd_rn(sqc, sqo);
+                for (int ki = 0; ki < Di; ++ki) {
+                    const double sqi = ti.sq[ki];
+                    const int offi = ti.off[ki];
+                    const double d2 = caseb ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
+                    if (!(d2 <= T)) continue;
+                    const bool ok = (offc | offo | offi) >= 0;
+                    const float v = ok ? __ldg(rho + (offc + offo + offi)) : 0.f;
+                    const int ir = inner == 1 ? ki : ko, is = inner == 2 ? ki : ko;
+                    f(ic, ir, is, ok, v);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int64_t vol = (int64_t)D0 * D1 * D2;
+        for (int64_t m = lane; m < vol; m += 32) {
+            const int ic = (int)(m % D0);
+            const int64_t t = m / D0;
+            const int ir = (int)(t % D1), is = (int)(t / D1);
+            const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+            double vx, vy, vz;
+            crs2xyz(g, c, r, s, vx, vy, vz);
+            if (!(dist2(ax, ay, az, vx, vy, vz) <= T)) continue;
+            const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
+            const bool ok = (oc | orr | os) >= 0;
+            const float v = ok ? __ldg(rho + (oc + orr + os)) : 0.f;
+            f(ic, ir, is, ok, v);
+        }
+        __syncwarp();
+    }
+}
+
+// Density predicate of getSphereCrsFromXyz (pdb_eda/cutils.pyx:245); all operands are exact float32 values.
+__device__ __forceinline__ bool passes(float v, float cut) { return (0.f < cut && cut < v) || (v < cut && cut < 0.f) || cut == 0.f; }
+
+__global__ void __launch_bounds__(kSphereWarps * 32)
+    sphere_count_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
+                        const double *__restrict__ xyz, const float *__restrict__ radius, float cutoff,
+                        int32_t *__restrict__ count, int32_t *__restrict__ box_out) {
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * kSphereWarps + warp;
+    if (a >= n_atoms) return;
+    const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+    AtomBox b;
+    double T;
+    atom_box(g, ax, ay, az, radius[a], b, T);
+    int n = 0;
+    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane,
+                    [&](int, int, int, bool, float v) { n += passes(v, cutoff) ? 1 : 0; });
+    n = warp_sum(n);
+    if (lane == 0) {
+        count[a] = n;
+        if (box_out) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                box_out[6 * a + k] = b.lo[k];
+                box_out[6 * a + 3 + k] = b.dim[k];
+            }
+        }
+    }
+}
+
+// Dynamic shared memory per warp: bits[nw] | pref[nw] | (labels only) pidx[maxbox] lab[maxbox] rnk[maxbox] as u16.
+template <bool LABELS>
+__global__ void sphere_fill_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
+                                   const double *__restrict__ xyz, const float *__restrict__ radius, float cutoff,
+                                   const int64_t *__restrict__ offset, int max_box, int32_t *__restrict__ out_index,
+                                   float *__restrict__ out_value, int32_t *__restrict__ out_label) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * warps + warp;
+    if (a >= n_atoms) return;
+    const int nw_max = (max_box + 31) / 32;
+    const size_t per_warp = (size_t)nw_max * 8 + (LABELS ? (size_t)((max_box + 1) / 2 * 2) * 6 : 0);
+    unsigned char *base = dyn_smem + per_warp * warp;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(base);
+    uint32_t *pref = bits + nw_max;
+    uint16_t *pidx = reinterpret_cast<uint16_t *>(pref + nw_max);
+    uint16_t *lab = pidx + (max_box + 1) / 2 * 2;
+    uint16_t *rnk = lab + (max_box + 1) / 2 * 2;
+
+    const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+    AtomBox b;
+    double T;
+    atom_box(g, ax, ay, az, radius[a], b, T);
+    const int D1 = b.dim[1], D2 = b.dim[2];
+    const int vol = b.dim[0] * D1 * D2;
+    if (vol > max_box) return;  // caller's bound was wrong; the count pass reported the real box, nothing is written
+    const int nw = (vol + 31) / 32;
+    for (int w = lane; w < nw; w += 32) bits[w] = 0u;
+    __syncwarp();
+    // 1. membership bits in the reference's order: p = (ic*D1 + ir)*D2 + is
+    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
+        if (passes(v, cutoff)) {
+            const int p = (ic * D1 + ir) * D2 + is;
+            atomicOr(bits + (p >> 5), 1u << (p & 31));
+        }
+    });
+    // 2. per-word prefix counts
+    int running = 0;
+    for (int w0 = 0; w0 < nw; w0 += 32) {
+        const int w = w0 + lane;
+        const int cnt = w < nw ? __popc(bits[w]) : 0;
+        const int ex = warp_excl_scan(cnt, lane);
+        if (w < nw) pref[w] = (uint32_t)(running + ex);
+        running += __shfl_sync(kFull, ex + cnt, 31);
+    }
+    __syncwarp();
+    const int n = running;
+    const int64_t obase = offset[a];
+    // 3. ordered emission
+    for (int w = lane; w < nw; w += 32) {
+        uint32_t word = bits[w];
+        int j = (int)pref[w];
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            const int p = w * 32 + bit;
+            out_index[obase + j] = p;
+            if (LABELS) pidx[j] = (uint16_t)p;
+            if (out_value) {
+                const int is = p % D2, t = p / D2, ir = t % D1, ic = t / D1;
+                const int oc = axis_off(g, 0, b.lo[0] + ic), orr = axis_off(g, 1, b.lo[1] + ir), os = axis_off(g, 2, b.lo[2] + is);
+                out_value[obase + j] = ((oc | orr | os) >= 0) ? __ldg(rho + (oc + orr + os)) : 0.f;
+            }
+            ++j;
+        }
+    }
+    if (!LABELS) return;
+    __syncwarp();
+    // 4. 26-connected clusters of the listed voxels: min-label propagation with pointer jumping.
+    for (int j = lane; j < n; j += 32) lab[j] = (uint16_t)j;
+    __syncwarp();
+    for (;;) {
+        bool changed = false;
+        for (int j = lane; j < n; j += 32) {
+            const int p = pidx[j];
+            const int is = p % D2, t = p / D2, ir = t % D1, ic = t / D1;
+            int m = lab[j];
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int c2 = ic + dc;
+                if (c2 < 0 || c2 >= b.dim[0]) continue;
+                for (int dr = -1; dr <= 1; ++dr) {
+                    const int r2 = ir + dr;
+                    if (r2 < 0 || r2 >= D1) continue;
+                    for (int ds = -1; ds <= 1; ++ds) {
+                        const int s2 = is + ds;
+                        if (s2 < 0 || s2 >= D2) continue;
+                        const int q = (c2 * D1 + r2) * D2 + s2;
+                        const uint32_t word = bits[q >> 5];
+                        if (!((word >> (q & 31)) & 1u)) continue;
+                        const int jn = (int)pref[q >> 5] + __popc(word & ((1u << (q & 31)) - 1u));
+                        m = min(m, (int)lab[jn]);
+                    }
+                }
+            }
+            m = min(m, (int)lab[m]);
+            if (m < (int)lab[j]) {
+                lab[j] = (uint16_t)m;
+                changed = true;
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(kFull, changed)) break;
+    }
+    // 5. number the clusters by their first member (the order createCrsLists creates them in)
+    int nroots = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const int isroot = (j < n && lab[j] == j) ? 1 : 0;
+        const int ex = warp_excl_scan(isroot, lane);
+        if (isroot) rnk[j] = (uint16_t)(nroots + ex);
+        nroots += __shfl_sync(kFull, ex + isroot, 31);
+    }
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) out_label[obase + j] = (int32_t)rnk[lab[j]];
+}
+
+}  // namespace pe
+
+using namespace pe;
+
+extern "C" {
+
+int64_t pe_sphere_workspace_bytes(int64_t n_atoms) {
+    if (n_atoms < 0) n_atoms = 0;
+    return align_up(n_atoms * 6 * 4, 256) + align_up(n_atoms * 8, 256) + align_up(n_atoms * 4, 256) +
+           align_up(n_atoms * PE_SPHERE_NOUT * 8, 256);
+}
+
+int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const double *d_xyz, const float *d_radius,
+                   int32_t n_groups, const int32_t *d_group_start, float cut_pos, float cut_neg, double *d_out,
+                   void *d_ws, void *stream) {
+    if (int rc = check_geom(g)) return rc;
+    PE_CHECK_ARG(n_atoms >= 0 && n_groups >= 0, "pe_sphere_sums: negative size");
+    if (n_atoms == 0 && n_groups == 0) return PE_OK;
+    PE_CHECK_ARG(d_rho && d_xyz && d_radius && d_out && d_ws, "pe_sphere_sums: null pointer");
+    PE_CHECK_ARG(d_group_start || n_groups == n_atoms, "pe_sphere_sums: n_groups must equal n_atoms without group offsets");
+    PE_CHECK_ARG(!(cut_pos < 0.f) && !(cut_neg > 0.f), "pe_sphere_sums: cut_pos must be >= 0 and cut_neg <= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    int32_t *box = (int32_t *)ws;
+    ws += align_up((int64_t)n_atoms * 6 * 4, 256);
+    double *thr = (double *)ws;
+    ws += align_up((int64_t)n_atoms * 8, 256);
+    int32_t *atom_first = (int32_t *)ws;
+    ws += align_up((int64_t)n_atoms * 4, 256);
+    double *partial = (double *)ws;
+    const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
+    if (n_atoms > 0) {
+        sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr);
+        PE_LAUNCH_CHECK();
+    }
+    if (d_group_start == nullptr) {
+        sphere_sums_kernel<false><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, nullptr, cut_pos,
+                                                                        cut_neg, d_out);
+        PE_LAUNCH_CHECK();
+        return PE_OK;
+    }
+    group_first_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, atom_first);
+    if (n_atoms > 0)
+        sphere_sums_kernel<true><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, atom_first,
+                                                                       cut_pos, cut_neg, partial);
+    group_reduce_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, partial, d_out);
+    PE_LAUNCH_CHECK();
+    return PE_OK;
+}
+
+int pe_sphere_count(const pe_geom *g, const float *d_rho, int32_t n_atoms, const double *d_xyz, const float *d_radius,
+                    float cutoff, int32_t *d_count, int32_t *d_box, void *stream) {
+    if (int rc = check_geom(g)) return rc;
+    PE_CHECK_ARG(n_atoms >= 0, "pe_sphere_count: negative size");
+    if (n_atoms == 0) return PE_OK;
+    PE_CHECK_ARG(d_rho && d_xyz && d_radius && d_count, "pe_sphere_count: null pointer");
+    const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
+    sphere_count_kernel<<<blocks, kSphereWarps * 32, 0, (cudaStream_t)stream>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff,
+                                                                                d_count, d_box);
+    PE_LAUNCH_CHECK();
+    return PE_OK;
+}
+
+int pe_sphere_fill(const pe_geom *g, const float *d_rho, int32_t n_atoms, const double *d_xyz, const float *d_radius,
+                   float cutoff, const int64_t *d_offset, int32_t max_box_voxels, int32_t *d_index, float *d_value,
+                   int32_t *d_label, void *stream) {
+    if (int rc = check_geom(g)) return rc;
+    PE_CHECK_ARG(n_atoms >= 0, "pe_sphere_fill: negative size");
+    if (n_atoms == 0) return PE_OK;
+    PE_CHECK_ARG(d_rho && d_xyz && d_radius && d_offset && d_index, "pe_sphere_fill: null pointer");
+    PE_CHECK_ARG(max_box_voxels > 0, "pe_sphere_fill: max_box_voxels must be positive");
+    const bool labels = d_label != nullptr;
+    PE_CHECK_ARG(!labels || max_box_voxels <= 32768, "pe_sphere_fill: cluster labels need boxes of at most 32768 voxels (got %d)",
+                 max_box_voxels);
+    PE_CHECK_ARG(max_box_voxels <= (1 << 19), "pe_sphere_fill: boxes of more than 2^19 voxels are not supported (got %d)",
+                 max_box_voxels);
+    const int nw_max = (max_box_voxels + 31) / 32;
+    const size_t per_warp = (size_t)nw_max * 8 + (labels ? (size_t)((max_box_voxels + 1) / 2 * 2) * 6 : 0);
+    const size_t budget = 200 * 1024;
+    int warps = (int)(budget / per_warp);
+    if (warps > kSphereWarps) warps = kSphereWarps;
+    PE_CHECK_ARG(warps >= 1, "pe_sphere_fill: box of %d voxels needs %zu bytes of shared memory per warp", max_box_voxels,
+                 per_warp);
+    const size_t smem = per_warp * warps;
+    const int blocks = (n_atoms + warps - 1) / warps;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (labels) {
+        PE_CUDA(cudaFuncSetAttribute(sphere_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sphere_fill_kernel<true><<<blocks, warps * 32, smem, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff, d_offset,
+                                                                   max_box_voxels, d_index, d_value, d_label);
+    } else {
+        PE_CUDA(cudaFuncSetAttribute(sphere_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sphere_fill_kernel<false><<<blocks, warps * 32, smem, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff, d_offset,
+                                                                    max_box_voxels, d_index, d_value, d_label);
+    }
+    PE_LAUNCH_CHECK();
+    return PE_OK;
+}
+
+}  // extern "C"
