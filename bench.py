@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- the voxel hot path on BASELINE.json's config 2 (one line of JSON on stdout).
+
+Workload ("config.workload": "C2"): a ~40k-atom synthetic poly-ALA structure (8,000 residues) on a 384^3 P1 map pair
+(cell 192 A, 0.5 A grid).  One step = one pass of the hot path over that structure:
+  cloud   per-atom sphere gather-sums at the atom-type radii (2Fo-Fc, cutoff mean + 1.5 sigma)
+  region  per-residue set-union sphere sums at 3.5 A (2Fo-Fc)
+  blobs   green + red blob lists of the Fo-Fc map at +-(mean + 3 sigma): threshold, 26-connected labelling in the
+          reference's blob order, per-blob sums
+Units: atom-sphere voxels ((atom, voxel) pairs passing the distance test; cloud + region) + blob-CCL voxels (voxels
+of the scanned unique volume).  `value` = units of all ranks / device time of the slowest rank, inputs resident in
+HBM.  `e2e` = the same through the public API with HOST buffers (maps + atoms copied in, results copied out, every
+step).  N > 1: replicas only -- a single structure does not shard; every rank runs its own
+structure, no data-path collective.
+
+--impl reference: the UNMODIFIED reference (oracle/_ref: pdb_eda 2.7.1 + its compiled Cython cutils) on the host
+CPU, one core (its single-structure path is single threaded), on a bounded sample of the same workload (64^3 map,
+same atom density, same three sub-workloads through the reference's public methods).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pdb_eda_b200 import synthetic  # noqa: E402
+
+METRIC = "voxels/s (atom-sphere voxels + blob-CCL voxels per pass of the voxel hot path)"
+UNIT = "voxels/s"
+REGION_RADIUS = 3.5
+FULL = dict(n=384, cell=192.0, residues=8000)
+SAMPLE = dict(n=64, cell=32.0, residues=37)   # same grid spacing and atom density as FULL (1/216 of the volume)
+
+
+def build_workload(spec, seed):
+    """Synthetic structure + (2Fo-Fc, Fo-Fc) volumes + per-atom radii + residue offsets."""
+    n, cell_len = spec["n"], spec["cell"]
+    cell = (cell_len, cell_len, cell_len, 90.0, 90.0, 90.0)
+    st = synthetic.polyAlaStructure(spec["residues"], (0, 0, 0), (cell_len,) * 3, seed=seed, residuesPerChain=1000)
+    fofc2, fofc = synthetic.mapPair(st, (n, n, n), cell, seed=seed + 6)
+    params = synthetic.defaultParams()
+    atoms, radii, res_start = [], [], [0]
+    for residue in st.get_residues():
+        for atom in residue:
+            key = residue.resname + "_" + atom.name
+            atoms.append(atom.coord)
+            radii.append(params["radii"][params["full_atom_name_map_atom_type"][key]])
+        res_start.append(len(atoms))
+    return dict(structure=st, cell=cell, n=n, fofc2=fofc2, fofc=fofc, xyz=np.asarray(atoms, dtype=np.float32),
+                radii=np.asarray(radii, dtype=np.float32), res_start=np.asarray(res_start, dtype=np.int32))
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def load_reference():
+    from oracle import refload
+    if refload.available():
+        return refload.load()
+    return None
+
+
+def reference_step(ref_mods, work):
+    """One pass of the three sub-workloads through the reference's own public methods."""
+    import io
+    ref_ccp4 = ref_mods[0]
+    cell, n = work["cell"], work["n"]
+    dens = ref_ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc2"], cell, (n, n, n))), "bench")
+    diff = ref_ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc"], cell, (n, n, n))), "bench")
+    t0 = time.perf_counter()
+    dcut = dens.meanDensity + 1.5 * dens.stdDensity
+    fcut = diff.meanDensity + 3.0 * diff.stdDensity
+    xyz, radii, rs = work["xyz"], work["radii"], work["res_start"]
+    cloud = [dens.findAberrantBlobs(xyz[i], float(radii[i]), dcut) for i in range(len(xyz))]
+    region = [dens.findAberrantBlobs([xyz[i] for i in range(rs[k], rs[k + 1])], REGION_RADIUS, dcut) for k in range(len(rs) - 1)]
+    green = diff.createFullBlobList(fcut)
+    red = diff.createFullBlobList(-fcut)
+    dt = time.perf_counter() - t0
+    return dt, (len(cloud), len(region), len(green), len(red))
+
+
+def oracle_units(work):
+    """Unit counts of a workload by the CPU oracle (outside any timed region)."""
+    import io
+    from oracle import orc
+    from pdb_eda_b200 import ccp4
+    cell, n = work["cell"], work["n"]
+    dm = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc2"], cell, (n, n, n))), "bench")
+    g = orc.geom(dm.header, dm.origin)
+    xyz = work["xyz"].astype(np.float64)
+    cloud = orc.sphere_sums_batch(g, work["fofc2"], xyz, work["radii"])[:, 0].sum()
+    region = orc.sphere_sums_batch(g, work["fofc2"], xyz, np.full(len(xyz), REGION_RADIUS, np.float32))[:, 0].sum()
+    return float(cloud), float(region), float(n) ** 3
+
+
+def oracle_step(work):
+    """The oracle port of the same pass (used only when oracle/_ref is absent)."""
+    import io
+    from oracle import orc
+    from pdb_eda_b200 import ccp4
+    cell, n = work["cell"], work["n"]
+    dm = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc2"], cell, (n, n, n))), "bench")
+    g = orc.geom(dm.header, dm.origin)
+    xyz = work["xyz"].astype(np.float64)
+    t0 = time.perf_counter()
+    v2 = work["fofc2"].astype(np.float64)
+    v1 = work["fofc"].astype(np.float64)
+    dcut = v2.mean() + 1.5 * v2.std()
+    fcut = v1.mean() + 3.0 * v1.std()
+    orc.sphere_sums_batch(g, work["fofc2"], xyz, work["radii"], dcut)
+    rs = work["res_start"]
+    for k in range(len(rs) - 1):
+        orc.sphere_union_sums(g, work["fofc2"], xyz[rs[k]:rs[k + 1]], np.full(rs[k + 1] - rs[k], REGION_RADIUS, np.float32), dcut, 0.0)
+    orc.full_blobs(g, work["fofc"], fcut)
+    orc.full_blobs(g, work["fofc"], -fcut)
+    return time.perf_counter() - t0, None
+
+
+def run_cpu_sample(steps, warmup):
+    work = build_workload(SAMPLE, seed=2)
+    units = sum(oracle_units(work))
+    ref_mods = load_reference()
+    kind = "reference" if ref_mods is not None else "port"
+    times = []
+    for i in range(warmup + steps):
+        dt, _ = reference_step(ref_mods, work) if ref_mods is not None else oracle_step(work)
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    value = units * len(times) / total
+    sample = ("%d^3 P1 map pair (cell %.0f A), %d atoms / %d residues, same grid spacing and atom density as C2; cloud + region "
+              "(3.5 A) + green/red blobs via DensityMatrix.findAberrantBlobs / createFullBlobList; %d steps, %.1f s/step"
+              % (SAMPLE["n"], SAMPLE["cell"], len(work["xyz"]), SAMPLE["residues"], len(times), total / len(times)))
+    return value, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}, total / len(times) * 1e3
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    value, cpu, ms = run_cpu_sample(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": "C2 (bounded sample: %s)" % cpu["sample"]},
+            "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main_gpu(args, rank, world, local_rank):
+    import io
+    import torch
+    import torch.distributed as dist
+    from pdb_eda_b200 import _device, _lib, ccp4
+    from pdb_eda_b200.pipeline import VoxelPass
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _device.require_cuda()
+
+    work = build_workload(FULL, seed=2 + rank)
+    n, cell = work["n"], work["cell"]
+    hdr_dens = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), cell, (n, n, n)))
+    # pinned host copies of the inputs (what a caller holds after reading the CCP4 / PDB files)
+    h_dens = torch.from_numpy(work["fofc2"].reshape(-1)).pin_memory()
+    h_diff = torch.from_numpy(work["fofc"].reshape(-1)).pin_memory()
+    h_xyz = torch.from_numpy(work["xyz"].astype(np.float64)).pin_memory()
+    geom = _device.geom_from_header(hdr_dens)
+    d_dens = torch.empty(n ** 3, dtype=torch.float32, device=device)
+    d_diff = torch.empty(n ** 3, dtype=torch.float32, device=device)
+    d_dens.copy_(h_dens, non_blocking=True)
+    d_diff.copy_(h_diff, non_blocking=True)
+    dens = _device.DeviceMap(geom, d_dens)
+    diff = _device.DeviceMap(geom, d_diff)
+    vp = VoxelPass(dens, diff, work["xyz"].astype(np.float64), work["radii"], work["res_start"], REGION_RADIUS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- unit counts (outside the timed region)
+    vp.step()
+    torch.cuda.synchronize()
+    res = vp.results()
+    cloud_units = float(res["cloud"][:, 0].sum())
+    region_pairs = float(dens.sphere_sums(vp.xyz, vp.region_radii)[:, 0].sum().item())
+    blob_units = float(vp.n_blob_voxels)
+    units = cloud_units + region_pairs + blob_units
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        vp.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib = _lib.load()
+    launches0 = lib.pe_launch_count()
+    _lib.profile(True, reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        vp.step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.pe_launch_count() - launches0
+    prof = _lib.profile()
+    _lib.profile(False)
+
+    # an un-instrumented repeat (no per-kernel events) for the headline device number
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        vp.step()
+    e1.record()
+    barrier()
+    ms_plain = e0.elapsed_time(e1)
+
+    # ---- end to end through the public API with host buffers
+    def e2e_step():
+        d_dens.copy_(h_dens, non_blocking=True)
+        d_diff.copy_(h_diff, non_blocking=True)
+        vp.xyz.copy_(h_xyz, non_blocking=True)
+        vp.step()
+        return vp.results()
+
+    for _ in range(2):
+        out = e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = h_dens.numel() * 4 + h_diff.numel() * 4 + h_xyz.numel() * 8
+    d2h = (out["cloud"].nbytes + out["region"].nbytes + out["blob_counts"].nbytes +
+           sum(out[t][k].nbytes for t in ("green", "red") for k in ("key", "label", "stats")))
+
+    # ---- max over ranks, sum of units
+    stats = torch.tensor([ms_plain, ms_e2e, ms_total], dtype=torch.float64, device=device)
+    tot_units = torch.tensor([units], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_units, op=dist.ReduceOp.SUM)
+    ms_plain, ms_e2e, ms_total = stats.tolist()
+    all_units = tot_units.item()
+
+    if rank == 0:
+        value = all_units * args.steps / (ms_plain * 1e-3)
+        e2e_value = all_units * args.steps / (ms_e2e * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        n_fg = float(res["blob_counts"][0] + res["blob_counts"][2])
+        n_blob = float(res["blob_counts"][1] + res["blob_counts"][3])
+        region_union = float(res["region"][:, 0].sum())
+        algo = {  # algorithmic bytes per launch
+            "threshold_bitmap_kernel": 4.0 * blob_units,
+            "sphere_sums_kernel": None,  # two launches per step with different byte counts, see below
+        }
+        kernels = []
+        for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            kernels.append({"kernel": name, "launches": count, "ms_total": round(ms, 4), "us_per_launch": round(ms * 1e3 / max(count, 1), 2)})
+        top = kernels[0]["kernel"] if kernels else None
+        per_launch_ms = {k["kernel"]: k["ms_total"] / max(k["launches"], 1) for k in kernels}
+        roof = None
+        if "threshold_bitmap_kernel" in per_launch_ms:
+            t = per_launch_ms["threshold_bitmap_kernel"] * 1e-3
+            ach = algo["threshold_bitmap_kernel"] / t / 1e9
+            roof = {"kernel": "threshold_bitmap_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": algo["threshold_bitmap_kernel"]}
+        sphere = None
+        if "sphere_sums_kernel" in per_launch_ms:
+            # cloud and region launches alternate; bytes = 4 V_in + 52 A for each
+            b = 4.0 * (cloud_units + region_pairs) + 52.0 * 2 * vp.n_atoms
+            t = prof["sphere_sums_kernel"][1] / (prof["sphere_sums_kernel"][0] / 2.0) * 1e-3
+            ach = b / t / 1e9
+            sphere = {"kernel": "sphere_sums_kernel (cloud + region launch pair)", "bound": "hbm", "achieved": round(ach, 1),
+                      "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                      "algorithmic_bytes_per_launch_pair": b,
+                      "note": "gathers hit L2 (map pinned by reuse); the kernel is fp64-issue bound, not HBM bound"}
+        dominant = roof
+        if top and top.startswith("sphere_sums") and sphere is not None:
+            dominant = sphere
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_plain / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2: 384^3 P1 map pair, %d atoms / %d residues per GPU; cloud + region(3.5 A) + green/red blobs"
+                                       % (vp.n_atoms, vp.n_res),
+                           "parallelism": "replicas x%d (single structure does not shard)" % world,
+                           "l2": "inputs larger than L2 (2 x 226 MB maps per pass); no explicit flush"},
+                "units_per_step": {"cloud_atom_sphere_voxels": cloud_units, "region_atom_sphere_voxels": region_pairs,
+                                   "region_union_voxels": region_union, "blob_ccl_voxels": blob_units,
+                                   "foreground_voxels": n_fg, "blobs": n_blob},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": dominant, "roofline_other": [r for r in (roof, sphere) if r is not dominant and r],
+                "kernels": kernels[:12], "ms_per_step_profiled": ms_total / args.steps, "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            _, cpu, _ = run_cpu_sample(1, 0)
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        main_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

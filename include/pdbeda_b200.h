@@ -66,6 +66,16 @@ const char *pe_last_error(void);
 /* Fills sm_count / cc_major / cc_minor of the current device; PE_ERR_NO_DEVICE when there is none. */
 int pe_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
 
+/* Launch accounting.  pe_launch_count: kernels launched by this library since load.  While profiling is enabled
+ * every launch is bracketed by CUDA events on its stream; pe_profile_entries() synchronises, folds them and returns
+ * the number of distinct kernels seen since the last reset; pe_profile_get(i) gives kernel name, launch count and
+ * total device milliseconds.  (No counterpart in the reference; used by bench.py for the roofline line.) */
+long long pe_launch_count(void);
+void pe_profile_enable(int on);
+void pe_profile_reset(void);
+int pe_profile_entries(void);
+int pe_profile_get(int index, const char **name, long long *count, double *total_ms);
+
 /* ---------------------------------------------------------------- map statistics --------------------------- */
 /* DensityMatrix.meanDensity / stdDensity (pdb_eda/ccp4.py:343-363): population mean and standard deviation of
  * all n stored voxels in float64.  d_out[0] = mean, d_out[1] = std.  d_ws: >= pe_stats_workspace_bytes(). */

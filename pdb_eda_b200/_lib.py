@@ -46,6 +46,12 @@ SIGNATURES = {
     "pe_abi_version": (ctypes.c_int, []),
     "pe_last_error": (ctypes.c_char_p, []),
     "pe_device_info": (ctypes.c_int, [ctypes.POINTER(_I32)] * 3),
+    "pe_launch_count": (ctypes.c_longlong, []),
+    "pe_profile_enable": (None, [ctypes.c_int]),
+    "pe_profile_reset": (None, []),
+    "pe_profile_entries": (ctypes.c_int, []),
+    "pe_profile_get": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_longlong),
+                                      ctypes.POINTER(ctypes.c_double)]),
     "pe_stats_workspace_bytes": (_I64, []),
     "pe_map_mean_std": (ctypes.c_int, [_P, _I64, _P, _P, _P]),
     "pe_map_sum_abs": (ctypes.c_int, [_P, _I64, _F32, _P, _P, _P]),
@@ -106,3 +112,24 @@ def require_device():
     sm, major, minor = _I32(0), _I32(0), _I32(0)
     check(lib.pe_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "pe_device_info")
     return sm.value, major.value, minor.value
+
+
+def profile(enable=None, reset=False):
+    """Kernel-level device timing of the library.  ``profile(True)`` / ``profile(False)`` switch it on and off;
+    ``profile()`` returns {kernel name: (launches, total ms)} accumulated since the last reset."""
+    lib = load()
+    if reset:
+        lib.pe_profile_reset()
+    if enable is not None:
+        lib.pe_profile_enable(1 if enable else 0)
+        return None
+    out = {}
+    for i in range(lib.pe_profile_entries()):
+        name, count, ms = ctypes.c_char_p(), ctypes.c_longlong(0), ctypes.c_double(0.0)
+        if lib.pe_profile_get(i, ctypes.byref(name), ctypes.byref(count), ctypes.byref(ms)) == 0:
+            out[name.value.decode()] = (count.value, ms.value)
+    return out
+
+
+def launch_count():
+    return load().pe_launch_count()

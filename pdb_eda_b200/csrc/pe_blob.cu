@@ -349,11 +349,11 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         dim3 grid((p.U0 + kBmpTx * vec - 1) / (kBmpTx * vec), (p.U1 + kBmpTy - 1) / kBmpTy, (p.W + kChunkWords - 1) / kChunkWords);
         PE_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "pe_blob_label: map too large for the launch grid");
         if (vec4)
-            threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos,
-                                                               use_neg, bmp[0], bmp[1]);
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos,
+                                                               use_neg, bmp[0], bmp[1]));
         else
-            threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos,
-                                                               use_neg, bmp[0], bmp[1]);
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos,
+                                                               use_neg, bmp[0], bmp[1]));
         PE_LAUNCH_CHECK();
     }
     const int sg = sparse_grid();
@@ -366,15 +366,15 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         double *stats = d_stats + (int64_t)k * cap_blobs * 8;
         // K2: position of every foreground voxel in the reference's list order
         if (int rc = exclusive_scan_u32(bmp[k], base[k], p.nwords, nullptr, d_nfg, scan_ws, st, true)) return rc;
-        blob_init_kernel<<<sg, kSparseThreads, 0, st>>>(d_rho, NC, NR, p.U1, p.U2, p.W, p.nwords, p.cap, bmp[k], base[k], d_nfg,
-                                                        d_overflow, key, value, parent[k]);
-        blob_merge_kernel<<<sg, kSparseThreads, 0, st>>>(p.U1, p.U2, p.W, p.cap, bmp[k], base[k], d_nfg, key, parent[k]);
-        blob_flatten_kernel<<<sg, kSparseThreads, 0, st>>>(p.cap, d_nfg, parent[k], flag[k]);
+        PE_LAUNCH("blob_init_kernel", st, blob_init_kernel<<<sg, kSparseThreads, 0, st>>>(d_rho, NC, NR, p.U1, p.U2, p.W, p.nwords, p.cap, bmp[k], base[k], d_nfg,
+                                                        d_overflow, key, value, parent[k]));
+        PE_LAUNCH("blob_merge_kernel", st, blob_merge_kernel<<<sg, kSparseThreads, 0, st>>>(p.U1, p.U2, p.W, p.cap, bmp[k], base[k], d_nfg, key, parent[k]));
+        PE_LAUNCH("blob_flatten_kernel", st, blob_flatten_kernel<<<sg, kSparseThreads, 0, st>>>(p.cap, d_nfg, parent[k], flag[k]));
         PE_LAUNCH_CHECK();
         // K6: blob number = rank of its root among roots
         if (int rc = exclusive_scan_u32(flag[k], rank[k], p.cap, d_nfg, d_nblobs, scan_ws, st, false)) return rc;
-        blob_zero_stats_kernel<<<sg, kSparseThreads, 0, st>>>(cap_blobs, d_nblobs, d_overflow, stats);
-        blob_stats_kernel<<<sg, kSparseThreads, 0, st>>>(*g, p.cap, cap_blobs, d_nfg, key, value, parent[k], rank[k], label, stats);
+        PE_LAUNCH("blob_zero_stats_kernel", st, blob_zero_stats_kernel<<<sg, kSparseThreads, 0, st>>>(cap_blobs, d_nblobs, d_overflow, stats));
+        PE_LAUNCH("blob_stats_kernel", st, blob_stats_kernel<<<sg, kSparseThreads, 0, st>>>(*g, p.cap, cap_blobs, d_nfg, key, value, parent[k], rank[k], label, stats));
         PE_LAUNCH_CHECK();
     }
     return PE_OK;

@@ -281,7 +281,7 @@ static int build_table(int64_t n, const int32_t *d_crs, const int32_t *d_group, 
     used = p - ws;
     PE_CUDA(cudaMemsetAsync(t.key, 0xff, cap * 8, st));
     PE_CUDA(cudaMemsetAsync(t.head, 0xff, cap * 4, st));
-    table_insert_kernel<<<grid_for(n), kClThreads, 0, st>>>(n, d_crs, d_group, t, d_bad);
+    PE_LAUNCH("table_insert_kernel", st, table_insert_kernel<<<grid_for(n), kClThreads, 0, st>>>(n, d_crs, d_group, t, d_bad));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -325,12 +325,12 @@ int pe_cluster_crs_grouped(int64_t n, const int32_t *d_crs, const int32_t *d_gro
     ws += align_up(n * 4, 256);
     void *scan_ws = ws;
     const int blocks = grid_for(n);
-    cluster_first_kernel<<<blocks, kClThreads, 0, st>>>(n, d_crs, d_group, t, parent, d_first);
-    cluster_merge_kernel<<<blocks, kClThreads, 0, st>>>(n, d_crs, d_group, t, parent);
-    cluster_flatten_kernel<<<blocks, kClThreads, 0, st>>>(n, parent, flag);
+    PE_LAUNCH("cluster_first_kernel", st, cluster_first_kernel<<<blocks, kClThreads, 0, st>>>(n, d_crs, d_group, t, parent, d_first));
+    PE_LAUNCH("cluster_merge_kernel", st, cluster_merge_kernel<<<blocks, kClThreads, 0, st>>>(n, d_crs, d_group, t, parent));
+    PE_LAUNCH("cluster_flatten_kernel", st, cluster_flatten_kernel<<<blocks, kClThreads, 0, st>>>(n, parent, flag));
     PE_LAUNCH_CHECK();
     if (int rc = exclusive_scan_u32(flag, rank, n, nullptr, d_nclusters, scan_ws, st, false)) return rc;
-    cluster_label_kernel<<<blocks, kClThreads, 0, st>>>(n, parent, rank, d_label);
+    PE_LAUNCH("cluster_label_kernel", st, cluster_label_kernel<<<blocks, kClThreads, 0, st>>>(n, parent, rank, d_label));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -349,7 +349,7 @@ int pe_crs_stats(const pe_geom *g, const float *d_rho, int64_t n, const int32_t 
     PE_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)n_clusters * 8 * sizeof(double), st));
     if (n == 0) return PE_OK;
     PE_CHECK_ARG(d_rho && d_crs, "pe_crs_stats: null pointer");
-    crs_stats_kernel<<<grid_for(n), kClThreads, 0, st>>>(*g, d_rho, n, d_crs, d_label, d_take, n_clusters, d_stats);
+    PE_LAUNCH("crs_stats_kernel", st, crs_stats_kernel<<<grid_for(n), kClThreads, 0, st>>>(*g, d_rho, n, d_crs, d_label, d_take, n_clusters, d_stats));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -377,8 +377,8 @@ int pe_overlap_pairs(int64_t n, const int32_t *d_crs, const int32_t *d_owner, co
     const int plog = table_log2cap(cap_pairs);
     unsigned long long *pair_set = (unsigned long long *)ws;
     PE_CUDA(cudaMemsetAsync(pair_set, 0xff, (size_t)(1ll << plog) * 8, st));
-    overlap_pairs_kernel<<<grid_for(n), kClThreads, 0, st>>>(n, d_crs, d_owner, d_group, t, pair_set, plog, cap_pairs,
-                                                             (unsigned long long *)d_npairs, d_pairs);
+    PE_LAUNCH("overlap_pairs_kernel", st, overlap_pairs_kernel<<<grid_for(n), kClThreads, 0, st>>>(n, d_crs, d_owner, d_group, t, pair_set, plog, cap_pairs,
+                                                             (unsigned long long *)d_npairs, d_pairs));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }

@@ -41,6 +41,21 @@ void set_error(const char *fmt, ...);
         }                                                                                     \
     } while (0)
 
+// Every kernel launch goes through PE_LAUNCH: it counts the launch (pe_launch_count) and, while profiling is enabled
+// (pe_profile_enable), brackets it with CUDA events on the launching stream so that bench.py can report per-kernel
+// device times measured inside its timed region.
+struct ProfScope {
+    int slot;
+    cudaStream_t stream;
+    ProfScope(const char *tag, cudaStream_t st);
+    ~ProfScope();
+};
+#define PE_LAUNCH(tag, stream, ...)                          \
+    do {                                                     \
+        pe::ProfScope prof_scope__(tag, (cudaStream_t)(stream)); \
+        __VA_ARGS__;                                         \
+    } while (0)
+
 int sm_count();  // cached SM count of the current device (148 on B200)
 int check_geom(const pe_geom *g);  // host-side validation shared by the entry points (pe_map.cu)
 

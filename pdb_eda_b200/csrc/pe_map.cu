@@ -168,10 +168,10 @@ int pe_map_mean_std(const float *d_rho, int64_t n, double *d_out, void *d_ws, vo
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)d_ws;
     const int nb = red_blocks();
-    reduce_partial<RED_SUM><<<nb, kRedThreads, 0, st>>>(d_rho, n, nullptr, 0.f, partial);
-    reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 0, d_out);
-    reduce_partial<RED_SQDEV><<<nb, kRedThreads, 0, st>>>(d_rho, n, d_out, 0.f, partial);
-    reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 1, d_out);
+    PE_LAUNCH("reduce_partial", st, reduce_partial<RED_SUM><<<nb, kRedThreads, 0, st>>>(d_rho, n, nullptr, 0.f, partial));
+    PE_LAUNCH("reduce_final", st, reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 0, d_out));
+    PE_LAUNCH("reduce_partial", st, reduce_partial<RED_SQDEV><<<nb, kRedThreads, 0, st>>>(d_rho, n, d_out, 0.f, partial));
+    PE_LAUNCH("reduce_final", st, reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 1, d_out));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -181,8 +181,8 @@ int pe_map_sum_abs(const float *d_rho, int64_t n, float cutoff, double *d_out, v
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)d_ws;
     const int nb = red_blocks();
-    reduce_partial<RED_ABS_ABOVE><<<nb, kRedThreads, 0, st>>>(d_rho, n, nullptr, cutoff, partial);
-    reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 2, d_out);
+    PE_LAUNCH("reduce_partial", st, reduce_partial<RED_ABS_ABOVE><<<nb, kRedThreads, 0, st>>>(d_rho, n, nullptr, cutoff, partial));
+    PE_LAUNCH("reduce_final", st, reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 2, d_out));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -192,8 +192,8 @@ int pe_sum_abs_f64(const double *d_values, int64_t n, float cutoff, double *d_ou
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)d_ws;
     const int nb = red_blocks();
-    reduce_abs_f64<<<nb, kRedThreads, 0, st>>>(d_values, n, cutoff, partial);
-    reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 2, d_out);
+    PE_LAUNCH("reduce_abs_f64", st, reduce_abs_f64<<<nb, kRedThreads, 0, st>>>(d_values, n, cutoff, partial));
+    PE_LAUNCH("reduce_final", st, reduce_final<<<1, kRedThreads, 0, st>>>(partial, nb, n, 2, d_out));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -204,8 +204,8 @@ int pe_point_density(const pe_geom *g, const float *d_rho, int64_t n, const int3
     PE_CHECK_ARG(n >= 0 && (n == 0 || (d_rho && d_crs)), "pe_point_density: null pointer");
     if (n == 0) return PE_OK;
     const int threads = 256;
-    point_density_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        *g, d_rho, n, d_crs, d_rho_out, d_valid);
+    PE_LAUNCH("point_density_kernel", (cudaStream_t)stream, point_density_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        *g, d_rho, n, d_crs, d_rho_out, d_valid));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -215,7 +215,7 @@ int pe_xyz2crs(const pe_geom *g, int64_t n, const double *d_xyz, int32_t *d_crs,
     PE_CHECK_ARG(n >= 0 && (n == 0 || (d_xyz && d_crs)), "pe_xyz2crs: null pointer");
     if (n == 0) return PE_OK;
     const int threads = 256;
-    xyz2crs_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*g, n, d_xyz, d_crs);
+    PE_LAUNCH("xyz2crs_kernel", (cudaStream_t)stream, xyz2crs_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*g, n, d_xyz, d_crs));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -225,7 +225,7 @@ int pe_crs2xyz(const pe_geom *g, int64_t n, const int32_t *d_crs, double *d_xyz,
     PE_CHECK_ARG(n >= 0 && (n == 0 || (d_xyz && d_crs)), "pe_crs2xyz: null pointer");
     if (n == 0) return PE_OK;
     const int threads = 256;
-    crs2xyz_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*g, n, d_crs, d_xyz);
+    PE_LAUNCH("crs2xyz_kernel", (cudaStream_t)stream, crs2xyz_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(*g, n, d_crs, d_xyz));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }

@@ -1,6 +1,9 @@
 // pe_scan.cu -- error state, device info and the exclusive prefix sum used by the compaction steps.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include "pe_common.cuh"
 
 namespace pe {
@@ -12,6 +15,67 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------ launch accounting
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_profiling{0};
+struct ProfEvent {
+    const char *tag;
+    cudaEvent_t start, stop;
+};
+static std::mutex g_prof_mutex;
+static std::vector<ProfEvent> g_prof_events;   // recorded, not yet folded
+static std::vector<ProfEvent> g_prof_free;     // reusable event pairs
+struct ProfTotal {
+    const char *tag;
+    long long count;
+    double ms;
+};
+static std::vector<ProfTotal> g_prof_totals;
+
+ProfScope::ProfScope(const char *tag, cudaStream_t st) : slot(-1), stream(st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_profiling.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    ProfEvent ev;
+    if (!g_prof_free.empty()) {
+        ev = g_prof_free.back();
+        g_prof_free.pop_back();
+    } else {
+        if (cudaEventCreate(&ev.start) != cudaSuccess || cudaEventCreate(&ev.stop) != cudaSuccess) return;
+    }
+    ev.tag = tag;
+    cudaEventRecord(ev.start, st);
+    g_prof_events.push_back(ev);
+    slot = (int)g_prof_events.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (slot < (int)g_prof_events.size()) cudaEventRecord(g_prof_events[slot].stop, stream);
+}
+
+// Folds all recorded event pairs into the per-tag totals (synchronises on each stop event).
+static void prof_fold() {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (ProfEvent &ev : g_prof_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.stop) == cudaSuccess && cudaEventElapsedTime(&ms, ev.start, ev.stop) == cudaSuccess) {
+            bool found = false;
+            for (ProfTotal &t : g_prof_totals)
+                if (strcmp(t.tag, ev.tag) == 0) {
+                    t.count += 1;
+                    t.ms += ms;
+                    found = true;
+                    break;
+                }
+            if (!found) g_prof_totals.push_back({ev.tag, 1, (double)ms});
+        }
+        g_prof_free.push_back(ev);
+    }
+    g_prof_events.clear();
 }
 
 int sm_count() {
@@ -165,13 +229,13 @@ int exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t capacity, 
     const int nblocks = (int)nblocks64;
     uint32_t *block_sums = (uint32_t *)d_block_ws;
     if (popcount_input) {
-        scan_tile_sums<true><<<nblocks, kScanThreads, 0, stream>>>(d_in, capacity, d_n, block_sums);
-        scan_block_offsets<<<1, 1024, 0, stream>>>(block_sums, nblocks, d_total);
-        scan_apply<true><<<nblocks, kScanThreads, 0, stream>>>(d_in, d_out, capacity, d_n, block_sums);
+        PE_LAUNCH("scan_tile_sums", stream, scan_tile_sums<true><<<nblocks, kScanThreads, 0, stream>>>(d_in, capacity, d_n, block_sums));
+        PE_LAUNCH("scan_block_offsets", stream, scan_block_offsets<<<1, 1024, 0, stream>>>(block_sums, nblocks, d_total));
+        PE_LAUNCH("scan_apply", stream, scan_apply<true><<<nblocks, kScanThreads, 0, stream>>>(d_in, d_out, capacity, d_n, block_sums));
     } else {
-        scan_tile_sums<false><<<nblocks, kScanThreads, 0, stream>>>(d_in, capacity, d_n, block_sums);
-        scan_block_offsets<<<1, 1024, 0, stream>>>(block_sums, nblocks, d_total);
-        scan_apply<false><<<nblocks, kScanThreads, 0, stream>>>(d_in, d_out, capacity, d_n, block_sums);
+        PE_LAUNCH("scan_tile_sums", stream, scan_tile_sums<false><<<nblocks, kScanThreads, 0, stream>>>(d_in, capacity, d_n, block_sums));
+        PE_LAUNCH("scan_block_offsets", stream, scan_block_offsets<<<1, 1024, 0, stream>>>(block_sums, nblocks, d_total));
+        PE_LAUNCH("scan_apply", stream, scan_apply<false><<<nblocks, kScanThreads, 0, stream>>>(d_in, d_out, capacity, d_n, block_sums));
     }
     PE_LAUNCH_CHECK();
     return PE_OK;
@@ -184,6 +248,34 @@ extern "C" {
 int pe_abi_version(void) { return PE_ABI_VERSION; }
 
 const char *pe_last_error(void) { return pe::g_error; }
+
+long long pe_launch_count(void) { return pe::g_launches.load(); }
+
+void pe_profile_enable(int on) {
+    pe::prof_fold();
+    pe::g_profiling.store(on ? 1 : 0);
+}
+
+void pe_profile_reset(void) {
+    pe::prof_fold();
+    std::lock_guard<std::mutex> lock(pe::g_prof_mutex);
+    pe::g_prof_totals.clear();
+}
+
+int pe_profile_entries(void) {
+    pe::prof_fold();
+    std::lock_guard<std::mutex> lock(pe::g_prof_mutex);
+    return (int)pe::g_prof_totals.size();
+}
+
+int pe_profile_get(int index, const char **name, long long *count, double *total_ms) {
+    std::lock_guard<std::mutex> lock(pe::g_prof_mutex);
+    if (index < 0 || index >= (int)pe::g_prof_totals.size()) return PE_ERR_ARG;
+    if (name) *name = pe::g_prof_totals[index].tag;
+    if (count) *count = pe::g_prof_totals[index].count;
+    if (total_ms) *total_ms = pe::g_prof_totals[index].ms;
+    return PE_OK;
+}
 
 int pe_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
     int dev = 0, ndev = 0;

@@ -521,20 +521,20 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     double *partial = (double *)ws;
     const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
     if (n_atoms > 0) {
-        sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr);
+        PE_LAUNCH("sphere_params_kernel", st, sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr));
         PE_LAUNCH_CHECK();
     }
     if (d_group_start == nullptr) {
-        sphere_sums_kernel<false><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, nullptr, cut_pos,
-                                                                        cut_neg, d_out);
+        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<false><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, nullptr, cut_pos,
+                                                                        cut_neg, d_out));
         PE_LAUNCH_CHECK();
         return PE_OK;
     }
-    group_first_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, atom_first);
+    PE_LAUNCH("group_first_kernel", st, group_first_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, atom_first));
     if (n_atoms > 0)
-        sphere_sums_kernel<true><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, atom_first,
-                                                                       cut_pos, cut_neg, partial);
-    group_reduce_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, partial, d_out);
+        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<true><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, atom_first,
+                                                                       cut_pos, cut_neg, partial));
+    PE_LAUNCH("group_reduce_kernel", st, group_reduce_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, partial, d_out));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -546,8 +546,8 @@ int pe_sphere_count(const pe_geom *g, const float *d_rho, int32_t n_atoms, const
     if (n_atoms == 0) return PE_OK;
     PE_CHECK_ARG(d_rho && d_xyz && d_radius && d_count, "pe_sphere_count: null pointer");
     const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
-    sphere_count_kernel<<<blocks, kSphereWarps * 32, 0, (cudaStream_t)stream>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff,
-                                                                                d_count, d_box);
+    PE_LAUNCH("sphere_count_kernel", (cudaStream_t)stream, sphere_count_kernel<<<blocks, kSphereWarps * 32, 0, (cudaStream_t)stream>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff,
+                                                                                d_count, d_box));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }
@@ -577,12 +577,12 @@ int pe_sphere_fill(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (labels) {
         PE_CUDA(cudaFuncSetAttribute(sphere_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sphere_fill_kernel<true><<<blocks, warps * 32, smem, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff, d_offset,
-                                                                   max_box_voxels, d_index, d_value, d_label);
+        PE_LAUNCH("sphere_fill_kernel", st, sphere_fill_kernel<true><<<blocks, warps * 32, smem, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff, d_offset,
+                                                                   max_box_voxels, d_index, d_value, d_label));
     } else {
         PE_CUDA(cudaFuncSetAttribute(sphere_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sphere_fill_kernel<false><<<blocks, warps * 32, smem, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff, d_offset,
-                                                                    max_box_voxels, d_index, d_value, d_label);
+        PE_LAUNCH("sphere_fill_kernel", st, sphere_fill_kernel<false><<<blocks, warps * 32, smem, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius, cutoff, d_offset,
+                                                                    max_box_voxels, d_index, d_value, d_label));
     }
     PE_LAUNCH_CHECK();
     return PE_OK;

@@ -194,13 +194,13 @@ int pe_symmetry_expand(const pe_geom *g, int32_t n_atoms, const double *d_xyz, i
     int64_t blocks64 = (total + kSymThreads - 1) / kSymThreads;
     const int64_t max_blocks = (int64_t)sm_count() * 16;
     const int blocks = (int)(blocks64 < max_blocks ? blocks64 : max_blocks);
-    sym_flag_kernel<<<blocks, kSymThreads, 0, st>>>(*g, d_xyz, d_rot, d_shift, n_ops, n_atoms, total, lo[0], lo[1], lo[2], hi[0],
-                                                    hi[1], hi[2], flag);
+    PE_LAUNCH("sym_flag_kernel", st, sym_flag_kernel<<<blocks, kSymThreads, 0, st>>>(*g, d_xyz, d_rot, d_shift, n_ops, n_atoms, total, lo[0], lo[1], lo[2], hi[0],
+                                                    hi[1], hi[2], flag));
     PE_LAUNCH_CHECK();
     if (int rc = exclusive_scan_u32(flag, pos, total, nullptr, d_count, scan_ws, st, false)) return rc;
     if (cap > 0) {
-        sym_scatter_kernel<<<blocks, kSymThreads, 0, st>>>(*g, d_xyz, d_rot, d_shift, n_ops, n_atoms, total, lo[0], lo[1], lo[2],
-                                                           hi[0], hi[1], hi[2], flag, pos, cap, d_atom, d_image, d_out_xyz);
+        PE_LAUNCH("sym_scatter_kernel", st, sym_scatter_kernel<<<blocks, kSymThreads, 0, st>>>(*g, d_xyz, d_rot, d_shift, n_ops, n_atoms, total, lo[0], lo[1], lo[2],
+                                                           hi[0], hi[1], hi[2], flag, pos, cap, d_atom, d_image, d_out_xyz));
         PE_LAUNCH_CHECK();
     }
     return PE_OK;
@@ -215,8 +215,8 @@ int pe_nearest_atom(int64_t n_blobs, const double *d_centroid, int64_t n_atoms, 
     PE_CHECK_ARG(d_centroid && d_coords && d_idx && d_dist, "pe_nearest_atom: null pointer");
     const int64_t blocks = (n_blobs + kNearBlobs - 1) / kNearBlobs;
     PE_CHECK_ARG(blocks < (1ll << 31), "pe_nearest_atom: too many blobs");
-    nearest_kernel<<<(unsigned)blocks, kNearThreads, 0, (cudaStream_t)stream>>>(n_blobs, d_centroid, n_atoms, d_coords, d_idx,
-                                                                                d_dist);
+    PE_LAUNCH("nearest_kernel", (cudaStream_t)stream, nearest_kernel<<<(unsigned)blocks, kNearThreads, 0, (cudaStream_t)stream>>>(n_blobs, d_centroid, n_atoms, d_coords, d_idx,
+                                                                                d_dist));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }

@@ -62,15 +62,22 @@ def cartesianOperators(spaceGroup, cell):
     return ops
 
 
+def ccp4Header(ncrs, cell, intervals, crsStart=(0, 0, 0), axisOrder=(1, 2, 3), spaceGroupNumber=1, stats=(0.0, 0.0, 0.0, 0.0)):
+    """The 1,024 header bytes of a little-endian mode-2 CCP4 file (format string of pdb_eda/ccp4.py:149).
+    ``ncrs`` = (columns, rows, sections); ``stats`` = (min, max, mean, rms)."""
+    header = struct.pack("<10i6f3i3f3i27f4cifi", ncrs[0], ncrs[1], ncrs[2], 2, crsStart[0], crsStart[1], crsStart[2],
+                         intervals[0], intervals[1], intervals[2], *[float(x) for x in cell], axisOrder[0], axisOrder[1],
+                         axisOrder[2], float(stats[0]), float(stats[1]), float(stats[2]), spaceGroupNumber, 0, 0,
+                         *([0.0] * 27), b"M", b"A", b"P", b" ", 0x00004144, float(stats[3]), 0)
+    return header + b" " * 800
+
+
 def ccp4Bytes(values, cell, intervals, crsStart=(0, 0, 0), axisOrder=(1, 2, 3), spaceGroupNumber=1):
     """A complete little-endian mode-2 CCP4 file.  ``values``: float32 array [section][row][column]."""
     values = np.ascontiguousarray(values, dtype="<f4")
     ns, nr, nc = values.shape
-    header = struct.pack("<10i6f3i3f3i27f4cifi", nc, nr, ns, 2, crsStart[0], crsStart[1], crsStart[2], intervals[0],
-                         intervals[1], intervals[2], *[float(x) for x in cell], axisOrder[0], axisOrder[1], axisOrder[2],
-                         float(values.min()), float(values.max()), float(values.mean()), spaceGroupNumber, 0, 0,
-                         *([0.0] * 27), b"M", b"A", b"P", b" ", 0x00004144, float(values.std()), 0)
-    return header + b" " * 800 + values.tobytes()
+    stats = (values.min(), values.max(), values.mean(), values.std())
+    return ccp4Header((nc, nr, ns), cell, intervals, crsStart, axisOrder, spaceGroupNumber, stats) + values.tobytes()
 
 
 def ccp4Handle(values, cell, intervals, **kw):
