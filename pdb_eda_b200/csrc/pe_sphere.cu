@@ -20,6 +20,7 @@
 //   * warp-shuffle reductions in a fixed order make the float64 sums run-to-run deterministic.
 // Skewed cells (and boxes wider than kDMax) take a generic path that evaluates the reference's 3x3 mat-vec per
 // candidate in the host BLAS's accumulation order.
+#include <limits.h>
 #include "pe_common.cuh"
 
 namespace pe {
@@ -126,12 +127,10 @@ struct SphereAcc {
 
 // ------------------------------------------------------------------------------------------------ sums kernel
 // CASEB: the column axis carries z (the last term of the reference's sum), so fl(X2 + Y2) depends on (row, section).
-template <bool CASEB, bool GROUPED>
+template <bool CASEB>
 __device__ __forceinline__ void sums_ortho(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
                                            double ay, double az, double T, const AxisTab *tab, int lane, float cp,
-                                           float cn, int gfirst, int self, const int32_t *__restrict__ box,
-                                           const double *__restrict__ thr, const double *__restrict__ xyz,
-                                           SphereAcc &acc) {
+                                           float cn, SphereAcc &acc) {
     // inner axis = the crs axis that carries z when that is the row or section axis; else sections.
     const int inner = CASEB ? 2 : g.map2xyz[2];       // 1 (rows) or 2 (sections)
     const int outer = 3 - inner;
@@ -163,13 +162,6 @@ __device__ __forceinline__ void sums_ortho(const pe_geom &g, const float *__rest
                 const bool ok = (offco | offi) >= 0;
                 float v = 0.f;
                 if (inside && ok) v = __ldg(rho + (int)((unsigned)sumco + (unsigned)offi));
-                if (GROUPED) {
-                    if (inside && gfirst < self) {
-                        const int r = b.lo[1] + (inner == 1 ? ki : ko);
-                        const int s = b.lo[2] + (inner == 2 ? ki : ko);
-                        if (claimed_by_earlier(g, gfirst, self, box, thr, xyz, c, r, s)) inside = false;
-                    }
-                }
                 acc.bad |= (inside && !ok) ? 1 : 0;
                 acc.add(inside, v, cp, cn);
             }
@@ -177,11 +169,8 @@ __device__ __forceinline__ void sums_ortho(const pe_geom &g, const float *__rest
     }
 }
 
-template <bool GROUPED>
 __device__ __forceinline__ void sums_generic(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
-                                             double ay, double az, double T, int lane, float cp, float cn, int gfirst,
-                                             int self, const int32_t *__restrict__ box, const double *__restrict__ thr,
-                                             const double *__restrict__ xyz, SphereAcc &acc) {
+                                             double ay, double az, double T, int lane, float cp, float cn, SphereAcc &acc) {
     const int D0 = b.dim[0], D1 = b.dim[1], D2 = b.dim[2];
     const int64_t vol = (int64_t)D0 * D1 * D2;
     for (int64_t m = lane; m < vol; m += 32) {
@@ -196,20 +185,15 @@ __device__ __forceinline__ void sums_generic(const pe_geom &g, const float *__re
         const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
         const bool ok = (oc | orr | os) >= 0;
         const float v = ok ? __ldg(rho + (oc + orr + os)) : 0.f;
-        if (GROUPED) {
-            if (gfirst < self && claimed_by_earlier(g, gfirst, self, box, thr, xyz, c, r, s)) inside = false;
-        }
         acc.bad |= (inside && !ok) ? 1 : 0;
         acc.add(inside, v, cp, cn);
     }
 }
 
-template <bool GROUPED>
 __global__ void __launch_bounds__(kSphereWarps * 32)
     sphere_sums_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
                        const double *__restrict__ xyz, const int32_t *__restrict__ box, const double *__restrict__ thr,
-                       const int32_t *__restrict__ atom_first /* first atom of the atom's group (GROUPED) */, float cp,
-                       float cn, double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
+                       float cp, float cn, double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
     __shared__ AxisTab tabs[kSphereWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a = blockIdx.x * kSphereWarps + warp;
@@ -222,17 +206,16 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     }
     const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
     const double T = thr[a];
-    const int gfirst = GROUPED ? atom_first[a] : a;
     SphereAcc acc;
     const bool tabulated = g.orthogonal && b.dim[0] <= kDMax * 32 && b.dim[1] <= kDMax && b.dim[2] <= kDMax;
     if (tabulated) {
         fill_tables(g, b, ax, ay, az, tabs[warp], lane);
         if (g.map2xyz[2] == 0)
-            sums_ortho<true, GROUPED>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, gfirst, a, box, thr, xyz, acc);
+            sums_ortho<true>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, acc);
         else
-            sums_ortho<false, GROUPED>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, gfirst, a, box, thr, xyz, acc);
+            sums_ortho<false>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, acc);
     } else {
-        sums_generic<GROUPED>(g, rho, b, ax, ay, az, T, lane, cp, cn, gfirst, a, box, thr, xyz, acc);
+        sums_generic(g, rho, b, ax, ay, az, T, lane, cp, cn, acc);
     }
     const int n_all = warp_sum(acc.n_all), n_pos = warp_sum(acc.n_pos), n_neg = warp_sum(acc.n_neg);
     const int bad = warp_sum(acc.bad);
@@ -250,34 +233,199 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     }
 }
 
-__global__ void group_first_kernel(int n_groups, const int32_t *__restrict__ group_start, int32_t *__restrict__ atom_first) {
-    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gidx >= n_groups) return;
-    const int s = group_start[gidx], e = group_start[gidx + 1];
-    for (int a = s; a < e; ++a) atom_first[a] = s;
-}
+// ------------------------------------------------------------------------------------------------ union kernel
+// Set-union of the spheres of one group of atoms (getSphereCrsFromXyzList, pdb_eda/cutils.pyx:250-271; the region
+// density / discrepancy sums of pdb_eda/densityAnalysis.py:1037-1068, :1160-1211).  One CTA per group.  A voxel
+// must be counted once however many spheres hold it: the group's bounding box is kept as a bitmap in shared memory
+// (one 64-bit word per (row, section), one bit per column) and every in-sphere voxel is claimed with one atomicOr
+// per box row -- the returned old word tells each lane whether an earlier atom already owns its voxel.  The CTA
+// walks the group's atoms one after another (all warps share an atom's box rows), so claims, and with them the
+// float64 summation order, are deterministic.
+constexpr int kUnionWarps = 4;
+constexpr int kUnionMaxRows = 2304;  // (row, section) pairs of the union bounding box that fit the shared bitmap
 
-// Per-group totals from the per-atom partials, in atom order (deterministic).
-__global__ void group_reduce_kernel(int n_groups, const int32_t *__restrict__ group_start,
-                                    const double *__restrict__ partial, double *__restrict__ out) {
-    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gidx >= n_groups) return;
-    double acc[PE_SPHERE_NOUT];
-#pragma unroll
-    for (int k = 0; k < PE_SPHERE_NOUT; ++k) acc[k] = 0.0;
-    acc[6] = 1.0;
-    for (int a = group_start[gidx]; a < group_start[gidx + 1]; ++a) {
-        const double *p = partial + (int64_t)a * PE_SPHERE_NOUT;
-#pragma unroll
-        for (int k = 0; k < PE_SPHERE_NOUT; ++k) {
-            if (k == 6)
-                acc[k] = (p[k] != 0.0 && acc[k] != 0.0) ? 1.0 : 0.0;
-            else
-                acc[k] += p[k];
+template <bool CASEB>
+__device__ __forceinline__ void union_pass_tab(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
+                                               double ay, double az, double T, const AxisTab *tab, int warp, int lane,
+                                               float cp, float cn, int ulo0, int ulo1, int ulo2, int U2,
+                                               unsigned long long *bitmap, SphereAcc &acc) {
+    const int inner = CASEB ? 2 : g.map2xyz[2];
+    const int outer = 3 - inner;
+    const AxisTab &ti = tab[inner - 1];
+    const AxisTab &to = tab[outer - 1];
+    const int Di = sel3(b.dim[0], b.dim[1], b.dim[2], inner), Do = sel3(b.dim[0], b.dim[1], b.dim[2], outer), D0 = b.dim[0];
+    int d0p = 1;
+    while (d0p < D0 && d0p < 32) d0p <<= 1;
+    const int rpi = 32 / d0p;
+    const int lrow = lane / d0p, lc = lane % d0p;
+    const unsigned rowmask = d0p == 32 ? 0xffffffffu : ((1u << d0p) - 1u);
+    for (int cbase = 0; cbase < D0; cbase += 32) {
+        const int ic = cbase + lc;
+        const bool act = ic < D0;
+        const int c = b.lo[0] + ic;
+        const double sqc = act ? axis_sq(g, 0, c, ax, ay, az) : 0.0;
+        const int offc = act ? axis_off(g, 0, c) : kInvalidOff;
+        const int shift = b.lo[0] - ulo0 + cbase;
+        for (int ko0 = warp * rpi; ko0 < Do; ko0 += kUnionWarps * rpi) {
+            const int ko = ko0 + lrow;
+            const bool rowact = act && ko < Do;
+            const double sqo = rowact ? to.sq[ko] : 0.0;
+            const int offo = rowact ? to.off[ko] : kInvalidOff;
+            const double P = __dadd_rn(sqc, sqo);
+            const int offco = offc | offo;
+            const int sumco = (int)((unsigned)offc + (unsigned)offo);
+#pragma unroll 2
+            for (int ki = 0; ki < Di; ++ki) {
+                const double sqi = ti.sq[ki];
+                const int offi = ti.off[ki];
+                const double d2 = CASEB ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
+                const bool inside = rowact && (d2 <= T);
+                const unsigned m = __ballot_sync(kFull, inside);
+                if (m == 0u) continue;  // warp-uniform
+                const unsigned mine = (m >> (lrow * d0p)) & rowmask;
+                unsigned long long old = 0ull;
+                if (lc == 0 && mine) {
+                    const int r = b.lo[1] + (inner == 1 ? ki : ko), s = b.lo[2] + (inner == 2 ? ki : ko);
+                    old = atomicOr(bitmap + ((r - ulo1) * U2 + (s - ulo2)), (unsigned long long)mine << shift);
+                }
+                old = __shfl_sync(kFull, old, lrow * d0p);
+                const bool ok = (offco | offi) >= 0;
+                const bool claim = inside && !((old >> (shift + lc)) & 1ull);
+                float v = 0.f;
+                if (claim && ok) v = __ldg(rho + (int)((unsigned)sumco + (unsigned)offi));
+                acc.bad |= (inside && !ok) ? 1 : 0;
+                acc.add(claim, v, cp, cn);
+            }
         }
     }
+}
+
+// Generic pass (skewed cells, very wide boxes): exact per-candidate geometry; claims through the bitmap when the
+// group's box fits it, else by testing the earlier atoms of the group.
+__device__ __forceinline__ void union_pass_generic(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
+                                                   double ay, double az, double T, int tid, int nthreads, float cp, float cn,
+                                                   bool fits, int ulo0, int ulo1, int ulo2, int U2, unsigned long long *bitmap,
+                                                   int gfirst, int self, const int32_t *__restrict__ box,
+                                                   const double *__restrict__ thr, const double *__restrict__ xyz,
+                                                   SphereAcc &acc) {
+    const int D0 = b.dim[0], D1 = b.dim[1], D2 = b.dim[2];
+    const int64_t vol = (int64_t)D0 * D1 * D2;
+    for (int64_t m = tid; m < vol; m += nthreads) {
+        const int ic = (int)(m % D0);
+        const int64_t t = m / D0;
+        const int ir = (int)(t % D1), is = (int)(t / D1);
+        const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+        double vx, vy, vz;
+        crs2xyz(g, c, r, s, vx, vy, vz);
+        if (!(dist2(ax, ay, az, vx, vy, vz) <= T)) continue;
+        const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
+        const bool ok = (oc | orr | os) >= 0;
+        acc.bad |= ok ? 0 : 1;
+        bool claim;
+        if (fits) {
+            const unsigned long long bit = 1ull << (c - ulo0);
+            claim = !(atomicOr(bitmap + ((r - ulo1) * U2 + (s - ulo2)), bit) & bit);
+        } else {
+            claim = !(gfirst < self && claimed_by_earlier(g, gfirst, self, box, thr, xyz, c, r, s));
+        }
+        const float v = (claim && ok) ? __ldg(rho + (oc + orr + os)) : 0.f;
+        acc.add(claim, v, cp, cn);
+    }
+}
+
+template <bool CASEB>
+__global__ void __launch_bounds__(kUnionWarps * 32)
+    sphere_union_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_groups,
+                        const int32_t *__restrict__ group_start, const double *__restrict__ xyz,
+                        const int32_t *__restrict__ box, const double *__restrict__ thr, float cp, float cn,
+                        double *__restrict__ out /* n_groups x PE_SPHERE_NOUT */) {
+    __shared__ unsigned long long bitmap[kUnionMaxRows];
+    __shared__ AxisTab tabs[2];
+    __shared__ double red_d[kUnionWarps][3];
+    __shared__ int red_i[kUnionWarps][4];
+    const int grp = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a0 = group_start[grp], a1 = group_start[grp + 1];
+    // the group's bounding box and whether the tabulated path applies to every atom
+    int ulo0 = INT_MAX, ulo1 = INT_MAX, ulo2 = INT_MAX, uhi0 = INT_MIN, uhi1 = INT_MIN, uhi2 = INT_MIN;
+    bool tab = g.orthogonal != 0;
+    double candidates = 0.0;
+    for (int a = a0; a < a1; ++a) {
+        const int32_t *bx = box + 6 * a;
+        const int d0 = bx[3], d1 = bx[4], d2 = bx[5];
+        candidates += (double)d0 * (double)d1 * (double)d2;
+        if (d0 <= 0 || d1 <= 0 || d2 <= 0) continue;
+        ulo0 = min(ulo0, bx[0]);
+        ulo1 = min(ulo1, bx[1]);
+        ulo2 = min(ulo2, bx[2]);
+        uhi0 = max(uhi0, bx[0] + d0);
+        uhi1 = max(uhi1, bx[1] + d1);
+        uhi2 = max(uhi2, bx[2] + d2);
+        tab = tab && d1 <= kDMax && d2 <= kDMax;
+    }
+    const bool any = uhi0 > ulo0;
+    const int U0 = any ? uhi0 - ulo0 : 0, U1 = any ? uhi1 - ulo1 : 0, U2 = any ? uhi2 - ulo2 : 0;
+    const bool fits = any && U0 <= 64 && (int64_t)U1 * U2 <= kUnionMaxRows;
+    SphereAcc acc;
+    if (fits)
+        for (int i = tid; i < U1 * U2; i += blockDim.x) bitmap[i] = 0ull;
+    for (int a = a0; a < a1; ++a) {
+        AtomBox b;
 #pragma unroll
-    for (int k = 0; k < PE_SPHERE_NOUT; ++k) out[(int64_t)gidx * PE_SPHERE_NOUT + k] = acc[k];
+        for (int k = 0; k < 3; ++k) {
+            b.lo[k] = box[6 * a + k];
+            b.dim[k] = box[6 * a + 3 + k];
+        }
+        const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+        const double T = thr[a];
+        __syncthreads();  // bitmap cleared / previous atom's claims and table reads complete
+        if (b.dim[0] <= 0 || b.dim[1] <= 0 || b.dim[2] <= 0) continue;
+        if (tab && fits) {
+            for (int k = tid; k < b.dim[1]; k += blockDim.x) {
+                tabs[0].sq[k] = axis_sq(g, 1, b.lo[1] + k, ax, ay, az);
+                tabs[0].off[k] = axis_off(g, 1, b.lo[1] + k);
+            }
+            for (int k = tid; k < b.dim[2]; k += blockDim.x) {
+                tabs[1].sq[k] = axis_sq(g, 2, b.lo[2] + k, ax, ay, az);
+                tabs[1].off[k] = axis_off(g, 2, b.lo[2] + k);
+            }
+            __syncthreads();
+            union_pass_tab<CASEB>(g, rho, b, ax, ay, az, T, tabs, warp, lane, cp, cn, ulo0, ulo1, ulo2, U2, bitmap, acc);
+        } else {
+            union_pass_generic(g, rho, b, ax, ay, az, T, tid, blockDim.x, cp, cn, fits, ulo0, ulo1, ulo2, U2, bitmap, a0, a, box,
+                               thr, xyz, acc);
+        }
+    }
+    const int n_all = warp_sum(acc.n_all), n_pos = warp_sum(acc.n_pos), n_neg = warp_sum(acc.n_neg);
+    const int bad = warp_sum(acc.bad);
+    const double s_all = warp_sum(acc.s_all), s_pos = warp_sum(acc.s_pos), s_neg = warp_sum(acc.s_neg);
+    if (lane == 0) {
+        red_i[warp][0] = n_all;
+        red_i[warp][1] = n_pos;
+        red_i[warp][2] = n_neg;
+        red_i[warp][3] = bad;
+        red_d[warp][0] = s_all;
+        red_d[warp][1] = s_pos;
+        red_d[warp][2] = s_neg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int ni[4] = {0, 0, 0, 0};
+        double sd[3] = {0.0, 0.0, 0.0};
+        for (int w = 0; w < kUnionWarps; ++w) {  // fixed order: deterministic
+            for (int k = 0; k < 4; ++k) ni[k] += red_i[w][k];
+            for (int k = 0; k < 3; ++k) sd[k] += red_d[w][k];
+        }
+        double *o = out + (int64_t)grp * PE_SPHERE_NOUT;
+        o[0] = (double)ni[0];
+        o[1] = sd[0];
+        o[2] = (double)ni[1];
+        o[3] = sd[1];
+        o[4] = (double)ni[2];
+        o[5] = sd[2];
+        o[6] = ni[3] ? 0.0 : 1.0;
+        o[7] = candidates;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ list kernels
@@ -516,25 +664,25 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     ws += align_up((int64_t)n_atoms * 6 * 4, 256);
     double *thr = (double *)ws;
     ws += align_up((int64_t)n_atoms * 8, 256);
-    int32_t *atom_first = (int32_t *)ws;
-    ws += align_up((int64_t)n_atoms * 4, 256);
-    double *partial = (double *)ws;
     const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
     if (n_atoms > 0) {
         PE_LAUNCH("sphere_params_kernel", st, sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr));
         PE_LAUNCH_CHECK();
     }
     if (d_group_start == nullptr) {
-        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<false><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, nullptr, cut_pos,
+        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, cut_pos,
                                                                         cut_neg, d_out));
         PE_LAUNCH_CHECK();
         return PE_OK;
     }
-    PE_LAUNCH("group_first_kernel", st, group_first_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, atom_first));
-    if (n_atoms > 0)
-        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<true><<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, atom_first,
-                                                                       cut_pos, cut_neg, partial));
-    PE_LAUNCH("group_reduce_kernel", st, group_reduce_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, d_group_start, partial, d_out));
+    if (n_groups > 0) {
+        if (g->map2xyz[2] == 0)
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<true><<<n_groups, kUnionWarps * 32, 0, st>>>(
+                *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
+        else
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<false><<<n_groups, kUnionWarps * 32, 0, st>>>(
+                *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
+    }
     PE_LAUNCH_CHECK();
     return PE_OK;
 }

@@ -1,0 +1,210 @@
+"""GPU tier: the CUDA library (through the C ABI) against the CPU oracle on seeded random inputs, beyond the sizes
+and shapes the golden vectors cover: ragged groups, empty inputs, very large and very small radii (every kernel
+path: tabulated / generic, bitmap claims / earlier-atom claims, boxes wider than a warp), the reference's own
+known-answer scenarios (planted cubes, wrap semantics, merge + testOverlap: tests/test_ccp4.py:68-131 of the
+reference), and size-independent properties on large maps."""
+import io
+
+import numpy as np
+import pytest
+
+import cases
+import golden_checks as gc
+
+pytestmark = pytest.mark.gpu
+
+
+def _impls(name, seed=11):
+    from impl_cuda import CudaImpl
+    from impl_oracle import OracleImpl
+    from pdb_eda_b200 import ccp4
+    data, _ = cases.make_case(name, seed)
+    dm = ccp4.parse(io.BytesIO(data), name)
+    return dm, CudaImpl(dm), OracleImpl(dm)
+
+
+def _cmp_sums(a, b):
+    for col in (0, 2, 4, 6):
+        assert np.array_equal(a[:, col], b[:, col]), col
+    for col in (1, 3, 5):
+        gc.close(a[:, col], b[:, col], atol=1e-10)
+
+
+@pytest.mark.parametrize("name", gc.CASES)
+def test_union_ragged_groups(name):
+    dm, cuda, orc = _impls(name)
+    rng = np.random.default_rng(5)
+    sizes = rng.integers(0, 9, 25)
+    sizes[3] = 0
+    start = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    n = int(start[-1])
+    # atoms of a group lie close together (like a residue)
+    centres = cases.random_atoms(dm, len(sizes), seed=6).astype(np.float64)
+    xyz = np.concatenate([centres[k] + rng.uniform(-2.5, 2.5, (s, 3)) for k, s in enumerate(sizes)]) if n else np.zeros((0, 3))
+    xyz = np.round(xyz, 3).astype(np.float32).astype(np.float64)
+    radii = rng.uniform(1.0, 3.5, n).astype(np.float32)
+    m, s = cuda.mean_std()
+    cut = m + 1.0 * s
+    _cmp_sums(cuda.sphere_sums(xyz, radii, start, cut, -cut), orc.sphere_sums(xyz, radii, start, cut, -cut))
+
+
+@pytest.mark.parametrize("name,radius", [("ortho", 9.0), ("ortho", 12.5), ("perm", 12.5), ("hex", 6.0)])
+def test_union_wide_boxes(name, radius):
+    """Boxes wider than a warp (two column passes), and groups whose bounding box exceeds the shared bitmap."""
+    dm, cuda, orc = _impls(name)
+    rng = np.random.default_rng(8)
+    centres = cases.random_atoms(dm, 2, seed=9).astype(np.float64)
+    xyz = np.concatenate([c + rng.uniform(-2, 2, (3, 3)) for c in centres])
+    xyz = np.round(xyz, 3).astype(np.float32).astype(np.float64)
+    start = np.array([0, 3, 6], dtype=np.int32)
+    radii = np.full(6, radius, dtype=np.float32)
+    _cmp_sums(cuda.sphere_sums(xyz, radii, start, 0.5, -0.5), orc.sphere_sums(xyz, radii, start, 0.5, -0.5))
+    _cmp_sums(cuda.sphere_sums(xyz[:2], radii[:2], None, 0.5, -0.5), orc.sphere_sums(xyz[:2], radii[:2], None, 0.5, -0.5))
+
+
+@pytest.mark.parametrize("name", ["ortho", "tric"])
+def test_degenerate_radii_and_empty_batches(name):
+    dm, cuda, orc = _impls(name)
+    xyz = cases.random_atoms(dm, 6, seed=3).astype(np.float64)
+    radii = np.array([0.0, 1e-3, 0.2, 0.25, 0.5, 30.0 if name == "ortho" else 3.0], dtype=np.float32)
+    _cmp_sums(cuda.sphere_sums(xyz, radii, None, 0.0, 0.0), orc.sphere_sums(xyz, radii, None, 0.0, 0.0))
+    crs_c, off_c = cuda.sphere_lists(xyz[:5], radii[:5], 0.0)
+    crs_o, off_o = orc.sphere_lists(xyz[:5], radii[:5], 0.0)
+    assert np.array_equal(off_c, off_o) and np.array_equal(crs_c, crs_o)
+    # empty batches
+    assert cuda.sphere_sums(np.zeros((0, 3)), np.zeros(0, np.float32), None, 0.0, 0.0).shape == (0, 8)
+    crs_e, off_e = cuda.sphere_lists(np.zeros((0, 3)), np.zeros(0, np.float32), 0.0)
+    assert len(crs_e) == 0 and list(off_e) == [0]
+
+
+@pytest.mark.parametrize("name", ["ortho", "perm", "hex"])
+def test_sphere_lists_and_clouds_large_radius(name):
+    """Per-atom clusters (findAberrantBlobs) at a region-size radius: many clusters per atom."""
+    dm, cuda, orc = _impls(name)
+    xyz = cases.random_atoms(dm, 10, seed=21).astype(np.float64)
+    radii = np.full(10, 3.5, dtype=np.float32)
+    m, s = cuda.mean_std()
+    for cut in (m + 1.2 * s, -(m + 1.2 * s)):
+        ca, cb = cuda.sphere_lists(xyz, radii, cut), orc.sphere_lists(xyz, radii, cut)
+        assert np.array_equal(ca[1], cb[1]) and np.array_equal(ca[0], cb[0])
+        a, b = cuda.sphere_clouds(xyz, radii, cut), orc.sphere_clouds(xyz, radii, cut)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        gc.close(a[2], b[2])
+
+
+def _planted(shape=(60, 50, 40), intervals=(112, 112, 192), cell=(56.0, 56.0, 96.0, 90, 90, 90), crsStart=(-7, 11, 5),
+             axisOrder=(2, 1, 3)):
+    from pdb_eda_b200 import ccp4, synthetic
+    values = np.zeros(shape, dtype=np.float32)
+    data = synthetic.ccp4Bytes(values, cell, intervals, crsStart=crsStart, axisOrder=axisOrder)
+    return ccp4.parse(io.BytesIO(data), "kat")
+
+
+def test_kat_planted_cubes_and_merge():
+    """The reference's own scenarios (tests/test_ccp4.py:75-131): 2^3 and 3^3 cubes of +-1; merge of an 8-cube
+    with an 8-cube plus a bridging voxel -> 17 voxels whose centroid is the centre."""
+    dm = _planted()
+    h = dm.header
+    d = dm.density
+    d[10:12, 10:12, 10:12] = 1.0       # 2^3 green
+    d[20:23, 20:23, 20:23] = 1.0       # 3^3 green
+    d[30:32, 5:7, 5:7] = -1.0          # 2^3 red
+    d[5:8, 30:33, 30:33] = -1.0        # 3^3 red
+    green = dm.createFullBlobList(0.5)
+    red = dm.createFullBlobList(-0.5)
+    assert [len(b.crsList) for b in green] == [8, 27] and [len(b.crsList) for b in red] == [8, 27]
+    gc.close([b.totalDensity for b in green], [8.0, 27.0])
+    gc.close([b.totalDensity for b in red], [-8.0, -27.0])
+    gc.close([b.volume for b in green], [8 * h.unitVolume, 27 * h.unitVolume])
+    centre = np.mean([h.crs2xyzCoord([c, r, s]) for c in (10, 11) for r in (10, 11) for s in (10, 11)], axis=0)
+    gc.close(green[0].centroid, centre, rtol=1e-9, atol=1e-9)
+    gc.close(green[0].coordCenter, centre, rtol=1e-9, atol=1e-9)
+    # green and red from one pass agree with the two single-sign calls
+    g2, r2 = dm.createFullBlobLists(0.5, -0.5)
+    assert all(a == b for a, b in zip(green, g2)) and all(a == b for a, b in zip(red, r2))
+    assert dm.createFullBlobList(0) is None
+    # merge + overlap
+    dm2 = _planted()
+    dm2.density[10:12, 10:12, 10:12] = 1.0
+    dm2.density[13:15, 10:12, 10:12] = 1.0
+    blobs = dm2.createFullBlobList(0.5)
+    assert len(blobs) == 2 and not blobs[0].testOverlap(blobs[1])
+    dm2.density[12, 11, 11] = 1.0       # the bridging voxel joins the cubes (through the tracked host array)
+    joined = dm2.createFullBlobList(0.5)
+    assert len(joined) == 1 and len(joined[0].crsList) == 17
+    a, b = blobs
+    b.crsList = set(b.crsList) | {(11, 11, 12)}
+    assert a.testOverlap(b)
+    a.merge(b)
+    assert len(a.crsList) == 17 and a == joined[0]
+
+
+def test_kat_wrap_semantics():
+    """getPointDensityFromCrs repeats after the interval, is 0 where the cell is not covered (tests/test_ccp4.py:68-72)."""
+    from pdb_eda_b200 import cutils
+    dm = _planted(shape=(20, 20, 20), intervals=(32, 32, 32), cell=(16.0, 16.0, 16.0, 90, 90, 90), crsStart=(0, 0, 0),
+                  axisOrder=(1, 2, 3))
+    dm.density[3, 4, 19] = 7.0
+    dm.density[0, 0, 0] = 5.0
+    assert cutils.getPointDensityFromCrs(dm, [19, 4, 3]) == 7.0
+    assert cutils.getPointDensityFromCrs(dm, [-13, 4, 3]) == 7.0       # -13 + 32 = 19
+    assert cutils.getPointDensityFromCrs(dm, [32, 32, 32]) == 5.0      # one interval further
+    assert cutils.getPointDensityFromCrs(dm, [20, 0, 0]) == 0 and not cutils.testValidCrs(dm, [20, 0, 0])
+    assert cutils.getPointDensityFromCrs(dm, [-1, 0, 0]) == 0 and not cutils.testValidCrs(dm, [31, 0, 0])
+    assert cutils.testValidCrsList(dm, [(0, 0, 0), (32, 19, -32)]) and not cutils.testValidCrsList(dm, [(0, 0, 0), (25, 0, 0)])
+
+
+@pytest.mark.parametrize("n", [128, 200])
+def test_blobs_on_larger_maps(n):
+    """Full blob labelling against the oracle at sizes the reference itself cannot cluster (O(N^2) cdist)."""
+    from pdb_eda_b200 import ccp4, synthetic
+    from impl_cuda import CudaImpl
+    from impl_oracle import OracleImpl
+    vol = synthetic.smoothNoiseMap(n, seed=n, sigma=1.5)
+    nc = n - 8  # stored columns differ from the interval: exercises the non-vectorised path on odd sizes too
+    data = synthetic.ccp4Bytes(vol[:, :, :nc], (n * 0.4,) * 3 + (90, 90, 90), (n, n, n))
+    dm = ccp4.parse(io.BytesIO(data), "big")
+    cuda, orc = CudaImpl(dm), OracleImpl(dm)
+    for (c1, l1, s1), (c2, l2, s2) in zip(cuda.full_blobs(2.8, -2.8), orc.full_blobs(2.8, -2.8)):
+        assert len(c1) > 1000
+        assert np.array_equal(c1, c2) and np.array_equal(l1, l2)
+        gc.close(s1, s2, rtol=1e-9, atol=1e-9)
+
+
+def test_blob_properties_at_scale():
+    """Size-independent properties on a 384^3 map (BASELINE.json config 2 size): labels are canonical (a blob's
+    number is the rank of its first voxel), every blob is a single 26-connected component, blobs are mutually
+    non-adjacent, and the per-blob counts add up."""
+    import torch
+    from pdb_eda_b200 import _device, ccp4, synthetic
+    n = 384
+    vol = synthetic.smoothNoiseMapDevice(n, seed=4)
+    hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), (192.0,) * 3 + (90, 90, 90), (n, n, n)))
+    dev = _device.DeviceMap(_device.geom_from_header(hdr), vol.reshape(-1))
+    m, s = dev.mean_std()
+    green, red = dev.blob_label(m + 3 * s, -(m + 3 * s))
+    for part in (green, red):
+        crs, label, stats = part["crs"], part["label"].long(), part["stats"]
+        nb = part["n_blobs"]
+        assert part["n_voxels"] > 10000 and nb > 100
+        key = (crs[:, 0].long() * n + crs[:, 1].long()) * n + crs[:, 2].long()
+        assert bool((key[1:] > key[:-1]).all())                       # createFullCrsList order
+        first = torch.full((nb,), len(label), dtype=torch.long, device=label.device)
+        first.scatter_reduce_(0, label, torch.arange(len(label), device=label.device), reduce="amin")
+        assert bool((first[1:] > first[:-1]).all())                   # blob b's first voxel precedes blob b+1's
+        assert torch.equal(torch.bincount(label, minlength=nb).double(), stats[:, 0])
+        # dense check of connectivity: no two voxels of different blobs are 26-adjacent
+        dense = torch.full((n + 2, n + 2, n + 2), -1, dtype=torch.int32, device=label.device)
+        dense[crs[:, 0].long() + 1, crs[:, 1].long() + 1, crs[:, 2].long() + 1] = label.int()
+        core = dense[1:-1, 1:-1, 1:-1]
+        for dc in (-1, 0, 1):
+            for dr in (-1, 0, 1):
+                for ds in (-1, 0, 1):
+                    nb_lab = dense[1 + dc:n + 1 + dc, 1 + dr:n + 1 + dr, 1 + ds:n + 1 + ds]
+                    both = (core >= 0) & (nb_lab >= 0)
+                    assert bool((core[both] == nb_lab[both]).all())
+        # every blob is connected: re-clustering its voxels as an arbitrary list gives the same partition
+        sub = crs[: min(len(crs), 200000)]
+        lab2, ncl = _device.cluster_crs(sub)
+        pairs = torch.unique(torch.stack((label[: len(sub)], lab2.long()), dim=1), dim=0)
+        assert len(pairs) == len(torch.unique(lab2)) or len(sub) < len(crs)
