@@ -110,18 +110,34 @@ __device__ __forceinline__ bool claimed_by_earlier(const pe_geom &g, int first, 
     return false;
 }
 
+// Exact float -> double widening on the integer pipe.  (F2F.F64.F32 is a slow-rate conversion and was the top
+// stall of the gather loops in the first ncu capture, profiles/r01a_first_path.md.)
+__device__ __forceinline__ double widen(float v) {
+    const unsigned u = __float_as_uint(v);
+    const unsigned e = u & 0x7f800000u;
+    if (e == 0x7f800000u || (e == 0u && (u & 0x007fffffu) != 0u)) return (double)v;  // inf, nan, denormal: rare
+    const unsigned hi = (u & 0x80000000u) | (((u >> 3) & 0x0fffffffu) + 0x38000000u);
+    const double d = __hiloint2double((int)hi, (int)(u << 29));
+    return e == 0u ? 0.0 : d;
+}
+
+// Effective cutoffs: a class whose cutoff is 0 is switched off by an unreachable threshold.
+__device__ __forceinline__ float eff_pos(float cp) { return cp > 0.f ? cp : __int_as_float(0x7f800000); }
+__device__ __forceinline__ float eff_neg(float cn) { return cn < 0.f ? cn : __int_as_float(0xff800000); }
+
 struct SphereAcc {
     int n_all = 0, n_pos = 0, n_neg = 0, bad = 0;
     double s_all = 0.0, s_pos = 0.0, s_neg = 0.0;
+    // v must be 0 when the voxel is not taken; cp / cn are the effective cutoffs (cp > 0 > cn).
     __device__ __forceinline__ void add(bool take, float v, float cp, float cn) {
+        const double d = widen(v);
+        const bool p = v > cp, q = v < cn;
         n_all += take ? 1 : 0;
-        s_all += take ? (double)v : 0.0;
-        const bool p = take && cp > 0.f && v > cp;
-        const bool q = take && cn < 0.f && v < cn;
+        s_all += d;
         n_pos += p ? 1 : 0;
-        s_pos += p ? (double)v : 0.0;
+        s_pos += p ? d : 0.0;
         n_neg += q ? 1 : 0;
-        s_neg += q ? (double)v : 0.0;
+        s_neg += q ? d : 0.0;
     }
 };
 
@@ -206,6 +222,8 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     }
     const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
     const double T = thr[a];
+    cp = eff_pos(cp);
+    cn = eff_neg(cn);
     SphereAcc acc;
     const bool tabulated = g.orthogonal && b.dim[0] <= kDMax * 32 && b.dim[1] <= kDMax && b.dim[2] <= kDMax;
     if (tabulated) {
@@ -235,120 +253,116 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
 
 // ------------------------------------------------------------------------------------------------ union kernel
 // Set-union of the spheres of one group of atoms (getSphereCrsFromXyzList, pdb_eda/cutils.pyx:250-271; the region
-// density / discrepancy sums of pdb_eda/densityAnalysis.py:1037-1068, :1160-1211).  One CTA per group.  A voxel
-// must be counted once however many spheres hold it: the group's bounding box is kept as a bitmap in shared memory
-// (one 64-bit word per (row, section), one bit per column) and every in-sphere voxel is claimed with one atomicOr
-// per box row -- the returned old word tells each lane whether an earlier atom already owns its voxel.  The CTA
-// walks the group's atoms one after another (all warps share an atom's box rows), so claims, and with them the
-// float64 summation order, are deterministic.
+// density / discrepancy sums of pdb_eda/densityAnalysis.py:1037-1068, :1160-1211).  One CTA per group, two phases
+// per tile of the group's bounding box (tiles of 64 columns x 48 rows x 48 sections; a residue at the reference's
+// default 3.5 A radius is one tile):
+//   1. membership: every warp walks its share of every atom's box rows and ORs the in-sphere columns of a box row
+//      into a shared-memory bitmap (two 32-bit words per (row, section)) -- one ballot and one or two atomicOr per
+//      warp iteration, no global memory traffic.  OR is commutative, so no ordering between atoms is needed.
+//   2. gather: the warps walk the bitmap rows; a lane owns a column, loads rho where its bit is set (a warp reads
+//      one contiguous run of the map row) and accumulates.  Each voxel of the union is read exactly once however
+//      many spheres hold it, and the float64 summation order is fixed, so results are run-to-run deterministic.
 constexpr int kUnionWarps = 4;
-constexpr int kUnionMaxRows = 2304;  // (row, section) pairs of the union bounding box that fit the shared bitmap
+constexpr int kTileC = 64, kTileR = 48, kTileS = 48;
 
-template <bool CASEB>
-__device__ __forceinline__ void union_pass_tab(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
-                                               double ay, double az, double T, const AxisTab *tab, int warp, int lane,
-                                               float cp, float cn, int ulo0, int ulo1, int ulo2, int U2,
-                                               unsigned long long *bitmap, SphereAcc &acc) {
-    const int inner = CASEB ? 2 : g.map2xyz[2];
-    const int outer = 3 - inner;
-    const AxisTab &ti = tab[inner - 1];
-    const AxisTab &to = tab[outer - 1];
-    const int Di = sel3(b.dim[0], b.dim[1], b.dim[2], inner), Do = sel3(b.dim[0], b.dim[1], b.dim[2], outer), D0 = b.dim[0];
+struct UnionShared {
+    uint32_t bits[kTileR * kTileS * 2];
+    double sq[kUnionWarps][2][kTileR > kTileS ? kTileR : kTileS];  // [warp][row axis / section axis][index in tile]
+    int offC[kTileC], offR[kTileR], offS[kTileS];                   // wrapped element offsets of the tile's indices
+};
+
+// MODE 0: z is carried by the row axis (inner loop over rows), 1: by the section axis, 2: by the column axis.
+template <int MODE>
+__device__ __forceinline__ void union_mark_tab(const pe_geom &g, const AtomBox &b, double ax, double ay, double az, double T,
+                                               double *sq1, double *sq2, int warp, int lane, int tc0, int tr0, int ts0, int tC,
+                                               int tR, int tS, uint32_t *bits) {
+    // intersection of the atom's box with the tile, in tile-relative coordinates
+    const int c_lo = max(b.lo[0], tc0), c_hi = min(b.lo[0] + b.dim[0], tc0 + tC);
+    const int r_lo = max(b.lo[1], tr0), r_hi = min(b.lo[1] + b.dim[1], tr0 + tR);
+    const int s_lo = max(b.lo[2], ts0), s_hi = min(b.lo[2] + b.dim[2], ts0 + tS);
+    if (c_lo >= c_hi || r_lo >= r_hi || s_lo >= s_hi) return;  // warp-uniform
+    const int n1 = r_hi - r_lo, n2 = s_hi - s_lo;
+    __syncwarp();
+    for (int k = lane; k < n1; k += 32) sq1[k] = axis_sq(g, 1, r_lo + k, ax, ay, az);
+    for (int k = lane; k < n2; k += 32) sq2[k] = axis_sq(g, 2, s_lo + k, ax, ay, az);
+    __syncwarp();
+    constexpr bool kInnerRows = (MODE == 0);
+    const double *sqi_tab = kInnerRows ? sq1 : sq2;
+    const double *sqo_tab = kInnerRows ? sq2 : sq1;
+    const int Di = kInnerRows ? n1 : n2, Do = kInnerRows ? n2 : n1;
+    const int width = c_hi - c_lo;
     int d0p = 1;
-    while (d0p < D0 && d0p < 32) d0p <<= 1;
+    while (d0p < width && d0p < 32) d0p <<= 1;
     const int rpi = 32 / d0p;
     const int lrow = lane / d0p, lc = lane % d0p;
     const unsigned rowmask = d0p == 32 ? 0xffffffffu : ((1u << d0p) - 1u);
-    for (int cbase = 0; cbase < D0; cbase += 32) {
-        const int ic = cbase + lc;
-        const bool act = ic < D0;
-        const int c = b.lo[0] + ic;
-        const double sqc = act ? axis_sq(g, 0, c, ax, ay, az) : 0.0;
-        const int offc = act ? axis_off(g, 0, c) : kInvalidOff;
-        const int shift = b.lo[0] - ulo0 + cbase;
+    const int rbase = r_lo - tr0, sbase = s_lo - ts0;
+    for (int cbase = 0; cbase < width; cbase += 32) {
+        const bool act = cbase + lc < width;
+        const double sqc = act ? axis_sq(g, 0, c_lo + cbase + lc, ax, ay, az) : 0.0;
+        const int shift = c_lo + cbase - tc0;  // bit position of lane column 0 in the tile row (0..63)
         for (int ko0 = warp * rpi; ko0 < Do; ko0 += kUnionWarps * rpi) {
             const int ko = ko0 + lrow;
             const bool rowact = act && ko < Do;
-            const double sqo = rowact ? to.sq[ko] : 0.0;
-            const int offo = rowact ? to.off[ko] : kInvalidOff;
+            const double sqo = rowact ? sqo_tab[ko] : 0.0;
             const double P = __dadd_rn(sqc, sqo);
-            const int offco = offc | offo;
-            const int sumco = (int)((unsigned)offc + (unsigned)offo);
-#pragma unroll 2
+            // tile-relative bitmap row of (ko, ki = 0) and its stride in ki
+            const int row0 = kInnerRows ? (rbase * kTileS + sbase + ko) : ((rbase + ko) * kTileS + sbase);
+            constexpr int kRowStep = kInnerRows ? kTileS : 1;
+#pragma unroll 4
             for (int ki = 0; ki < Di; ++ki) {
-                const double sqi = ti.sq[ki];
-                const int offi = ti.off[ki];
-                const double d2 = CASEB ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
-                const bool inside = rowact && (d2 <= T);
-                const unsigned m = __ballot_sync(kFull, inside);
-                if (m == 0u) continue;  // warp-uniform
+                const double sqi = sqi_tab[ki];
+                const double d2 = (MODE == 2) ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
+                const unsigned m = __ballot_sync(kFull, rowact && (d2 <= T));
                 const unsigned mine = (m >> (lrow * d0p)) & rowmask;
-                unsigned long long old = 0ull;
-                if (lc == 0 && mine) {
-                    const int r = b.lo[1] + (inner == 1 ? ki : ko), s = b.lo[2] + (inner == 2 ? ki : ko);
-                    old = atomicOr(bitmap + ((r - ulo1) * U2 + (s - ulo2)), (unsigned long long)mine << shift);
+                if (lc == 0 && mine != 0u) {
+                    const unsigned long long wide = (unsigned long long)mine << shift;
+                    uint32_t *word = bits + 2 * (row0 + ki * kRowStep);
+                    const uint32_t lo = (uint32_t)wide, hi = (uint32_t)(wide >> 32);
+                    if (lo) atomicOr(word, lo);
+                    if (hi) atomicOr(word + 1, hi);
                 }
-                old = __shfl_sync(kFull, old, lrow * d0p);
-                const bool ok = (offco | offi) >= 0;
-                const bool claim = inside && !((old >> (shift + lc)) & 1ull);
-                float v = 0.f;
-                if (claim && ok) v = __ldg(rho + (int)((unsigned)sumco + (unsigned)offi));
-                acc.bad |= (inside && !ok) ? 1 : 0;
-                acc.add(claim, v, cp, cn);
             }
         }
     }
 }
 
-// Generic pass (skewed cells, very wide boxes): exact per-candidate geometry; claims through the bitmap when the
-// group's box fits it, else by testing the earlier atoms of the group.
-__device__ __forceinline__ void union_pass_generic(const pe_geom &g, const float *__restrict__ rho, const AtomBox &b, double ax,
-                                                   double ay, double az, double T, int tid, int nthreads, float cp, float cn,
-                                                   bool fits, int ulo0, int ulo1, int ulo2, int U2, unsigned long long *bitmap,
-                                                   int gfirst, int self, const int32_t *__restrict__ box,
-                                                   const double *__restrict__ thr, const double *__restrict__ xyz,
-                                                   SphereAcc &acc) {
-    const int D0 = b.dim[0], D1 = b.dim[1], D2 = b.dim[2];
-    const int64_t vol = (int64_t)D0 * D1 * D2;
-    for (int64_t m = tid; m < vol; m += nthreads) {
-        const int ic = (int)(m % D0);
-        const int64_t t = m / D0;
-        const int ir = (int)(t % D1), is = (int)(t / D1);
-        const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+__device__ __forceinline__ void union_mark_generic(const pe_geom &g, const AtomBox &b, double ax, double ay, double az,
+                                                   double T, int tid, int nthreads, int tc0, int tr0, int ts0, int tC, int tR,
+                                                   int tS, uint32_t *bits) {
+    const int c_lo = max(b.lo[0], tc0), c_hi = min(b.lo[0] + b.dim[0], tc0 + tC);
+    const int r_lo = max(b.lo[1], tr0), r_hi = min(b.lo[1] + b.dim[1], tr0 + tR);
+    const int s_lo = max(b.lo[2], ts0), s_hi = min(b.lo[2] + b.dim[2], ts0 + tS);
+    if (c_lo >= c_hi || r_lo >= r_hi || s_lo >= s_hi) return;
+    const int nc = c_hi - c_lo, n1 = r_hi - r_lo;
+    const int vol = nc * n1 * (s_hi - s_lo);
+    for (int m = tid; m < vol; m += nthreads) {
+        const int ic = m % nc, t = m / nc;
+        const int c = c_lo + ic, r = r_lo + t % n1, s = s_lo + t / n1;
         double vx, vy, vz;
         crs2xyz(g, c, r, s, vx, vy, vz);
         if (!(dist2(ax, ay, az, vx, vy, vz) <= T)) continue;
-        const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
-        const bool ok = (oc | orr | os) >= 0;
-        acc.bad |= ok ? 0 : 1;
-        bool claim;
-        if (fits) {
-            const unsigned long long bit = 1ull << (c - ulo0);
-            claim = !(atomicOr(bitmap + ((r - ulo1) * U2 + (s - ulo2)), bit) & bit);
-        } else {
-            claim = !(gfirst < self && claimed_by_earlier(g, gfirst, self, box, thr, xyz, c, r, s));
-        }
-        const float v = (claim && ok) ? __ldg(rho + (oc + orr + os)) : 0.f;
-        acc.add(claim, v, cp, cn);
+        const int cb = c - tc0;
+        atomicOr(bits + 2 * ((r - tr0) * kTileS + (s - ts0)) + (cb >> 5), 1u << (cb & 31));
     }
 }
 
-template <bool CASEB>
-__global__ void __launch_bounds__(kUnionWarps * 32)
+template <int MODE>
+__global__ void __launch_bounds__(kUnionWarps * 32, 7)
     sphere_union_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_groups,
                         const int32_t *__restrict__ group_start, const double *__restrict__ xyz,
                         const int32_t *__restrict__ box, const double *__restrict__ thr, float cp, float cn,
                         double *__restrict__ out /* n_groups x PE_SPHERE_NOUT */) {
-    __shared__ unsigned long long bitmap[kUnionMaxRows];
-    __shared__ AxisTab tabs[2];
+    __shared__ UnionShared sh;
     __shared__ double red_d[kUnionWarps][3];
     __shared__ int red_i[kUnionWarps][4];
     const int grp = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a0 = group_start[grp], a1 = group_start[grp + 1];
-    // the group's bounding box and whether the tabulated path applies to every atom
+    cp = eff_pos(cp);
+    cn = eff_neg(cn);
+    // the group's bounding box
     int ulo0 = INT_MAX, ulo1 = INT_MAX, ulo2 = INT_MAX, uhi0 = INT_MIN, uhi1 = INT_MIN, uhi2 = INT_MIN;
-    bool tab = g.orthogonal != 0;
     double candidates = 0.0;
     for (int a = a0; a < a1; ++a) {
         const int32_t *bx = box + 6 * a;
@@ -361,40 +375,101 @@ __global__ void __launch_bounds__(kUnionWarps * 32)
         uhi0 = max(uhi0, bx[0] + d0);
         uhi1 = max(uhi1, bx[1] + d1);
         uhi2 = max(uhi2, bx[2] + d2);
-        tab = tab && d1 <= kDMax && d2 <= kDMax;
     }
-    const bool any = uhi0 > ulo0;
-    const int U0 = any ? uhi0 - ulo0 : 0, U1 = any ? uhi1 - ulo1 : 0, U2 = any ? uhi2 - ulo2 : 0;
-    const bool fits = any && U0 <= 64 && (int64_t)U1 * U2 <= kUnionMaxRows;
     SphereAcc acc;
-    if (fits)
-        for (int i = tid; i < U1 * U2; i += blockDim.x) bitmap[i] = 0ull;
-    for (int a = a0; a < a1; ++a) {
-        AtomBox b;
+    for (int i = tid; i < kTileR * kTileS * 2; i += blockDim.x) sh.bits[i] = 0u;
+    if (uhi0 > ulo0) {
+        for (int ts0 = ulo2; ts0 < uhi2; ts0 += kTileS)
+            for (int tr0 = ulo1; tr0 < uhi1; tr0 += kTileR)
+                for (int tc0 = ulo0; tc0 < uhi0; tc0 += kTileC) {
+                    const int tC = min(kTileC, uhi0 - tc0), tR = min(kTileR, uhi1 - tr0), tS = min(kTileS, uhi2 - ts0);
+                    for (int k = tid; k < tC; k += blockDim.x) sh.offC[k] = axis_off(g, 0, tc0 + k);
+                    for (int k = tid; k < tR; k += blockDim.x) sh.offR[k] = axis_off(g, 1, tr0 + k);
+                    for (int k = tid; k < tS; k += blockDim.x) sh.offS[k] = axis_off(g, 2, ts0 + k);
+                    __syncthreads();  // bitmap is clear, offsets are in place
+                    // phase 1: membership
+                    for (int a = a0; a < a1; ++a) {
+                        AtomBox b;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            b.lo[k] = box[6 * a + k];
-            b.dim[k] = box[6 * a + 3 + k];
-        }
-        const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
-        const double T = thr[a];
-        __syncthreads();  // bitmap cleared / previous atom's claims and table reads complete
-        if (b.dim[0] <= 0 || b.dim[1] <= 0 || b.dim[2] <= 0) continue;
-        if (tab && fits) {
-            for (int k = tid; k < b.dim[1]; k += blockDim.x) {
-                tabs[0].sq[k] = axis_sq(g, 1, b.lo[1] + k, ax, ay, az);
-                tabs[0].off[k] = axis_off(g, 1, b.lo[1] + k);
-            }
-            for (int k = tid; k < b.dim[2]; k += blockDim.x) {
-                tabs[1].sq[k] = axis_sq(g, 2, b.lo[2] + k, ax, ay, az);
-                tabs[1].off[k] = axis_off(g, 2, b.lo[2] + k);
-            }
-            __syncthreads();
-            union_pass_tab<CASEB>(g, rho, b, ax, ay, az, T, tabs, warp, lane, cp, cn, ulo0, ulo1, ulo2, U2, bitmap, acc);
-        } else {
-            union_pass_generic(g, rho, b, ax, ay, az, T, tid, blockDim.x, cp, cn, fits, ulo0, ulo1, ulo2, U2, bitmap, a0, a, box,
-                               thr, xyz, acc);
-        }
+                        for (int k = 0; k < 3; ++k) {
+                            b.lo[k] = box[6 * a + k];
+                            b.dim[k] = box[6 * a + 3 + k];
+                        }
+                        if (b.dim[0] <= 0 || b.dim[1] <= 0 || b.dim[2] <= 0) continue;
+                        const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+                        if (g.orthogonal)
+                            union_mark_tab<MODE>(g, b, ax, ay, az, thr[a], sh.sq[warp][0], sh.sq[warp][1], warp, lane, tc0, tr0, ts0,
+                                                 tC, tR, tS, sh.bits);
+                        else
+                            union_mark_generic(g, b, ax, ay, az, thr[a], tid, blockDim.x, tc0, tr0, ts0, tC, tR, tS, sh.bits);
+                    }
+                    __syncthreads();
+                    // phase 2: gather every voxel of the union once.  A warp owns tile rows rl = warp, warp + 4, ...
+                    // and walks their sections four at a time: the four (predicated) loads are issued back to
+                    // back before any is consumed, which is what hides the L2 latency of this gather.
+                    {
+                        const int oc0 = lane < tC ? sh.offC[lane] : kInvalidOff;
+                        const int oc1 = lane + 32 < tC ? sh.offC[lane + 32] : kInvalidOff;
+                        for (int rl = warp; rl < tR; rl += kUnionWarps) {
+                            const int orow = sh.offR[rl];
+                            uint32_t *rowbits = sh.bits + 2 * rl * kTileS;
+                            for (int sl0 = 0; sl0 < tS; sl0 += 4) {
+                                uint32_t w0[4], w1[4];
+                                uint32_t any0 = 0u, any1 = 0u;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const bool live = sl0 + j < tS;
+                                    const uint2 w = live ? *reinterpret_cast<const uint2 *>(rowbits + 2 * (sl0 + j)) : make_uint2(0u, 0u);
+                                    w0[j] = w.x;
+                                    w1[j] = w.y;
+                                    any0 |= w.x;
+                                    any1 |= w.y;
+                                }
+                                if ((any0 | any1) == 0u) continue;  // warp-uniform
+                                int ors[4];
+                                unsigned srs[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int os = sl0 + j < tS ? sh.offS[sl0 + j] : kInvalidOff;
+                                    ors[j] = orow | os;
+                                    srs[j] = (unsigned)orow + (unsigned)os;
+                                }
+                                if (any0) {
+                                    float v[4];
+                                    bool bit[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        bit[j] = (w0[j] >> lane) & 1u;
+                                        const bool ok = (ors[j] | oc0) >= 0;
+                                        v[j] = 0.f;
+                                        if (bit[j] && ok) v[j] = __ldg(rho + (int)(srs[j] + (unsigned)oc0));
+                                        acc.bad |= (bit[j] && !ok) ? 1 : 0;
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc.add(bit[j], v[j], cp, cn);
+                                }
+                                if (any1) {
+                                    float v[4];
+                                    bool bit[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        bit[j] = (w1[j] >> lane) & 1u;
+                                        const bool ok = (ors[j] | oc1) >= 0;
+                                        v[j] = 0.f;
+                                        if (bit[j] && ok) v[j] = __ldg(rho + (int)(srs[j] + (unsigned)oc1));
+                                        acc.bad |= (bit[j] && !ok) ? 1 : 0;
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc.add(bit[j], v[j], cp, cn);
+                                }
+                                __syncwarp();
+                                if (lane < 4 && sl0 + lane < tS)  // leave the bitmap clear for the next tile
+                                    *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
     }
     const int n_all = warp_sum(acc.n_all), n_pos = warp_sum(acc.n_pos), n_neg = warp_sum(acc.n_neg);
     const int bad = warp_sum(acc.bad);
@@ -676,11 +751,15 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
         return PE_OK;
     }
     if (n_groups > 0) {
-        if (g->map2xyz[2] == 0)
-            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<true><<<n_groups, kUnionWarps * 32, 0, st>>>(
+        const int mode = g->map2xyz[2] == 1 ? 0 : (g->map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
+        if (mode == 0)
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<0><<<n_groups, kUnionWarps * 32, 0, st>>>(
+                *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
+        else if (mode == 1)
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<1><<<n_groups, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
         else
-            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<false><<<n_groups, kUnionWarps * 32, 0, st>>>(
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<2><<<n_groups, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
     }
     PE_LAUNCH_CHECK();
