@@ -1,0 +1,157 @@
+"""Multiple-structures mode across GPUs: structures sharded over ranks, cumulative statistics all-reduced.
+
+The reference runs one structure per ``multiprocessing.Pool`` task and gathers the per-structure results through
+temporary JSON files (pdb_eda/multipleStructures.py:164-180, :320-356; pdb_eda/optimizeParams.py:341-408).  Here a
+rank is one process per GPU (``torch.distributed``, NCCL over NVLink; gloo in the CPU tests): structures are dealt
+out longest-first, every rank analyses its share on its own GPU, and two collectives replace the file gather:
+
+  * one fused ``all_reduce(SUM)`` of the cumulative vector [structures analysed, voxels aggregated, electrons,
+    density, per-atom-type complete / incomplete overlap counts] (pdb_eda/optimizeParams.py:376-379);
+  * one ``all_gather`` of the fixed-width per-structure rows (ratio, counts, per-type diffs and slopes), because the
+    medians over structures need every value (pdb_eda/optimizeParams.py:400-405).
+
+A structure that fails to load or has too few electrons yields no row and contributes zeros, as in the reference
+(``analyzePDBID`` returns 0, pdb_eda/multipleStructures.py:331-333).  There is no data-path collective: structures are
+independent units.
+"""
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+STAT_COLUMNS = ("density_electron_ratio", "voxel_volume", "num_voxels_aggregated", "total_aggregated_electrons",
+                "total_aggregated_density", "num_atoms_analyzed", "num_residue_clouds_analyzed",
+                "num_domain_clouds_analyzed", "atom_overlap_completeness", "execution_time")
+
+
+def shardStructures(costs, worldSize):
+    """Longest-processing-time-first assignment (cf. the longest-job-first reordering of pdb_eda/optimizeParams.py:392-393).
+    ``costs``: one number per structure (e.g. voxels x atoms).  Returns ``worldSize`` lists of structure indices; every
+    rank computes the same assignment."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    loads = [0.0] * worldSize
+    shards = [[] for _ in range(worldSize)]
+    for i in order:
+        r = min(range(worldSize), key=lambda k: (loads[k], k))
+        shards[r].append(i)
+        loads[r] += float(costs[i])
+    return shards
+
+
+def analyzeStructure(analyzer, atomTypes):
+    """The per-structure result of ``analyzePDBID`` (pdb_eda/multipleStructures.py:320-356) /
+    ``processFunction`` (pdb_eda/optimizeParams.py:410-448), or 0 when the structure cannot be analysed."""
+    start = time.process_time()
+    if not analyzer or not analyzer.densityElectronRatio:
+        return 0
+    ratio = analyzer.densityElectronRatio
+    corrected = analyzer.medians['corrected_density_electron_ratio']
+    diffs = {t: ((corrected[t] - ratio) / ratio) if t in corrected else 0 for t in atomTypes}
+    slopes = {t: analyzer.medians['slopes'][t] if t in analyzer.medians['slopes'] else np.nan for t in atomTypes}
+    complete = sum(analyzer.atomTypeOverlapCompleteness.values())
+    incomplete = sum(analyzer.atomTypeOverlapIncompleteness.values())
+    completeness = complete / (complete + incomplete) if (complete > 0 or incomplete > 0) else complete
+    stats = {'density_electron_ratio': ratio, 'voxel_volume': analyzer.densityObj.header.unitVolume,
+             'num_voxels_aggregated': analyzer.numVoxelsAggregated, 'total_aggregated_electrons': analyzer.totalAggregatedElectrons,
+             'total_aggregated_density': analyzer.totalAggregatedDensity, 'num_atoms_analyzed': len(analyzer.atomCloudDescriptions),
+             'num_residue_clouds_analyzed': len(analyzer.residueCloudDescriptions),
+             'num_domain_clouds_analyzed': len(analyzer.domainCloudDescriptions), 'atom_overlap_completeness': completeness}
+    stats['execution_time'] = time.process_time() - start
+    return {"pdbid": analyzer.pdbid, "diffs": diffs, "slopes": slopes, "stats": stats,
+            "atomtype_overlap_completeness": dict(analyzer.atomTypeOverlapCompleteness),
+            "atomtype_overlap_incompleteness": dict(analyzer.atomTypeOverlapIncompleteness)}
+
+
+def _pack(results, indices, atomTypes):
+    """Local results -> (cumulative vector, fixed-width row matrix)."""
+    T = len(atomTypes)
+    cumulative = np.zeros(4 + 2 * T, dtype=np.float64)
+    rows = []
+    for idx in indices:
+        res = results.get(idx, 0)
+        if not res:
+            continue
+        st = res["stats"]
+        cumulative[0] += 1
+        cumulative[1] += st["num_voxels_aggregated"]
+        cumulative[2] += st["total_aggregated_electrons"]
+        cumulative[3] += st["total_aggregated_density"]
+        for k, t in enumerate(atomTypes):
+            cumulative[4 + k] += res["atomtype_overlap_completeness"].get(t, 0)
+            cumulative[4 + T + k] += res["atomtype_overlap_incompleteness"].get(t, 0)
+        rows.append([float(idx)] + [float(st[c]) for c in STAT_COLUMNS] + [float(res["diffs"][t]) for t in atomTypes] +
+                    [float(res["slopes"][t]) for t in atomTypes])
+    width = 1 + len(STAT_COLUMNS) + 2 * T
+    return cumulative, np.asarray(rows, dtype=np.float64).reshape(-1, width)
+
+
+def gatherResults(results, indices, nStructures, atomTypes, device="cpu", group=None):
+    """Collective step of multiple-structures mode.  ``results``: {structure index: result dict or 0} of THIS rank's
+    shard ``indices``.  Returns the same summary on every rank:
+    ``cumulative`` (dict), ``rows`` (n_ok x width float64, ordered by structure index), ``medianDiffs``, ``meanDiffs``,
+    ``overallStdDevDiffs``, ``medianSlopes``, ``sizeDiffs``, ``atomTypeOverlapCompleteness`` --
+    the quantities of ``calculateMedianDiffsSlopes`` (pdb_eda/optimizeParams.py:400-408)."""
+    atomTypes = list(atomTypes)
+    T = len(atomTypes)
+    cumulative, rows = _pack(results, indices, atomTypes)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    width = 1 + len(STAT_COLUMNS) + 2 * T
+    if world > 1:
+        cum_t = torch.from_numpy(cumulative).to(device)
+        dist.all_reduce(cum_t, op=dist.ReduceOp.SUM, group=group)       # ONE fused all-reduce of all cumulative counts
+        cumulative = cum_t.cpu().numpy()
+        # rows: pad every rank's block to the largest shard (an 8-byte MAX all-reduce), gather, drop the padding
+        cap_t = torch.tensor([len(rows)], dtype=torch.int64, device=device)
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
+        cap = max(int(cap_t.item()), 1)
+        block = torch.full((cap, width), -1.0, dtype=torch.float64, device=device)
+        if len(rows):
+            block[:len(rows)] = torch.from_numpy(rows).to(device)
+        gathered = [torch.empty_like(block) for _ in range(world)]
+        dist.all_gather(gathered, block, group=group)
+        allrows = torch.cat(gathered).cpu().numpy()
+        allrows = allrows[allrows[:, 0] >= 0]
+    else:
+        allrows = rows
+    allrows = allrows[np.argsort(allrows[:, 0], kind="stable")] if len(allrows) else allrows
+    ns = 1 + len(STAT_COLUMNS)
+    diffs = {t: allrows[:, ns + k].tolist() for k, t in enumerate(atomTypes)}
+    slopes = {t: allrows[:, ns + T + k].tolist() for k, t in enumerate(atomTypes)}
+    complete = {t: cumulative[4 + k] for k, t in enumerate(atomTypes)}
+    incomplete = {t: cumulative[4 + T + k] for k, t in enumerate(atomTypes)}
+    completeness = {t: (complete[t] / (complete[t] + incomplete[t]) if (complete[t] > 0 or incomplete[t] > 0) else 1) for t in atomTypes}
+    with np.errstate(all="ignore"):
+        medianDiffs = {t: (np.nanmedian(v) if (v and not np.isnan(v).all()) else 0) for t, v in diffs.items()}
+        meanDiffs = {t: (np.nanmean(v) if (v and not np.isnan(v).all()) else 0) for t, v in diffs.items()}
+        sizeDiffs = {t: int(np.sum(~np.isnan(v))) if v else 0 for t, v in diffs.items()}
+        squared = [x ** 2 for v in diffs.values() for x in v if not np.isnan(x)]
+        overallStd = float(np.sqrt(sum(squared) / (len(squared) - 1))) if len(squared) > 1 else float("nan")
+        medianSlopes = {t: np.nanmedian(v) for t, v in slopes.items() if v and not np.isnan(v).all()}
+    return {"cumulative": {"structures": int(cumulative[0]), "num_voxels_aggregated": cumulative[1],
+                           "total_aggregated_electrons": cumulative[2], "total_aggregated_density": cumulative[3],
+                           "density_electron_ratio": cumulative[3] / cumulative[2] if cumulative[2] else None,
+                           "atomtype_overlap_completeness": complete, "atomtype_overlap_incompleteness": incomplete},
+            "rows": allrows, "columns": ["index"] + list(STAT_COLUMNS) + ["diff:" + t for t in atomTypes] + ["slope:" + t for t in atomTypes],
+            "medianDiffs": medianDiffs, "meanDiffs": meanDiffs, "overallStdDevDiffs": overallStd, "medianSlopes": medianSlopes,
+            "sizeDiffs": sizeDiffs, "atomTypeOverlapCompleteness": completeness}
+
+
+def runMultipleStructures(items, loader, costs=None, atomTypes=None, device=None, group=None):
+    """Multiple-structures mode: ``loader(item)`` returns a DensityAnalysis (or 0); structures are sharded over the
+    ranks of the default process group, analysed on this rank's GPU, and summarised collectively."""
+    from . import densityAnalysis
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    atomTypes = sorted(densityAnalysis.paramsGlobal["radii"]) if atomTypes is None else list(atomTypes)
+    costs = [1.0] * len(items) if costs is None else costs
+    mine = shardStructures(costs, world)[rank]
+    results = {}
+    for idx in mine:
+        try:
+            results[idx] = analyzeStructure(loader(items[idx]), atomTypes)
+        except Exception:
+            results[idx] = 0                     # a bad structure yields no row; the run continues
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    return gatherResults(results, mine, len(items), atomTypes, device, group)
