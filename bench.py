@@ -319,35 +319,28 @@ def main_gpu(args, rank, world, local_rank):
         n_fg = float(res["blob_counts"][0] + res["blob_counts"][2])
         n_blob = float(res["blob_counts"][1] + res["blob_counts"][3])
         region_union = float(res["region"][:, 0].sum())
-        algo = {  # algorithmic bytes per launch
-            "threshold_bitmap_kernel": 4.0 * blob_units,
-            "sphere_sums_kernel": None,  # two launches per step with different byte counts, see below
-        }
+        # algorithmic bytes per launch
+        algo = {"threshold_bitmap_kernel": 4.0 * blob_units,                               # 4 N_vox
+                "sphere_union_kernel": 4.0 * region_union + 52.0 * vp.n_atoms,            # 4 V_in + 52 A (region pass)
+                "sphere_sums_kernel": 4.0 * cloud_units + 52.0 * vp.n_atoms}              # 4 V_in + 52 A (cloud pass)
+        notes = {"sphere_union_kernel": "bound by fp64 membership tests + sector-granular L2 gathers, not by HBM; V_in = union voxels",
+                 "sphere_sums_kernel": "bound by fp64 membership tests (216 candidates per atom at cloud radii), not by HBM"}
         kernels = []
         for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             kernels.append({"kernel": name, "launches": count, "ms_total": round(ms, 4), "us_per_launch": round(ms * 1e3 / max(count, 1), 2)})
-        top = kernels[0]["kernel"] if kernels else None
-        per_launch_ms = {k["kernel"]: k["ms_total"] / max(k["launches"], 1) for k in kernels}
-        roof = None
-        if "threshold_bitmap_kernel" in per_launch_ms:
-            t = per_launch_ms["threshold_bitmap_kernel"] * 1e-3
-            ach = algo["threshold_bitmap_kernel"] / t / 1e9
-            roof = {"kernel": "threshold_bitmap_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": algo["threshold_bitmap_kernel"]}
-        sphere = None
-        if "sphere_sums_kernel" in per_launch_ms:
-            # cloud and region launches alternate; bytes = 4 V_in + 52 A for each
-            b = 4.0 * (cloud_units + region_pairs) + 52.0 * 2 * vp.n_atoms
-            t = prof["sphere_sums_kernel"][1] / (prof["sphere_sums_kernel"][0] / 2.0) * 1e-3
-            ach = b / t / 1e9
-            sphere = {"kernel": "sphere_sums_kernel (cloud + region launch pair)", "bound": "hbm", "achieved": round(ach, 1),
-                      "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
-                      "algorithmic_bytes_per_launch_pair": b,
-                      "note": "gathers hit L2 (map pinned by reuse); the kernel is fp64-issue bound, not HBM bound"}
-        dominant = roof
-        if top and top.startswith("sphere_sums") and sphere is not None:
-            dominant = sphere
+        roofs = []
+        for k in kernels:
+            if k["kernel"] in algo:
+                t = k["ms_total"] / max(k["launches"], 1) * 1e-3
+                ach = algo[k["kernel"]] / t / 1e9
+                r = {"kernel": k["kernel"], "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo[k["kernel"]], "us_per_launch": k["us_per_launch"]}
+                if k["kernel"] in notes:
+                    r["note"] = notes[k["kernel"]]
+                roofs.append(r)
+        dominant = roofs[0] if roofs else None      # kernels are sorted by total device time
+        others = roofs[1:]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_plain / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -358,9 +351,9 @@ def main_gpu(args, rank, world, local_rank):
                 "units_per_step": {"cloud_atom_sphere_voxels": cloud_units, "region_atom_sphere_voxels": region_pairs,
                                    "region_union_voxels": region_union, "blob_ccl_voxels": blob_units,
                                    "foreground_voxels": n_fg, "blobs": n_blob},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "roofline": dominant, "roofline_other": [r for r in (roof, sphere) if r is not dominant and r],
+                "gpu_launches": int(launches), "roofline": dominant, "roofline_other": others,
                 "kernels": kernels[:12], "ms_per_step_profiled": ms_total / args.steps, "clocks": clocks}
         if world == 1 and not args.no_cpu:
             _, cpu, _ = run_cpu_sample(1, 0)
