@@ -123,6 +123,9 @@ int pe_crs2xyz(const pe_geom *g, int64_t n, const int32_t *d_crs, double *d_xyz,
  * d_ws: >= pe_sphere_workspace_bytes(n_atoms) bytes. */
 #define PE_SPHERE_NOUT 8
 int64_t pe_sphere_workspace_bytes(int64_t n_atoms);
+/* Diagnostic: SM cycles of the grouped (union) kernel by phase -- prologue, membership, gather, epilogue -- summed
+ * over all CTAs since the last call; synchronises and resets. */
+int pe_sphere_union_cycles(unsigned long long *out4);
 int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const double *d_xyz,
                    const float *d_radius, int32_t n_groups, const int32_t *d_group_start, float cut_pos,
                    float cut_neg, double *d_out, void *d_ws, void *stream);
@@ -165,6 +168,9 @@ int pe_sphere_fill(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
  *   d_stats[(k*cap_blobs + b)*8 ..] = n, sum rho, sum rho*x, sum rho*y, sum rho*z, sum x, sum y, sum z  (float64)
  * d_ws: >= pe_blob_workspace_bytes(g, cap_voxels) bytes. */
 int64_t pe_blob_workspace_bytes(const pe_geom *g, int64_t cap_voxels);
+/* Diagnostic: device timestamps (ns) at the stage boundaries of the most recent sparse-stage kernel
+ * (start, after each of its grid barriers, end); synchronises. */
+int pe_blob_stage_times(unsigned long long *out12);
 int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut_neg, int64_t cap_voxels,
                   int64_t cap_blobs, int64_t *d_counts, uint32_t *d_key, float *d_value, int32_t *d_label,
                   double *d_stats, void *d_ws, void *stream);

@@ -60,10 +60,12 @@ SIGNATURES = {
     "pe_xyz2crs": (ctypes.c_int, [_GEOM, _I64, _P, _P, _P]),
     "pe_crs2xyz": (ctypes.c_int, [_GEOM, _I64, _P, _P, _P]),
     "pe_sphere_workspace_bytes": (_I64, [_I64]),
+    "pe_sphere_union_cycles": (ctypes.c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "pe_sphere_sums": (ctypes.c_int, [_GEOM, _P, _I32, _P, _P, _I32, _P, _F32, _F32, _P, _P, _P]),
     "pe_sphere_count": (ctypes.c_int, [_GEOM, _P, _I32, _P, _P, _F32, _P, _P, _P]),
     "pe_sphere_fill": (ctypes.c_int, [_GEOM, _P, _I32, _P, _P, _F32, _P, _I32, _P, _P, _P, _P]),
     "pe_blob_workspace_bytes": (_I64, [_GEOM, _I64]),
+    "pe_blob_stage_times": (ctypes.c_int, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "pe_blob_label": (ctypes.c_int, [_GEOM, _P, _F32, _F32, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "pe_cluster_workspace_bytes": (_I64, [_I64]),
     "pe_cluster_crs": (ctypes.c_int, [_I64, _P, _P, _P, _P, _P]),

@@ -19,21 +19,27 @@
 // 4 adjacent columns of one row and walks 32 sections, so the 32 loads it issues are independent 16-byte loads
 // that are contiguous across the warp (512 B per warp per section), and the word it builds is complete in
 // registers.
+#include <stdlib.h>
+#include <cooperative_groups.h>
 #include "pe_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pe {
 
 constexpr int kBmpTx = 32;         // threads along columns (x VEC columns each)
 constexpr int kBmpTy = 8;          // threads along rows
 constexpr int kChunkWords = 4;     // 32-section words per thread (grid.z splits the section axis)
-constexpr int kSparseThreads = 256;
+constexpr int kSparseThreads = 512;
+constexpr int kSparseMaxBlocks = 1024;  // size of the per-block partial-sum arrays
 
 struct BlobPlan {
-    int U0, U1, U2, W;   // unique columns, rows, sections; words per (column,row)
-    int64_t nwords;      // U0*U1*W per class
-    int64_t cap;         // foreground capacity per class
-    // workspace carve-up (per class k: base + k*stride)
-    int64_t off_bmp, off_base, off_parent, off_flag, off_rank, off_scan, total;
+    int U0, U1, U2, W;    // unique columns, rows, sections; words per (column,row)
+    int64_t nwords;       // U0*U1*W words per class
+    int64_t nwords_pad;   // the same rounded up to 64: distance between the two bit planes
+    int64_t cap;          // foreground capacity per class
+    // workspace carve-up
+    int64_t off_bmp, off_base, off_parent, off_rank, off_sums, total;
 };
 
 static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
@@ -43,21 +49,19 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
     p.U2 = g->unique_ncrs[2];
     p.W = (p.U2 + 31) / 32;
     p.nwords = (int64_t)p.U0 * p.U1 * p.W;
+    p.nwords_pad = align_up(p.nwords, 64);
     p.cap = cap;
     int64_t o = 0;
     p.off_bmp = o;
-    o += 2 * align_up(p.nwords * 4, 256);
+    o += align_up(2 * p.nwords_pad * 4, 256);
     p.off_base = o;
-    o += 2 * align_up(p.nwords * 4, 256);
+    o += align_up(2 * p.nwords_pad * 4, 256);
     p.off_parent = o;
-    o += 2 * align_up(cap * 4, 256);
-    p.off_flag = o;
-    o += 2 * align_up(cap * 4, 256);
+    o += align_up(2 * cap * 4, 256);
     p.off_rank = o;
-    o += 2 * align_up(cap * 4, 256);
-    p.off_scan = o;
-    const int64_t larger = p.nwords > cap ? p.nwords : cap;
-    o += scan_ws_bytes(larger);
+    o += align_up(2 * cap * 4, 256);
+    p.off_sums = o;
+    o += align_up(2 * kSparseMaxBlocks * 4, 256);
     p.total = o;
     return p;
 }
@@ -70,6 +74,15 @@ __global__ void __launch_bounds__(kBmpTx *kBmpTy)
                             uint32_t *__restrict__ bmp_neg) {
     const int c = (blockIdx.x * kBmpTx + threadIdx.x) * VEC;
     const int r = blockIdx.y * kBmpTy + threadIdx.y;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0) {  // padding between / after the planes
+        const int64_t nwords = (int64_t)U0 * U1 * W;
+        for (int64_t i = nwords + threadIdx.x; i < nwords + 64; i += kBmpTx) {
+            if (i < (nwords + 63) / 64 * 64) {
+                bmp_pos[i] = 0u;
+                bmp_neg[i] = 0u;
+            }
+        }
+    }
     if (c >= U0 || r >= U1) return;
     const int w_begin = blockIdx.z * kChunkWords;
     const int w_end = min(W, w_begin + kChunkWords);
@@ -131,59 +144,88 @@ __global__ void __launch_bounds__(kBmpTx *kBmpTy)
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K3: sparse init
-// One thread per bitmap word: writes key / density / initial parent for each of its set bits.
-__global__ void __launch_bounds__(kSparseThreads)
-    blob_init_kernel(const float *__restrict__ rho, int NC, int NR, int U1, int U2, int W, int64_t nwords, int64_t cap,
-                     const uint32_t *__restrict__ bmp, const uint32_t *__restrict__ base, const int64_t *__restrict__ d_nfg,
-                     int64_t *__restrict__ d_overflow, uint32_t *__restrict__ key, float *__restrict__ value,
-                     uint32_t *__restrict__ parent) {
-    if (*d_nfg > cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) *d_overflow = 1;
-        return;
-    }
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t widx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; widx < nwords; widx += stride) {
-        uint32_t word = bmp[widx];
-        if (!word) continue;
-        const int w = (int)(widx % W);
-        const int64_t colrow = widx / W;
-        const int r = (int)(colrow % U1), c = (int)(colrow / U1);
-        const bool prev_last = (w > 0) && (bmp[widx - 1] >> 31);
-        const uint32_t linked = (word << 1) | (prev_last ? 1u : 0u);  // bit b set: voxel b-1 of this column is foreground
-        uint32_t p = base[widx];
-        const uint32_t keybase = (uint32_t)(colrow * U2 + (int64_t)w * 32);
-        uint32_t rest = word;
-        while (rest) {
-            const int b = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const int s = w * 32 + b;
-            key[p] = keybase + (uint32_t)b;
-            value[p] = __ldg(rho + ((int64_t)s * NR + r) * NC + c);
-            parent[p] = ((linked >> b) & 1u) ? p - 1 : p;
-            ++p;
-        }
+// ------------------------------------------------------------------------------------------------ sparse stage
+// Everything after the streaming kernel touches only the bit planes and the sparse foreground, for BOTH signs at
+// once: the planes are scanned as one concatenated word array, so green voxels occupy positions [0, n0) and red
+// voxels [n0, n0 + n1) of one index space, and one union-find / one root ranking serves both.  The stages are
+// separated by grid-wide barriers inside ONE cooperative kernel (grid = resident blocks, cg::grid_group::sync)
+// instead of ten tiny launches per sign.
+// Stage boundaries of the last blob_sparse_kernel launch (globaltimer ns, written by block 0): a cheap built-in
+// diagnostic, read with pe_blob_stage_times().
+__device__ unsigned long long g_stage_ns[12];
+__device__ __forceinline__ void stamp(int i) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_stage_ns[i] = t;
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K4: merge
+struct SparseArgs {
+    const float *rho;
+    int NC, NR, U1, U2, W;
+    int64_t nwords, nwords_pad, cap, cap_blobs;
+    const uint32_t *bmp;   // two planes, nwords_pad apart
+    uint32_t *base;        // per word: position of its first set bit in the concatenated voxel list
+    uint32_t *parent;      // 2 * cap
+    uint32_t *rank;        // 2 * cap (valid at roots)
+    uint32_t *sums;        // 2 * kSparseMaxBlocks block partials
+    int64_t *counts;       // n_fg0, n_blobs0, n_fg1, n_blobs1, overflow
+    uint32_t *key;         // outputs, class k at k * cap
+    float *value;
+    int32_t *label;
+    double *stats;         // class k at k * cap_blobs * 8
+    bool use_pos, use_neg;
+    int debug;
+};
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *smem /* >= 32 */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = (uint32_t)warp_sum((int)v);
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += smem[i];
+    return t;
+}
+
+// Exclusive prefix of sums[0 .. nb) at index b (every block scans the few hundred partials itself).
+__device__ __forceinline__ void grid_prefix(const uint32_t *sums, int nb, int b, uint32_t *smem, uint32_t &before, uint32_t &total) {
+    uint32_t mine = 0, all = 0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const uint32_t v = sums[i];
+        all += v;
+        if (i < b) mine += v;
+    }
+    before = block_sum_u32(mine, smem);
+    total = block_sum_u32(all, smem);
+}
+
+__device__ int g_debug_sink;
 __device__ __forceinline__ void merge_with_column(uint32_t *parent, const uint32_t *__restrict__ bmp,
                                                   const uint32_t *__restrict__ base, int64_t nwidx, int w, int b, int W,
-                                                  uint32_t p) {
+                                                  uint32_t p, int debug = 0) {
     const uint32_t B = bmp[nwidx];
+    if (debug == 2) {
+        if (B == 0xdeadbeefu) g_debug_sink = 1;
+        return;
+    }
+    if (debug == 1) {
+        if (B && base[nwidx] == 0xdeadbeefu) g_debug_sink = 1;
+        return;
+    }
     if ((B >> b) & 1u) {  // same section: its s-1 / s+1 neighbours are chained to it already
         uf_union(parent, p, base[nwidx] + (uint32_t)__popc(B & ((1u << b) - 1u)));
         return;
     }
-    // section s-1
-    if (b > 0) {
+    if (b > 0) {  // section s-1
         if ((B >> (b - 1)) & 1u) uf_union(parent, p, base[nwidx] + (uint32_t)__popc(B & ((1u << (b - 1)) - 1u)));
     } else if (w > 0) {
         const uint32_t Bm = bmp[nwidx - 1];
         if (Bm >> 31) uf_union(parent, p, base[nwidx - 1] + (uint32_t)__popc(Bm & 0x7fffffffu));
     }
-    // section s+1
-    if (b < 31) {
+    if (b < 31) {  // section s+1
         if ((B >> (b + 1)) & 1u) uf_union(parent, p, base[nwidx] + (uint32_t)__popc(B & ((1u << (b + 1)) - 1u)));
     } else if (w + 1 < W) {
         const uint32_t Bp = bmp[nwidx + 1];
@@ -191,84 +233,200 @@ __device__ __forceinline__ void merge_with_column(uint32_t *parent, const uint32
     }
 }
 
-__global__ void __launch_bounds__(kSparseThreads)
-    blob_merge_kernel(int U1, int U2, int W, int64_t cap, const uint32_t *__restrict__ bmp, const uint32_t *__restrict__ base,
-                      const int64_t *__restrict__ d_nfg, const uint32_t *__restrict__ key, uint32_t *parent) {
-    const int64_t n = *d_nfg;
-    if (n > cap) return;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t p = (uint32_t)i;
-        const uint32_t k = key[p];
-        const int s = (int)(k % (uint32_t)U2);
-        const uint32_t colrow = k / (uint32_t)U2;
-        const int r = (int)(colrow % (uint32_t)U1), c = (int)(colrow / (uint32_t)U1);
-        const int w = s >> 5, b = s & 31;
-        // the 12 predecessor neighbours outside the voxel's own column: columns (c-1, r-1..r+1) and (c, r-1)
-        if (c > 0) {
-            const int64_t rowbase = (int64_t)(c - 1) * U1;
-            if (r > 0) merge_with_column(parent, bmp, base, (rowbase + r - 1) * W + w, w, b, W, p);
-            merge_with_column(parent, bmp, base, (rowbase + r) * W + w, w, b, W, p);
-            if (r + 1 < U1) merge_with_column(parent, bmp, base, (rowbase + r + 1) * W + w, w, b, W, p);
+__global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __grid_constant__ pe_geom g, const SparseArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t smem[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = gridDim.x, b = blockIdx.x;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t total_words = 2 * a.nwords_pad;
+    // contiguous word segment of this warp (multiple of 32 words)
+    const int64_t nwarps = (int64_t)nb * warps_per_block;
+    const int64_t seg = (((total_words + nwarps - 1) / nwarps) + 31) / 32 * 32;
+    const int64_t gw = (int64_t)b * warps_per_block + warp;
+    const int64_t w_begin = min(gw * seg, total_words), w_end = min(w_begin + seg, total_words);
+    stamp(0);
+
+    // ---- S1a: popcount of every warp segment -> block partials
+    uint32_t cnt = 0;
+    for (int64_t i = w_begin + lane; i < w_end; i += 32) cnt += (uint32_t)__popc(a.bmp[i]);
+    const uint32_t warp_cnt = (uint32_t)warp_sum((int)cnt);
+    __shared__ uint32_t warp_cnts[32];
+    if (lane == 0) warp_cnts[warp] = warp_cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < warps_per_block; ++i) t += warp_cnts[i];
+        a.sums[b] = t;
+    }
+    grid.sync();
+    stamp(1);
+
+    // ---- S1b + S2: positions, then key / value / initial parent of every foreground voxel
+    uint32_t before, n_all;
+    grid_prefix(a.sums, nb, b, smem, before, n_all);
+    // class 0 count = positions below the first word of plane 1; found by whoever owns that word (see below)
+    uint32_t run = before;
+    for (int i = 0; i < warp; ++i) run += warp_cnts[i];
+    __shared__ int s_overflow;
+    for (int64_t i0 = w_begin; i0 < w_end; i0 += 32) {
+        const int64_t widx = i0 + lane;
+        const uint32_t word = widx < w_end ? a.bmp[widx] : 0u;
+        const int c0 = __popc(word);
+        const uint32_t p0 = run + (uint32_t)warp_excl_scan(c0, lane);
+        run += (uint32_t)__shfl_sync(kFull, (int)(p0 - run) + c0, 31);
+        if (widx < w_end) {
+            a.base[widx] = p0;
+            if (widx == a.nwords_pad) a.counts[0] = (int64_t)p0;  // everything before plane 1 is class 0
         }
-        if (r > 0) merge_with_column(parent, bmp, base, ((int64_t)c * U1 + r - 1) * W + w, w, b, W, p);
     }
-}
-
-// ------------------------------------------------------------------------------------------------ K5: flatten
-__global__ void __launch_bounds__(kSparseThreads)
-    blob_flatten_kernel(int64_t cap, const int64_t *__restrict__ d_nfg, uint32_t *parent, uint32_t *__restrict__ flag) {
-    const int64_t n = *d_nfg;
-    if (n > cap) return;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t root = uf_find(parent, (uint32_t)i);
-        parent[i] = root;
-        flag[i] = root == (uint32_t)i ? 1u : 0u;
+    if (b == 0 && threadIdx.x == 0) a.counts[2] = (int64_t)n_all;  // provisional: total; fixed up after the barrier
+    grid.sync();
+    stamp(2);
+    const int64_t n0 = a.counts[0];
+    const int64_t n = (int64_t)n_all;
+    const int64_t n1 = n - n0;
+    const bool overflow = n0 > a.cap || n1 > a.cap;
+    if (b == 0 && threadIdx.x == 0) {
+        a.counts[2] = n1;
+        if (overflow) a.counts[4] = 1;
     }
-}
-
-__global__ void __launch_bounds__(kSparseThreads)
-    blob_zero_stats_kernel(int64_t cap_blobs, const int64_t *__restrict__ d_nblobs, int64_t *__restrict__ d_overflow,
-                           double *__restrict__ stats) {
-    int64_t n = *d_nblobs;
-    if (n > cap_blobs) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) *d_overflow = 1;
-        n = cap_blobs;
+    if (overflow) return;  // grid-uniform
+    (void)s_overflow;
+    for (int64_t i0 = w_begin; i0 < w_end; i0 += 32) {
+        const int64_t widx = i0 + lane;
+        if (widx >= w_end) continue;
+        uint32_t word = a.bmp[widx];
+        if (!word) continue;
+        const int k = widx >= a.nwords_pad ? 1 : 0;
+        const int64_t local = widx - (k ? a.nwords_pad : 0);
+        const int w = (int)(local % a.W);
+        const int64_t colrow = local / a.W;
+        const int r = (int)(colrow % a.U1), c = (int)(colrow / a.U1);
+        const bool prev_last = (w > 0) && (a.bmp[widx - 1] >> 31);
+        // bits that start a run of consecutive sections inside this word (a run entering from the previous word
+        // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
+        const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
+        const uint32_t p_first = a.base[widx];
+        uint32_t p = p_first;
+        const uint32_t keybase = (uint32_t)(colrow * a.U2 + (int64_t)w * 32);
+        const int64_t out0 = (int64_t)k * a.cap - (k ? n0 : 0);
+        const uint32_t all = word;
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            const int s = w * 32 + bit;
+            a.key[out0 + p] = keybase + (uint32_t)bit;
+            a.value[out0 + p] = __ldg(a.rho + ((int64_t)s * a.NR + r) * a.NC + c);
+            // parent = first voxel of the run (path-compressed chaining: finds stay O(1) instead of O(run length))
+            const uint32_t below = starts & ((2u << bit) - 1u);
+            uint32_t par;
+            if (below) {
+                const int sb = 31 - __clz(below);
+                par = p_first + (uint32_t)__popc(all & ((1u << sb) - 1u));
+            } else {
+                par = p_first - 1;  // the run continues from the previous word (prev_last is set)
+            }
+            a.parent[p] = par;
+            ++p;
+        }
     }
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 8; i += stride) stats[i] = 0.0;
-}
+    grid.sync();
+    stamp(3);
 
-// ------------------------------------------------------------------------------------------------ K7: labels + stats
-// label[p] = rank of p's root; per-blob sums of DensityBlob.fromCrsList (pdb_eda/ccp4.py:534-545).  Lanes that hold
-// consecutive voxels of one blob (the common case: runs along the section axis) are combined by a segmented warp
-// reduction before the float64 atomics.
-__global__ void __launch_bounds__(kSparseThreads)
-    blob_stats_kernel(const __grid_constant__ pe_geom g, int64_t cap, int64_t cap_blobs, const int64_t *__restrict__ d_nfg,
-                      const uint32_t *__restrict__ key, const float *__restrict__ value, const uint32_t *__restrict__ parent,
-                      const uint32_t *__restrict__ rank, int32_t *__restrict__ label, double *__restrict__ stats) {
-    const int64_t n = *d_nfg;
-    if (n > cap) return;
-    const int U1 = g.unique_ncrs[1], U2 = g.unique_ncrs[2];
-    const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i0 = start - lane; i0 < n; i0 += stride) {  // warp-uniform trip count
+    // ---- S3: hook the 12 predecessor neighbours outside the voxel's own column
+    const int64_t gstride = (int64_t)nb * blockDim.x;
+    const int64_t gtid = (int64_t)b * blockDim.x + threadIdx.x;
+    for (int64_t i = gtid; i < n; i += gstride) {
+        const int k = i >= n0 ? 1 : 0;
+        const uint32_t p = (uint32_t)i;
+        const uint32_t kk = a.key[(int64_t)k * a.cap + (i - (k ? n0 : 0))];
+        const int s = (int)(kk % (uint32_t)a.U2);
+        const uint32_t colrow = kk / (uint32_t)a.U2;
+        const int r = (int)(colrow % (uint32_t)a.U1), c = (int)(colrow / (uint32_t)a.U1);
+        const int w = s >> 5, bit = s & 31;
+        const uint32_t *bmp = a.bmp + (k ? a.nwords_pad : 0);
+        const uint32_t *base = a.base + (k ? a.nwords_pad : 0);
+        if (c > 0) {
+            const int64_t rowbase = (int64_t)(c - 1) * a.U1;
+            if (r > 0) merge_with_column(a.parent, bmp, base, (rowbase + r - 1) * a.W + w, w, bit, a.W, p, a.debug);
+            merge_with_column(a.parent, bmp, base, (rowbase + r) * a.W + w, w, bit, a.W, p, a.debug);
+            if (r + 1 < a.U1) merge_with_column(a.parent, bmp, base, (rowbase + r + 1) * a.W + w, w, bit, a.W, p, a.debug);
+        }
+        if (r > 0) merge_with_column(a.parent, bmp, base, ((int64_t)c * a.U1 + r - 1) * a.W + w, w, bit, a.W, p, a.debug);
+    }
+    grid.sync();
+    stamp(4);
+
+    // ---- S4: flatten; S5: rank the roots (blob number = rank of the blob's first voxel)
+    const int64_t vseg = (((n + nwarps - 1) / nwarps) + 31) / 32 * 32;
+    const int64_t v_begin = min(gw * vseg, n), v_end = min(v_begin + vseg, n);
+    uint32_t roots = 0;
+    for (int64_t i = v_begin + lane; i < v_end; i += 32) {
+        const uint32_t root = uf_find(a.parent, (uint32_t)i);
+        a.parent[i] = root;  // still a valid ancestor for concurrent finds
+        roots += root == (uint32_t)i ? 1u : 0u;
+    }
+    const uint32_t warp_roots = (uint32_t)warp_sum((int)roots);
+    __syncthreads();
+    if (lane == 0) warp_cnts[warp] = warp_roots;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < warps_per_block; ++i) t += warp_cnts[i];
+        a.sums[kSparseMaxBlocks + b] = t;
+    }
+    grid.sync();
+    stamp(5);
+    uint32_t roots_before, n_roots;
+    grid_prefix(a.sums + kSparseMaxBlocks, nb, b, smem, roots_before, n_roots);
+    uint32_t rrun = roots_before;
+    for (int i = 0; i < warp; ++i) rrun += warp_cnts[i];
+    for (int64_t i0 = v_begin; i0 < v_end; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const int isroot = (i < v_end && a.parent[i] == (uint32_t)i) ? 1 : 0;
+        const uint32_t ex = rrun + (uint32_t)warp_excl_scan(isroot, lane);
+        if (isroot) a.rank[i] = ex;
+        if (i < v_end && i == n0) a.counts[1] = (int64_t)ex;  // roots among the class-0 voxels
+        rrun += (uint32_t)__shfl_sync(kFull, (int)(ex - rrun) + isroot, 31);
+    }
+    if (b == 0 && threadIdx.x == 0 && n0 == n) a.counts[1] = (int64_t)n_roots;
+    grid.sync();
+    stamp(6);
+    const int64_t nb0 = a.counts[1];
+    const int64_t nb1 = (int64_t)n_roots - nb0;
+    if (b == 0 && threadIdx.x == 0) a.counts[3] = nb1;
+    const bool blob_overflow = nb0 > a.cap_blobs || nb1 > a.cap_blobs;
+    if (blob_overflow) {
+        if (b == 0 && threadIdx.x == 0) a.counts[4] = 1;
+        return;  // grid-uniform
+    }
+
+    // ---- S6: zero the per-blob sums, then labels + sums (DensityBlob.fromCrsList, pdb_eda/ccp4.py:534-545)
+    for (int64_t i = gtid; i < nb0 * 8; i += gstride) a.stats[i] = 0.0;
+    for (int64_t i = gtid; i < nb1 * 8; i += gstride) a.stats[a.cap_blobs * 8 + i] = 0.0;
+    grid.sync();
+    stamp(7);
+    for (int64_t i0 = gtid - lane; i0 < n; i0 += gstride) {  // warp-uniform trip count
         const int64_t i = i0 + lane;
         const bool live = i < n;
         int32_t blob = -1;
+        int k = 0;
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (live) {
-            blob = (int32_t)rank[parent[i]];
-            label[i] = blob;
-            const uint32_t k = key[i];
-            const int s = (int)(k % (uint32_t)U2);
-            const uint32_t colrow = k / (uint32_t)U2;
-            const int r = (int)(colrow % (uint32_t)U1), c = (int)(colrow / (uint32_t)U1);
+            k = i >= n0 ? 1 : 0;
+            const int64_t oi = (int64_t)k * a.cap + (i - (k ? n0 : 0));
+            const uint32_t gr = a.rank[a.parent[i]];
+            blob = (int32_t)(gr - (k ? (uint32_t)nb0 : 0u));
+            a.label[oi] = blob;
+            blob += k ? (int32_t)a.cap_blobs : 0;  // row of the combined stats table
+            const uint32_t kk = a.key[oi];
+            const int s = (int)(kk % (uint32_t)a.U2);
+            const uint32_t colrow = kk / (uint32_t)a.U2;
+            const int r = (int)(colrow % (uint32_t)a.U1), c = (int)(colrow / (uint32_t)a.U1);
             double x, y, z;
             crs2xyz(g, c, r, s, x, y, z);
-            const double d = (double)value[i];
+            const double d = (double)a.value[oi];
             v[0] = 1.0;
             v[1] = d;
             v[2] = __dmul_rn(d, x);
@@ -278,36 +436,41 @@ __global__ void __launch_bounds__(kSparseThreads)
             v[6] = y;
             v[7] = z;
         }
-        // segmented reduction over runs of equal blob id
+        // segmented reduction over runs of equal blob id (runs along the section axis are the common case)
         const int32_t prev = __shfl_up_sync(kFull, blob, 1);
         const bool head = (lane == 0) || (prev != blob);
         const unsigned heads = __ballot_sync(kFull, head);
-        const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));  // run number of this lane (1-based)
+        const int segno = __popc(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int seg_o = __shfl_down_sync(kFull, seg, o);
-            const bool take = (lane + o < 32) && (seg_o == seg);
+            const int seg_o = __shfl_down_sync(kFull, segno, o);
+            const bool take = (lane + o < 32) && (seg_o == segno);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const double other = __shfl_down_sync(kFull, v[q], o);
                 if (take) v[q] += other;
             }
         }
-        if (live && head && blob < cap_blobs) {
-            double *st = stats + (int64_t)blob * 8;
+        if (live && head) {
+            double *st = a.stats + (int64_t)blob * 8;
 #pragma unroll
             for (int q = 0; q < 8; ++q) atomicAdd(st + q, v[q]);
         }
     }
+    stamp(8);
 }
-
-static int sparse_grid() { return sm_count() * 8; }
 
 }  // namespace pe
 
 using namespace pe;
 
 extern "C" {
+
+int pe_blob_stage_times(unsigned long long *out12) {
+    PE_CHECK_ARG(out12 != nullptr, "pe_blob_stage_times: null pointer");
+    PE_CUDA(cudaMemcpyFromSymbol(out12, g_stage_ns, sizeof(unsigned long long) * 12));
+    return PE_OK;
+}
 
 int64_t pe_blob_workspace_bytes(const pe_geom *g, int64_t cap_voxels) {
     if (!g || cap_voxels < 0) return -1;
@@ -320,7 +483,7 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     if (int rc = check_geom(g)) return rc;
     PE_CHECK_ARG(d_rho && d_counts && d_key && d_value && d_label && d_stats && d_ws, "pe_blob_label: null pointer");
     PE_CHECK_ARG(cap_voxels > 0 && cap_blobs > 0, "pe_blob_label: capacities must be positive");
-    PE_CHECK_ARG(cap_voxels < (1ll << 31), "pe_blob_label: cap_voxels must be below 2^31");
+    PE_CHECK_ARG(cap_voxels < (1ll << 30), "pe_blob_label: cap_voxels must be below 2^30");
     PE_CHECK_ARG(!(cut_pos < 0.f) && !(cut_neg > 0.f), "pe_blob_label: cut_pos must be >= 0 and cut_neg <= 0");
     PE_CHECK_ARG(cut_pos == cut_pos && cut_neg == cut_neg, "pe_blob_label: NaN cutoff");
     const BlobPlan p = make_plan(g, cap_voxels);
@@ -328,16 +491,7 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)d_ws;
     const int NC = g->ncrs[0], NR = g->ncrs[1];
-    const int64_t bmp_stride = align_up(p.nwords * 4, 256), cap_stride = align_up(p.cap * 4, 256);
-    uint32_t *bmp[2], *base[2], *parent[2], *flag[2], *rank[2];
-    for (int k = 0; k < 2; ++k) {
-        bmp[k] = (uint32_t *)(ws + p.off_bmp + k * bmp_stride);
-        base[k] = (uint32_t *)(ws + p.off_base + k * bmp_stride);
-        parent[k] = (uint32_t *)(ws + p.off_parent + k * cap_stride);
-        flag[k] = (uint32_t *)(ws + p.off_flag + k * cap_stride);
-        rank[k] = (uint32_t *)(ws + p.off_rank + k * cap_stride);
-    }
-    void *scan_ws = ws + p.off_scan;
+    uint32_t *bmp = (uint32_t *)(ws + p.off_bmp);
     const bool use_pos = cut_pos > 0.f, use_neg = cut_neg < 0.f;
 
     PE_CUDA(cudaMemsetAsync(d_counts, 0, 5 * sizeof(int64_t), st));
@@ -349,34 +503,50 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         dim3 grid((p.U0 + kBmpTx * vec - 1) / (kBmpTx * vec), (p.U1 + kBmpTy - 1) / kBmpTy, (p.W + kChunkWords - 1) / kChunkWords);
         PE_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "pe_blob_label: map too large for the launch grid");
         if (vec4)
-            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos,
-                                                               use_neg, bmp[0], bmp[1]));
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(
+                d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
         else
-            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos,
-                                                               use_neg, bmp[0], bmp[1]));
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(
+                d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
         PE_LAUNCH_CHECK();
     }
-    const int sg = sparse_grid();
-    for (int k = 0; k < 2; ++k) {
-        if (!(k == 0 ? use_pos : use_neg)) continue;
-        int64_t *d_nfg = d_counts + 2 * k, *d_nblobs = d_counts + 2 * k + 1, *d_overflow = d_counts + 4;
-        uint32_t *key = d_key + (int64_t)k * cap_voxels;
-        float *value = d_value + (int64_t)k * cap_voxels;
-        int32_t *label = d_label + (int64_t)k * cap_voxels;
-        double *stats = d_stats + (int64_t)k * cap_blobs * 8;
-        // K2: position of every foreground voxel in the reference's list order
-        if (int rc = exclusive_scan_u32(bmp[k], base[k], p.nwords, nullptr, d_nfg, scan_ws, st, true)) return rc;
-        PE_LAUNCH("blob_init_kernel", st, blob_init_kernel<<<sg, kSparseThreads, 0, st>>>(d_rho, NC, NR, p.U1, p.U2, p.W, p.nwords, p.cap, bmp[k], base[k], d_nfg,
-                                                        d_overflow, key, value, parent[k]));
-        PE_LAUNCH("blob_merge_kernel", st, blob_merge_kernel<<<sg, kSparseThreads, 0, st>>>(p.U1, p.U2, p.W, p.cap, bmp[k], base[k], d_nfg, key, parent[k]));
-        PE_LAUNCH("blob_flatten_kernel", st, blob_flatten_kernel<<<sg, kSparseThreads, 0, st>>>(p.cap, d_nfg, parent[k], flag[k]));
-        PE_LAUNCH_CHECK();
-        // K6: blob number = rank of its root among roots
-        if (int rc = exclusive_scan_u32(flag[k], rank[k], p.cap, d_nfg, d_nblobs, scan_ws, st, false)) return rc;
-        PE_LAUNCH("blob_zero_stats_kernel", st, blob_zero_stats_kernel<<<sg, kSparseThreads, 0, st>>>(cap_blobs, d_nblobs, d_overflow, stats));
-        PE_LAUNCH("blob_stats_kernel", st, blob_stats_kernel<<<sg, kSparseThreads, 0, st>>>(*g, p.cap, cap_blobs, d_nfg, key, value, parent[k], rank[k], label, stats));
-        PE_LAUNCH_CHECK();
+    // sparse stage: one cooperative kernel for both signs
+    SparseArgs a;
+    a.rho = d_rho;
+    a.NC = NC;
+    a.NR = NR;
+    a.U1 = p.U1;
+    a.U2 = p.U2;
+    a.W = p.W;
+    a.nwords = p.nwords;
+    a.nwords_pad = p.nwords_pad;
+    a.cap = p.cap;
+    a.cap_blobs = cap_blobs;
+    a.bmp = bmp;
+    a.base = (uint32_t *)(ws + p.off_base);
+    a.parent = (uint32_t *)(ws + p.off_parent);
+    a.rank = (uint32_t *)(ws + p.off_rank);
+    a.sums = (uint32_t *)(ws + p.off_sums);
+    a.counts = d_counts;
+    a.key = d_key;
+    a.value = d_value;
+    a.label = d_label;
+    a.stats = d_stats;
+    a.use_pos = use_pos;
+    a.use_neg = use_neg;
+    a.debug = getenv("PE_BLOB_DEBUG") ? atoi(getenv("PE_BLOB_DEBUG")) : 0;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, blob_sparse_kernel, kSparseThreads, 0));
+        PE_CHECK_ARG(blocks_per_sm > 0, "pe_blob_label: the sparse kernel does not fit an SM");
     }
+    int nblocks = sm_count() * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    if (nblocks > kSparseMaxBlocks) nblocks = kSparseMaxBlocks;
+    pe_geom geom = *g;
+    void *args[] = {(void *)&geom, (void *)&a};
+    PE_LAUNCH("blob_sparse_kernel", st,
+              PE_CUDA(cudaLaunchCooperativeKernel((const void *)blob_sparse_kernel, dim3(nblocks), dim3(kSparseThreads), args, 0, st)));
+    PE_LAUNCH_CHECK();
     return PE_OK;
 }
 

@@ -184,17 +184,30 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane) {
 // Lock-free union-find over uint32 node ids; a root is always the smallest id of its set, which is what makes
 // the labels canonical (blob number = rank of the blob's first voxel in the reference's scan order).
 __device__ __forceinline__ uint32_t uf_find(const uint32_t *parent, uint32_t x) {
-    uint32_t p = parent[x];
+    uint32_t p = __ldcg(parent + x);
     while (p != x) {
         x = p;
-        p = parent[x];
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+// find with path halving: every visited node is re-pointed at its grandparent.  The plain stores race with the
+// atomicMin hooks benignly: a node only ever points at a smaller id of its own (eventual) set, and a thread whose
+// hook is overwritten carries on uniting the roots it saw (see uf_union).
+__device__ __forceinline__ uint32_t uf_find_halve(uint32_t *parent, uint32_t x) {
+    uint32_t p = __ldcg(parent + x);
+    while (p != x) {
+        const uint32_t gp = __ldcg(parent + p);
+        if (gp != p) __stcg(parent + x, gp);
+        x = p;
+        p = gp;
     }
     return x;
 }
 __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b) {
     for (;;) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find_halve(parent, a);
+        b = uf_find_halve(parent, b);
         if (a == b) return;
         if (a < b) {
             const uint32_t t = a;

@@ -347,6 +347,10 @@ __device__ __forceinline__ void union_mark_generic(const pe_geom &g, const AtomB
     }
 }
 
+// Diagnostic: SM cycles spent per phase, summed over all CTAs of the launches since the last read
+// (prologue, membership, gather, epilogue); read and reset with pe_sphere_union_cycles().
+__device__ unsigned long long g_union_cycles[4];
+
 template <int MODE>
 __global__ void __launch_bounds__(kUnionWarps * 32, 7)
     sphere_union_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_groups,
@@ -359,6 +363,8 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
     const int grp = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a0 = group_start[grp], a1 = group_start[grp + 1];
+    long long t_mark = clock64();
+    long long t_phase[4] = {0, 0, 0, 0};
     cp = eff_pos(cp);
     cn = eff_neg(cn);
     // the group's bounding box
@@ -387,6 +393,11 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                     for (int k = tid; k < tR; k += blockDim.x) sh.offR[k] = axis_off(g, 1, tr0 + k);
                     for (int k = tid; k < tS; k += blockDim.x) sh.offS[k] = axis_off(g, 2, ts0 + k);
                     __syncthreads();  // bitmap is clear, offsets are in place
+                    {
+                        const long long now = clock64();
+                        t_phase[0] += now - t_mark;
+                        t_mark = now;
+                    }
                     // phase 1: membership
                     for (int a = a0; a < a1; ++a) {
                         AtomBox b;
@@ -404,71 +415,73 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                             union_mark_generic(g, b, ax, ay, az, thr[a], tid, blockDim.x, tc0, tr0, ts0, tC, tR, tS, sh.bits);
                     }
                     __syncthreads();
-                    // phase 2: gather every voxel of the union once.  A warp owns tile rows rl = warp, warp + 4, ...
-                    // and walks their sections four at a time: the four (predicated) loads are issued back to
-                    // back before any is consumed, which is what hides the L2 latency of this gather.
                     {
-                        const int oc0 = lane < tC ? sh.offC[lane] : kInvalidOff;
-                        const int oc1 = lane + 32 < tC ? sh.offC[lane + 32] : kInvalidOff;
+                        const long long now = clock64();
+                        t_phase[1] += now - t_mark;
+                        t_mark = now;
+                    }
+                    // phase 2: gather every voxel of the union once.  A warp owns tile rows rl = warp, warp + 4, ...;
+                    // per 32 sections every lane fetches "its" (row, section) bitmap words, a ballot finds the
+                    // non-empty ones, and they are consumed four at a time: each quarter-warp walks one of them in
+                    // windows of 8 consecutive columns starting at its lowest set bit (the set bits of a row are
+                    // one or two short runs), so nearly every lane of every load carries a voxel and the 8 lanes
+                    // of a window read one 32-byte sector.
+                    {
+                        const int sg = lane >> 3, lr = lane & 7;
                         for (int rl = warp; rl < tR; rl += kUnionWarps) {
                             const int orow = sh.offR[rl];
                             uint32_t *rowbits = sh.bits + 2 * rl * kTileS;
-                            for (int sl0 = 0; sl0 < tS; sl0 += 4) {
-                                uint32_t w0[4], w1[4];
-                                uint32_t any0 = 0u, any1 = 0u;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const bool live = sl0 + j < tS;
-                                    const uint2 w = live ? *reinterpret_cast<const uint2 *>(rowbits + 2 * (sl0 + j)) : make_uint2(0u, 0u);
-                                    w0[j] = w.x;
-                                    w1[j] = w.y;
-                                    any0 |= w.x;
-                                    any1 |= w.y;
-                                }
-                                if ((any0 | any1) == 0u) continue;  // warp-uniform
-                                int ors[4];
-                                unsigned srs[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int os = sl0 + j < tS ? sh.offS[sl0 + j] : kInvalidOff;
-                                    ors[j] = orow | os;
-                                    srs[j] = (unsigned)orow + (unsigned)os;
-                                }
-                                if (any0) {
-                                    float v[4];
-                                    bool bit[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        bit[j] = (w0[j] >> lane) & 1u;
-                                        const bool ok = (ors[j] | oc0) >= 0;
-                                        v[j] = 0.f;
-                                        if (bit[j] && ok) v[j] = __ldg(rho + (int)(srs[j] + (unsigned)oc0));
-                                        acc.bad |= (bit[j] && !ok) ? 1 : 0;
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc.add(bit[j], v[j], cp, cn);
-                                }
-                                if (any1) {
-                                    float v[4];
-                                    bool bit[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        bit[j] = (w1[j] >> lane) & 1u;
-                                        const bool ok = (ors[j] | oc1) >= 0;
-                                        v[j] = 0.f;
-                                        if (bit[j] && ok) v[j] = __ldg(rho + (int)(srs[j] + (unsigned)oc1));
-                                        acc.bad |= (bit[j] && !ok) ? 1 : 0;
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc.add(bit[j], v[j], cp, cn);
-                                }
-                                __syncwarp();
-                                if (lane < 4 && sl0 + lane < tS)  // leave the bitmap clear for the next tile
+                            for (int sl0 = 0; sl0 < tS; sl0 += 32) {
+                                uint2 mine = make_uint2(0u, 0u);
+                                if (sl0 + lane < tS) mine = *reinterpret_cast<const uint2 *>(rowbits + 2 * (sl0 + lane));
+                                unsigned nz = __ballot_sync(kFull, (mine.x | mine.y) != 0u);
+                                if (nz == 0u) continue;  // warp-uniform
+                                if ((mine.x | mine.y) != 0u)  // leave the bitmap clear for the next tile
                                     *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
+                                while (nz) {
+                                    // the next (up to) four non-empty sections, one per quarter-warp
+                                    int src = -1;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int f = nz ? (__ffs(nz) - 1) : -1;
+                                        if (nz) nz &= nz - 1;
+                                        if (q == sg) src = f;
+                                    }
+                                    const uint32_t lo = __shfl_sync(kFull, mine.x, src < 0 ? 0 : src);
+                                    const uint32_t hi = __shfl_sync(kFull, mine.y, src < 0 ? 0 : src);
+                                    unsigned long long w = src < 0 ? 0ull : (((unsigned long long)hi << 32) | lo);
+                                    const int os = src < 0 ? kInvalidOff : sh.offS[sl0 + src];
+                                    const int ors = orow | os;
+                                    const unsigned srs = (unsigned)orow + (unsigned)os;
+                                    while (__any_sync(kFull, w != 0ull)) {
+                                        // two windows per trip: both loads are issued before either is consumed
+                                        float v[2];
+                                        bool bit[2];
+#pragma unroll
+                                        for (int u = 0; u < 2; ++u) {
+                                            const int first = w ? (__ffsll((long long)w) - 1) : 0;
+                                            const int col = first + lr;
+                                            bit[u] = w != 0ull && col < 64 && ((w >> col) & 1ull);
+                                            const int oc = bit[u] ? sh.offC[col] : kInvalidOff;
+                                            const bool ok = (ors | oc) >= 0;
+                                            v[u] = 0.f;
+                                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs + (unsigned)oc));
+                                            acc.bad |= (bit[u] && !ok) ? 1 : 0;
+                                            if (w) w &= ~(0xffull << first);
+                                        }
+                                        acc.add(bit[0], v[0], cp, cn);
+                                        acc.add(bit[1], v[1], cp, cn);
+                                    }
+                                }
                             }
                         }
                     }
                     __syncthreads();
+                    {
+                        const long long now = clock64();
+                        t_phase[2] += now - t_mark;
+                        t_mark = now;
+                    }
                 }
     }
     const int n_all = warp_sum(acc.n_all), n_pos = warp_sum(acc.n_pos), n_neg = warp_sum(acc.n_neg);
@@ -500,6 +513,9 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
         o[5] = sd[2];
         o[6] = ni[3] ? 0.0 : 1.0;
         o[7] = candidates;
+        t_phase[3] = clock64() - t_mark;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(g_union_cycles + k, (unsigned long long)t_phase[k]);
     }
 }
 
@@ -717,6 +733,14 @@ __global__ void sphere_fill_kernel(const __grid_constant__ pe_geom g, const floa
 using namespace pe;
 
 extern "C" {
+
+int pe_sphere_union_cycles(unsigned long long *out4) {
+    PE_CHECK_ARG(out4 != nullptr, "pe_sphere_union_cycles: null pointer");
+    PE_CUDA(cudaMemcpyFromSymbol(out4, g_union_cycles, sizeof(unsigned long long) * 4));
+    unsigned long long zero[4] = {0, 0, 0, 0};
+    PE_CUDA(cudaMemcpyToSymbol(g_union_cycles, zero, sizeof(zero)));
+    return PE_OK;
+}
 
 int64_t pe_sphere_workspace_bytes(int64_t n_atoms) {
     if (n_atoms < 0) n_atoms = 0;

@@ -49,3 +49,12 @@ print("ms/step: %.4f" % (e0.elapsed_time(e1) / steps))
 for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
     print("%-28s %4d launches %9.2f us/launch" % (name, count, ms * 1e3 / count))
 print("units:", vp.unit_counts(), "blob counts:", vp.blob_counts.tolist())
+import ctypes
+t = (ctypes.c_ulonglong * 12)()
+_lib.load().pe_blob_stage_times(t)
+t = list(t)
+print("blob sparse stages (us):", [round((t[i + 1] - t[i]) / 1e3, 1) for i in range(8)])
+u = (ctypes.c_ulonglong * 4)()
+_lib.load().pe_sphere_union_cycles(u)
+tot = float(sum(u)) or 1.0
+print("union kernel cycles by phase (prologue, membership, gather, epilogue): %s" % [round(x / tot, 3) for x in u])
