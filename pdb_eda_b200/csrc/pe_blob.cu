@@ -19,7 +19,6 @@
 // 4 adjacent columns of one row and walks 32 sections, so the 32 loads it issues are independent 16-byte loads
 // that are contiguous across the warp (512 B per warp per section), and the word it builds is complete in
 // registers.
-#include <stdlib.h>
 #include <cooperative_groups.h>
 #include "pe_common.cuh"
 
@@ -176,7 +175,6 @@ struct SparseArgs {
     int32_t *label;
     double *stats;         // class k at k * cap_blobs * 8
     bool use_pos, use_neg;
-    int debug;
 };
 
 __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *smem /* >= 32 */) {
@@ -202,34 +200,26 @@ __device__ __forceinline__ void grid_prefix(const uint32_t *sums, int nb, int b,
     total = block_sum_u32(all, smem);
 }
 
-__device__ int g_debug_sink;
-__device__ __forceinline__ void merge_with_column(uint32_t *parent, const uint32_t *__restrict__ bmp,
-                                                  const uint32_t *__restrict__ base, int64_t nwidx, int w, int b, int W,
-                                                  uint32_t p, int debug = 0) {
+// Positions of the voxels of neighbour column `nwidx` (same class) that are 26-adjacent to section bit b of word w:
+// the voxel at the same section if set (its s-1 / s+1 neighbours are chained to it already), else those at s-1 and s+1.
+__device__ __forceinline__ void neighbours_in_column(const uint32_t *__restrict__ bmp, const uint32_t *__restrict__ base,
+                                                     int64_t nwidx, int w, int b, int W, uint32_t *nb, int &cnt) {
     const uint32_t B = bmp[nwidx];
-    if (debug == 2) {
-        if (B == 0xdeadbeefu) g_debug_sink = 1;
-        return;
-    }
-    if (debug == 1) {
-        if (B && base[nwidx] == 0xdeadbeefu) g_debug_sink = 1;
-        return;
-    }
-    if ((B >> b) & 1u) {  // same section: its s-1 / s+1 neighbours are chained to it already
-        uf_union(parent, p, base[nwidx] + (uint32_t)__popc(B & ((1u << b) - 1u)));
+    if ((B >> b) & 1u) {
+        nb[cnt++] = base[nwidx] + (uint32_t)__popc(B & ((1u << b) - 1u));
         return;
     }
     if (b > 0) {  // section s-1
-        if ((B >> (b - 1)) & 1u) uf_union(parent, p, base[nwidx] + (uint32_t)__popc(B & ((1u << (b - 1)) - 1u)));
+        if ((B >> (b - 1)) & 1u) nb[cnt++] = base[nwidx] + (uint32_t)__popc(B & ((1u << (b - 1)) - 1u));
     } else if (w > 0) {
         const uint32_t Bm = bmp[nwidx - 1];
-        if (Bm >> 31) uf_union(parent, p, base[nwidx - 1] + (uint32_t)__popc(Bm & 0x7fffffffu));
+        if (Bm >> 31) nb[cnt++] = base[nwidx - 1] + (uint32_t)__popc(Bm & 0x7fffffffu);
     }
     if (b < 31) {  // section s+1
-        if ((B >> (b + 1)) & 1u) uf_union(parent, p, base[nwidx] + (uint32_t)__popc(B & ((1u << (b + 1)) - 1u)));
+        if ((B >> (b + 1)) & 1u) nb[cnt++] = base[nwidx] + (uint32_t)__popc(B & ((1u << (b + 1)) - 1u));
     } else if (w + 1 < W) {
         const uint32_t Bp = bmp[nwidx + 1];
-        if (Bp & 1u) uf_union(parent, p, base[nwidx + 1]);
+        if (Bp & 1u) nb[cnt++] = base[nwidx + 1];
     }
 }
 
@@ -315,9 +305,7 @@ __global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __
         while (word) {
             const int bit = __ffs(word) - 1;
             word &= word - 1;
-            const int s = w * 32 + bit;
             a.key[out0 + p] = keybase + (uint32_t)bit;
-            a.value[out0 + p] = __ldg(a.rho + ((int64_t)s * a.NR + r) * a.NC + c);
             // parent = first voxel of the run (path-compressed chaining: finds stay O(1) instead of O(run length))
             const uint32_t below = starts & ((2u << bit) - 1u);
             uint32_t par;
@@ -347,13 +335,21 @@ __global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __
         const int w = s >> 5, bit = s & 31;
         const uint32_t *bmp = a.bmp + (k ? a.nwords_pad : 0);
         const uint32_t *base = a.base + (k ? a.nwords_pad : 0);
+        // the density of the voxel (one independent gather per thread, in flight while the neighbours are looked up)
+        a.value[(int64_t)k * a.cap + (i - (k ? n0 : 0))] = __ldg(a.rho + ((int64_t)s * a.NR + r) * a.NC + c);
+        // the 12 predecessor neighbours outside the voxel's own column: columns (c-1, r-1..r+1) and (c, r-1)
+        uint32_t nbr[8];
+        int cnt = 0;
         if (c > 0) {
             const int64_t rowbase = (int64_t)(c - 1) * a.U1;
-            if (r > 0) merge_with_column(a.parent, bmp, base, (rowbase + r - 1) * a.W + w, w, bit, a.W, p, a.debug);
-            merge_with_column(a.parent, bmp, base, (rowbase + r) * a.W + w, w, bit, a.W, p, a.debug);
-            if (r + 1 < a.U1) merge_with_column(a.parent, bmp, base, (rowbase + r + 1) * a.W + w, w, bit, a.W, p, a.debug);
+            if (r > 0) neighbours_in_column(bmp, base, (rowbase + r - 1) * a.W + w, w, bit, a.W, nbr, cnt);
+            neighbours_in_column(bmp, base, (rowbase + r) * a.W + w, w, bit, a.W, nbr, cnt);
+            if (r + 1 < a.U1) neighbours_in_column(bmp, base, (rowbase + r + 1) * a.W + w, w, bit, a.W, nbr, cnt);
         }
-        if (r > 0) merge_with_column(a.parent, bmp, base, ((int64_t)c * a.U1 + r - 1) * a.W + w, w, bit, a.W, p, a.debug);
+        if (r > 0) neighbours_in_column(bmp, base, ((int64_t)c * a.U1 + r - 1) * a.W + w, w, bit, a.W, nbr, cnt);
+        // one union site for all lanes: the finds and hooks of a warp proceed in lock step instead of once per case
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) uf_union(a.parent, p, nbr[j]);
     }
     grid.sync();
     stamp(4);
@@ -534,7 +530,6 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     a.stats = d_stats;
     a.use_pos = use_pos;
     a.use_neg = use_neg;
-    a.debug = getenv("PE_BLOB_DEBUG") ? atoi(getenv("PE_BLOB_DEBUG")) : 0;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, blob_sparse_kernel, kSparseThreads, 0));

@@ -139,6 +139,15 @@ struct SphereAcc {
         n_neg += q ? 1 : 0;
         s_neg += q ? d : 0.0;
     }
+    // the same with the negative class switched off (cn == -inf): a third less work per voxel
+    __device__ __forceinline__ void add_pos(bool take, float v, float cp) {
+        const double d = widen(v);
+        const bool p = v > cp;
+        n_all += take ? 1 : 0;
+        s_all += d;
+        n_pos += p ? 1 : 0;
+        s_pos += p ? d : 0.0;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ sums kernel
@@ -265,65 +274,75 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
 constexpr int kUnionWarps = 4;
 constexpr int kTileC = 64, kTileR = 48, kTileS = 48;
 
+constexpr int kUnionChunk = 8;  // atoms whose tables are resident at once
+
 struct UnionShared {
     uint32_t bits[kTileR * kTileS * 2];
-    double sq[kUnionWarps][2][kTileR > kTileS ? kTileR : kTileS];  // [warp][row axis / section axis][index in tile]
-    int offC[kTileC], offR[kTileR], offS[kTileS];                   // wrapped element offsets of the tile's indices
+    double sqC[kUnionChunk][kTileC];  // per atom of the chunk: squares along the tile's columns / rows / sections
+    double sqR[kUnionChunk][kTileR];  // (only the part of the atom's box that lies inside the tile)
+    double sqS[kUnionChunk][kTileS];
+    double T[kUnionChunk];
+    int offC[kTileC], offR[kTileR], offS[kTileS];  // wrapped element offsets of the tile's indices
+    int cLo[kUnionChunk], nC[kUnionChunk], rLo[kUnionChunk], nR[kUnionChunk], sLo[kUnionChunk], nS[kUnionChunk];
+    int kMin[kUnionChunk];             // column (index into sqC) nearest the atom: the minimum of its sqC
+    int itemStart[kUnionChunk + 1];    // prefix sums of nR * nS: one work item per box row
 };
 
-// MODE 0: z is carried by the row axis (inner loop over rows), 1: by the section axis, 2: by the column axis.
+// MODE 0: z is carried by the row axis, 1: by the section axis, 2: by the column axis.
+// Squared distance of column k of a box row exactly as the reference adds it: fl(fl(X2 + Y2) + Z2).
 template <int MODE>
-__device__ __forceinline__ void union_mark_tab(const pe_geom &g, const AtomBox &b, double ax, double ay, double az, double T,
-                                               double *sq1, double *sq2, int warp, int lane, int tc0, int tr0, int ts0, int tC,
-                                               int tR, int tS, uint32_t *bits) {
-    // intersection of the atom's box with the tile, in tile-relative coordinates
-    const int c_lo = max(b.lo[0], tc0), c_hi = min(b.lo[0] + b.dim[0], tc0 + tC);
-    const int r_lo = max(b.lo[1], tr0), r_hi = min(b.lo[1] + b.dim[1], tr0 + tR);
-    const int s_lo = max(b.lo[2], ts0), s_hi = min(b.lo[2] + b.dim[2], ts0 + tS);
-    if (c_lo >= c_hi || r_lo >= r_hi || s_lo >= s_hi) return;  // warp-uniform
-    const int n1 = r_hi - r_lo, n2 = s_hi - s_lo;
-    __syncwarp();
-    for (int k = lane; k < n1; k += 32) sq1[k] = axis_sq(g, 1, r_lo + k, ax, ay, az);
-    for (int k = lane; k < n2; k += 32) sq2[k] = axis_sq(g, 2, s_lo + k, ax, ay, az);
-    __syncwarp();
-    constexpr bool kInnerRows = (MODE == 0);
-    const double *sqi_tab = kInnerRows ? sq1 : sq2;
-    const double *sqo_tab = kInnerRows ? sq2 : sq1;
-    const int Di = kInnerRows ? n1 : n2, Do = kInnerRows ? n2 : n1;
-    const int width = c_hi - c_lo;
-    int d0p = 1;
-    while (d0p < width && d0p < 32) d0p <<= 1;
-    const int rpi = 32 / d0p;
-    const int lrow = lane / d0p, lc = lane % d0p;
-    const unsigned rowmask = d0p == 32 ? 0xffffffffu : ((1u << d0p) - 1u);
-    const int rbase = r_lo - tr0, sbase = s_lo - ts0;
-    for (int cbase = 0; cbase < width; cbase += 32) {
-        const bool act = cbase + lc < width;
-        const double sqc = act ? axis_sq(g, 0, c_lo + cbase + lc, ax, ay, az) : 0.0;
-        const int shift = c_lo + cbase - tc0;  // bit position of lane column 0 in the tile row (0..63)
-        for (int ko0 = warp * rpi; ko0 < Do; ko0 += kUnionWarps * rpi) {
-            const int ko = ko0 + lrow;
-            const bool rowact = act && ko < Do;
-            const double sqo = rowact ? sqo_tab[ko] : 0.0;
-            const double P = __dadd_rn(sqc, sqo);
-            // tile-relative bitmap row of (ko, ki = 0) and its stride in ki
-            const int row0 = kInnerRows ? (rbase * kTileS + sbase + ko) : ((rbase + ko) * kTileS + sbase);
-            constexpr int kRowStep = kInnerRows ? kTileS : 1;
-#pragma unroll 4
-            for (int ki = 0; ki < Di; ++ki) {
-                const double sqi = sqi_tab[ki];
-                const double d2 = (MODE == 2) ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
-                const unsigned m = __ballot_sync(kFull, rowact && (d2 <= T));
-                const unsigned mine = (m >> (lrow * d0p)) & rowmask;
-                if (lc == 0 && mine != 0u) {
-                    const unsigned long long wide = (unsigned long long)mine << shift;
-                    uint32_t *word = bits + 2 * (row0 + ki * kRowStep);
-                    const uint32_t lo = (uint32_t)wide, hi = (uint32_t)(wide >> 32);
-                    if (lo) atomicOr(word, lo);
-                    if (hi) atomicOr(word + 1, hi);
-                }
-            }
+__device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, double B, double T) {
+    // MODE 0/1: A = square of the non-z axis among (row, section), B = square of the z axis;
+    // MODE 2  : A = fl(row square + section square), the column carries z.
+    const double d2 = (MODE == 2) ? __dadd_rn(A, sqc[k]) : __dadd_rn(__dadd_rn(sqc[k], A), B);
+    return d2 <= T;
+}
+
+// Membership of one chunk of atoms in one tile: a work item is one box row (row, section) of one atom.  Along the
+// columns of a box row the squared distance falls to the column nearest the atom and rises again (every rounding
+// step is monotone), so the in-sphere columns are one interval around that column and two binary searches with
+// the EXACT predicate find its ends -- ~8 float64 tests per box row instead of one per candidate voxel.
+template <int MODE>
+__device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int tid, int nthreads) {
+    const int total = sh.itemStart[nchunk];
+    for (int item = tid; item < total; item += nthreads) {
+        int j = 0;
+        while (item >= sh.itemStart[j + 1]) ++j;
+        const int li = item - sh.itemStart[j];
+        const int nS = sh.nS[j];
+        const int ir = li / nS, is = li - ir * nS;
+        const double sr = sh.sqR[j][ir], ss = sh.sqS[j][is];
+        const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
+        const double B = (MODE == 0) ? sr : ss;
+        const double T = sh.T[j];
+        const double *sqc = sh.sqC[j];
+        const int km = sh.kMin[j];
+        if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
+        int lo = 0, hi = km;  // smallest k in [0, km] inside
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (row_pred<MODE>(sqc, mid, A, B, T))
+                hi = mid;
+            else
+                lo = mid + 1;
         }
+        const int kl = lo;
+        lo = km;
+        hi = sh.nC[j] - 1;  // largest k in [km, nC) inside
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (row_pred<MODE>(sqc, mid, A, B, T))
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const int count = lo - kl + 1;
+        const unsigned long long run = count >= 64 ? ~0ull : ((1ull << count) - 1ull);
+        const unsigned long long wide = run << (sh.cLo[j] + kl);
+        uint32_t *word = sh.bits + 2 * ((sh.rLo[j] + ir) * kTileS + (sh.sLo[j] + is));
+        const uint32_t wlo = (uint32_t)wide, whi = (uint32_t)(wide >> 32);
+        if (wlo) atomicOr(word, wlo);
+        if (whi) atomicOr(word + 1, whi);
     }
 }
 
@@ -399,20 +418,76 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                         t_mark = now;
                     }
                     // phase 1: membership
-                    for (int a = a0; a < a1; ++a) {
-                        AtomBox b;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            b.lo[k] = box[6 * a + k];
-                            b.dim[k] = box[6 * a + 3 + k];
+                    if (g.orthogonal) {
+                        for (int c0 = a0; c0 < a1; c0 += kUnionChunk) {
+                            const int nchunk = min(kUnionChunk, a1 - c0);
+                            if (tid < nchunk) {  // the part of each atom's box inside the tile (tile-relative)
+                                const int32_t *bx = box + 6 * (c0 + tid);
+                                const bool any = bx[3] > 0 && bx[4] > 0 && bx[5] > 0;
+                                const int cl = max(bx[0], tc0), ch = min(bx[0] + bx[3], tc0 + tC);
+                                const int rl = max(bx[1], tr0), rh = min(bx[1] + bx[4], tr0 + tR);
+                                const int sl = max(bx[2], ts0), shh = min(bx[2] + bx[5], ts0 + tS);
+                                const bool hit = any && cl < ch && rl < rh && sl < shh;
+                                sh.cLo[tid] = cl - tc0;
+                                sh.nC[tid] = hit ? ch - cl : 0;
+                                sh.rLo[tid] = rl - tr0;
+                                sh.nR[tid] = hit ? rh - rl : 0;
+                                sh.sLo[tid] = sl - ts0;
+                                sh.nS[tid] = hit ? shh - sl : 0;
+                                sh.T[tid] = thr[c0 + tid];
+                            }
+                            __syncthreads();
+                            if (tid == 0) {
+                                int run = 0;
+                                for (int j = 0; j < nchunk; ++j) {
+                                    sh.itemStart[j] = run;
+                                    run += sh.nR[j] * sh.nS[j];
+                                }
+                                sh.itemStart[nchunk] = run;
+                            }
+                            for (int idx = tid; idx < nchunk * (kTileC + kTileR + kTileS); idx += blockDim.x) {
+                                const int j = idx / (kTileC + kTileR + kTileS), e = idx - j * (kTileC + kTileR + kTileS);
+                                const int a = c0 + j;
+                                const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+                                if (e < kTileC) {
+                                    if (e < sh.nC[j]) sh.sqC[j][e] = axis_sq(g, 0, tc0 + sh.cLo[j] + e, ax, ay, az);
+                                } else if (e < kTileC + kTileR) {
+                                    const int k = e - kTileC;
+                                    if (k < sh.nR[j]) sh.sqR[j][k] = axis_sq(g, 1, tr0 + sh.rLo[j] + k, ax, ay, az);
+                                } else {
+                                    const int k = e - kTileC - kTileR;
+                                    if (k < sh.nS[j]) sh.sqS[j][k] = axis_sq(g, 2, ts0 + sh.sLo[j] + k, ax, ay, az);
+                                }
+                            }
+                            __syncthreads();
+                            if (tid < nchunk) {  // exact argmin of the column squares
+                                int km = 0;
+                                double best = sh.nC[tid] > 0 ? sh.sqC[tid][0] : 0.0;
+                                for (int k = 1; k < sh.nC[tid]; ++k) {
+                                    const double v = sh.sqC[tid][k];
+                                    if (v < best) {
+                                        best = v;
+                                        km = k;
+                                    }
+                                }
+                                sh.kMin[tid] = km;
+                            }
+                            __syncthreads();
+                            union_mark_rows<MODE>(sh, nchunk, tid, blockDim.x);
+                            __syncthreads();  // tables are reused by the next chunk
                         }
-                        if (b.dim[0] <= 0 || b.dim[1] <= 0 || b.dim[2] <= 0) continue;
-                        const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
-                        if (g.orthogonal)
-                            union_mark_tab<MODE>(g, b, ax, ay, az, thr[a], sh.sq[warp][0], sh.sq[warp][1], warp, lane, tc0, tr0, ts0,
-                                                 tC, tR, tS, sh.bits);
-                        else
-                            union_mark_generic(g, b, ax, ay, az, thr[a], tid, blockDim.x, tc0, tr0, ts0, tC, tR, tS, sh.bits);
+                    } else {
+                        for (int a = a0; a < a1; ++a) {
+                            AtomBox b;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                b.lo[k] = box[6 * a + k];
+                                b.dim[k] = box[6 * a + 3 + k];
+                            }
+                            if (b.dim[0] <= 0 || b.dim[1] <= 0 || b.dim[2] <= 0) continue;
+                            union_mark_generic(g, b, xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2], thr[a], tid, blockDim.x, tc0, tr0,
+                                               ts0, tC, tR, tS, sh.bits);
+                        }
                     }
                     __syncthreads();
                     {
@@ -428,6 +503,7 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                     // of a window read one 32-byte sector.
                     {
                         const int sg = lane >> 3, lr = lane & 7;
+                        const bool has_neg = cn > __int_as_float(0xff800000);
                         for (int rl = warp; rl < tR; rl += kUnionWarps) {
                             const int orow = sh.offR[rl];
                             uint32_t *rowbits = sh.bits + 2 * rl * kTileS;
@@ -439,38 +515,50 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                                 if ((mine.x | mine.y) != 0u)  // leave the bitmap clear for the next tile
                                     *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
                                 while (nz) {
-                                    // the next (up to) four non-empty sections, one per quarter-warp
-                                    int src = -1;
+                                    // the next (up to) eight non-empty sections, two per quarter-warp
+                                    int src[2] = {-1, -1};
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
+                                    for (int q = 0; q < 8; ++q) {
                                         const int f = nz ? (__ffs(nz) - 1) : -1;
                                         if (nz) nz &= nz - 1;
-                                        if (q == sg) src = f;
+                                        if ((q >> 1) == sg) src[q & 1] = f;
                                     }
-                                    const uint32_t lo = __shfl_sync(kFull, mine.x, src < 0 ? 0 : src);
-                                    const uint32_t hi = __shfl_sync(kFull, mine.y, src < 0 ? 0 : src);
-                                    unsigned long long w = src < 0 ? 0ull : (((unsigned long long)hi << 32) | lo);
-                                    const int os = src < 0 ? kInvalidOff : sh.offS[sl0 + src];
-                                    const int ors = orow | os;
-                                    const unsigned srs = (unsigned)orow + (unsigned)os;
-                                    while (__any_sync(kFull, w != 0ull)) {
-                                        // two windows per trip: both loads are issued before either is consumed
-                                        float v[2];
-                                        bool bit[2];
+                                    unsigned long long w[2];
+                                    int ors[2];
+                                    unsigned srs[2];
 #pragma unroll
-                                        for (int u = 0; u < 2; ++u) {
-                                            const int first = w ? (__ffsll((long long)w) - 1) : 0;
+                                    for (int u = 0; u < 2; ++u) {
+                                        const uint32_t lo = __shfl_sync(kFull, mine.x, src[u] < 0 ? 0 : src[u]);
+                                        const uint32_t hi = __shfl_sync(kFull, mine.y, src[u] < 0 ? 0 : src[u]);
+                                        w[u] = src[u] < 0 ? 0ull : (((unsigned long long)hi << 32) | lo);
+                                        const int os = src[u] < 0 ? kInvalidOff : sh.offS[sl0 + src[u]];
+                                        ors[u] = orow | os;
+                                        srs[u] = (unsigned)orow + (unsigned)os;
+                                    }
+                                    while (__any_sync(kFull, (w[0] | w[1]) != 0ull)) {
+                                        // four windows per trip (two per row): all loads are issued before any is consumed
+                                        float v[4];
+                                        bool bit[4];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            unsigned long long &ww = w[u >> 1];
+                                            const int first = ww ? (__ffsll((long long)ww) - 1) : 0;
                                             const int col = first + lr;
-                                            bit[u] = w != 0ull && col < 64 && ((w >> col) & 1ull);
+                                            bit[u] = ww != 0ull && col < 64 && ((ww >> col) & 1ull);
                                             const int oc = bit[u] ? sh.offC[col] : kInvalidOff;
-                                            const bool ok = (ors | oc) >= 0;
+                                            const bool ok = (ors[u >> 1] | oc) >= 0;
                                             v[u] = 0.f;
-                                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs + (unsigned)oc));
+                                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs[u >> 1] + (unsigned)oc));
                                             acc.bad |= (bit[u] && !ok) ? 1 : 0;
-                                            if (w) w &= ~(0xffull << first);
+                                            if (ww) ww &= ~(0xffull << first);
                                         }
-                                        acc.add(bit[0], v[0], cp, cn);
-                                        acc.add(bit[1], v[1], cp, cn);
+                                        if (has_neg) {
+#pragma unroll
+                                            for (int u = 0; u < 4; ++u) acc.add(bit[u], v[u], cp, cn);
+                                        } else {
+#pragma unroll
+                                            for (int u = 0; u < 4; ++u) acc.add_pos(bit[u], v[u], cp);
+                                        }
                                     }
                                 }
                             }
