@@ -328,13 +328,17 @@ def main_gpu(args, rank, world, local_rank):
         kernels = []
         for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             kernels.append({"kernel": name, "launches": count, "ms_total": round(ms, 4), "us_per_launch": round(ms * 1e3 / max(count, 1), 2)})
+        try:  # DRAM traffic per launch from the committed ncu capture of this workload (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            traffic = {}
         roofs = []
         for k in kernels:
             if k["kernel"] in algo:
                 t = k["ms_total"] / max(k["launches"], 1) * 1e-3
                 ach = algo[k["kernel"]] / t / 1e9
                 r = {"kernel": k["kernel"], "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(ach / peak, 4), "traffic": traffic.get(k["kernel"]), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo[k["kernel"]], "us_per_launch": k["us_per_launch"]}
                 if k["kernel"] in notes:
                     r["note"] = notes[k["kernel"]]

@@ -28,7 +28,6 @@ namespace pe {
 
 constexpr int kBmpTx = 32;         // threads along columns (x VEC columns each)
 constexpr int kBmpTy = 8;          // threads along rows
-constexpr int kChunkWords = 4;     // 32-section words per thread (grid.z splits the section axis)
 constexpr int kSparseThreads = 512;
 constexpr int kSparseMaxBlocks = 1024;  // size of the per-block partial-sum arrays
 
@@ -46,7 +45,7 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
     p.U0 = g->unique_ncrs[0];
     p.U1 = g->unique_ncrs[1];
     p.U2 = g->unique_ncrs[2];
-    p.W = (p.U2 + 31) / 32;
+    p.W = ((p.U2 + 31) / 32 + 7) / 8 * 8;  // padded: see threshold_bitmap_kernel
     p.nwords = (int64_t)p.U0 * p.U1 * p.W;
     p.nwords_pad = align_up(p.nwords, 64);
     p.cap = cap;
@@ -66,13 +65,20 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
 }
 
 // ------------------------------------------------------------------------------------------------ K1: stream
-template <int VEC>
-__global__ void __launch_bounds__(kBmpTx *kBmpTy)
+// W (words per (column, row)) is padded to a multiple of 8, so the kWordsPerThread = 4 words a thread produces for
+// one (column, row) are one aligned 16-byte store, and the two thread blocks that share a 32-byte sector are
+// neighbours in launch order (the word-group index is blockIdx.x, the fastest-varying block index): every bit-plane
+// sector reaches DRAM as one full write.  Scattered 4-byte word stores cost a read-modify-write per sector once the
+// bit planes no longer fit L2 (768^3 ran at 28 % of the HBM peak, tune log in profiles/r01_threshold_tuning.md).
+constexpr int kWordsPerThread = 4;
+
+template <int VEC, int TY, int MINB>
+__global__ void __launch_bounds__(kBmpTx *TY, MINB)
     threshold_bitmap_kernel(const float *__restrict__ rho, int NC, int NR, int U0, int U1, int U2, int W, float cpos,
                             float cneg, bool use_pos, bool use_neg, uint32_t *__restrict__ bmp_pos,
                             uint32_t *__restrict__ bmp_neg) {
-    const int c = (blockIdx.x * kBmpTx + threadIdx.x) * VEC;
-    const int r = blockIdx.y * kBmpTy + threadIdx.y;
+    const int c = (blockIdx.y * kBmpTx + threadIdx.x) * VEC;
+    const int r = blockIdx.z * TY + threadIdx.y;
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0) {  // padding between / after the planes
         const int64_t nwords = (int64_t)U0 * U1 * W;
         for (int64_t i = nwords + threadIdx.x; i < nwords + 64; i += kBmpTx) {
@@ -83,16 +89,18 @@ __global__ void __launch_bounds__(kBmpTx *kBmpTy)
         }
     }
     if (c >= U0 || r >= U1) return;
-    const int w_begin = blockIdx.z * kChunkWords;
-    const int w_end = min(W, w_begin + kChunkWords);
+    const int w_begin = blockIdx.x * kWordsPerThread;
     const int64_t plane = (int64_t)NR * NC;
     const float *col = rho + (int64_t)r * NC + c;
-    for (int w = w_begin; w < w_end; ++w) {
+    uint32_t accp[VEC][kWordsPerThread], accn[VEC][kWordsPerThread];
+#pragma unroll
+    for (int q = 0; q < kWordsPerThread; ++q) {
+        const int w = w_begin + q;
         uint32_t pos[VEC], neg[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) pos[i] = neg[i] = 0u;
         const int s0 = w * 32;
-        const int nbits = min(32, U2 - s0);
+        const int nbits = min(32, U2 - s0);  // <= 0 in the padding words
         const float *p = col + (int64_t)s0 * plane;
         if (nbits == 32) {
             if (VEC == 4) {
@@ -134,11 +142,16 @@ __global__ void __launch_bounds__(kBmpTx *kBmpTy)
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            if (c + i < U0) {
-                const int64_t widx = ((int64_t)(c + i) * U1 + r) * W + w;
-                bmp_pos[widx] = use_pos ? pos[i] : 0u;
-                bmp_neg[widx] = use_neg ? neg[i] : 0u;
-            }
+            accp[i][q] = use_pos ? pos[i] : 0u;
+            accn[i][q] = use_neg ? neg[i] : 0u;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        if (c + i < U0) {
+            const int64_t widx = ((int64_t)(c + i) * U1 + r) * W + w_begin;  // multiple of 4 words: 16-byte aligned
+            *reinterpret_cast<uint4 *>(bmp_pos + widx) = make_uint4(accp[i][0], accp[i][1], accp[i][2], accp[i][3]);
+            *reinterpret_cast<uint4 *>(bmp_neg + widx) = make_uint4(accn[i][0], accn[i][1], accn[i][2], accn[i][3]);
         }
     }
 }
@@ -496,13 +509,13 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         const bool vec4 = (NC % 4 == 0) && (((uintptr_t)d_rho & 15u) == 0);
         const int vec = vec4 ? 4 : 1;
         dim3 block(kBmpTx, kBmpTy, 1);
-        dim3 grid((p.U0 + kBmpTx * vec - 1) / (kBmpTx * vec), (p.U1 + kBmpTy - 1) / kBmpTy, (p.W + kChunkWords - 1) / kChunkWords);
+        dim3 grid(p.W / kWordsPerThread, (p.U0 + kBmpTx * vec - 1) / (kBmpTx * vec), (p.U1 + kBmpTy - 1) / kBmpTy);
         PE_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "pe_blob_label: map too large for the launch grid");
         if (vec4)
-            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4, kBmpTy, 1><<<grid, block, 0, st>>>(
                 d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
         else
-            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1, kBmpTy, 1><<<grid, block, 0, st>>>(
                 d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
         PE_LAUNCH_CHECK();
     }
