@@ -198,6 +198,13 @@ int pe_cluster_crs_grouped(int64_t n, const int32_t *d_crs, const int32_t *d_gro
 int pe_crs_stats(const pe_geom *g, const float *d_rho, int64_t n, const int32_t *d_crs, const int32_t *d_label,
                  const uint8_t *d_take, int64_t n_clusters, double *d_stats, void *stream);
 
+/* calculateRsccRsrMetrics (pdb_eda/densityAnalysis.py:860-882) for every group of a labelled voxel list at once, on the
+ * Fo map (d_rho_fo = 2Fo-Fc) and the Fc map formed on the fly as fo - 2 * diff in float64 (pdb_eda/densityAnalysis.py:433):
+ * d_out[g*8 ..] = n, sum fo, sum fc, sum |fo - fc|, sum |fo + fc|, sum (fo-mean)^2, sum (fc-mean)^2, sum (fo-mean)(fc-mean).
+ * RSCC = out[7] / sqrt(out[5] * out[6]), RSR = out[3] / out[4].  Entries with d_take[i] == 0 are skipped. */
+int pe_pair_metrics(const pe_geom *g, const float *d_rho_fo, const float *d_rho_diff, int64_t n, const int32_t *d_crs,
+                    const int32_t *d_label, const uint8_t *d_take, int64_t n_groups, double *d_out, void *stream);
+
 /* testOverlap (pdb_eda/cutils.pyx:8-25), all pairs at once: every entry is a voxel of the blob d_owner[i]; two
  * blobs overlap iff some voxel of one is identical or 26-adjacent to some voxel of the other (same group when
  * d_group is given).  Writes each overlapping unordered pair once as (smaller owner, larger owner) to d_pairs

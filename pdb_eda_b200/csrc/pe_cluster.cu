@@ -206,6 +206,48 @@ __global__ void __launch_bounds__(kClThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ two-map metrics
+// Real-space correlation / R factor over voxel sets (calculateRsccRsrMetrics, pdb_eda/densityAnalysis.py:860-882):
+// fo = 2Fo-Fc value, fc = fo - 2 * (Fo-Fc) value formed in float64 exactly as the reference's
+// `densityObj.density - diffDensityObj.density * 2` (pdb_eda/densityAnalysis.py:433).  Pass 0 accumulates
+// n, sum fo, sum fc, sum |fo - fc|, sum |fo + fc|; pass 1 the centred second moments (two-pass, like scipy's pearsonr).
+template <int PASS>
+__global__ void __launch_bounds__(kClThreads)
+    pair_metrics_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho_fo, const float *__restrict__ rho_diff,
+                        int64_t n, const int32_t *__restrict__ crs, const int32_t *__restrict__ label,
+                        const uint8_t *__restrict__ take, int64_t n_groups, double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (take && !take[i]) continue;
+        const int grp = label ? label[i] : 0;
+        if (grp < 0 || grp >= n_groups) continue;
+        const int wc = wrap_index(crs[3 * i], g.ncrs[0], g.crs_interval[0]);
+        const int wr = wrap_index(crs[3 * i + 1], g.ncrs[1], g.crs_interval[1]);
+        const int wsx = wrap_index(crs[3 * i + 2], g.ncrs[2], g.crs_interval[2]);
+        double fo = 0.0, df = 0.0;
+        if ((wc | wr | wsx) >= 0) {
+            const int64_t off = ((int64_t)wsx * g.ncrs[1] + wr) * g.ncrs[0] + wc;
+            fo = (double)__ldg(rho_fo + off);
+            df = (double)__ldg(rho_diff + off);
+        }
+        const double fc = __dsub_rn(fo, __dmul_rn(df, 2.0));
+        double *o = out + (int64_t)grp * 8;
+        if (PASS == 0) {
+            atomicAdd(o + 0, 1.0);
+            atomicAdd(o + 1, fo);
+            atomicAdd(o + 2, fc);
+            atomicAdd(o + 3, fabs(fo - fc));
+            atomicAdd(o + 4, fabs(fo + fc));
+        } else {
+            const double cnt = o[0];
+            const double xm = fo - o[1] / cnt, ym = fc - o[2] / cnt;
+            atomicAdd(o + 5, xm * xm);
+            atomicAdd(o + 6, ym * ym);
+            atomicAdd(o + 7, xm * ym);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ overlap pairs
 // For every entry, every entry of another owner at an identical or 26-adjacent voxel (same group) yields the
 // unordered owner pair; pairs are de-duplicated through a second hash set and appended to the output.
@@ -350,6 +392,24 @@ int pe_crs_stats(const pe_geom *g, const float *d_rho, int64_t n, const int32_t 
     if (n == 0) return PE_OK;
     PE_CHECK_ARG(d_rho && d_crs, "pe_crs_stats: null pointer");
     PE_LAUNCH("crs_stats_kernel", st, crs_stats_kernel<<<grid_for(n), kClThreads, 0, st>>>(*g, d_rho, n, d_crs, d_label, d_take, n_clusters, d_stats));
+    PE_LAUNCH_CHECK();
+    return PE_OK;
+}
+
+int pe_pair_metrics(const pe_geom *g, const float *d_rho_fo, const float *d_rho_diff, int64_t n, const int32_t *d_crs,
+                    const int32_t *d_label, const uint8_t *d_take, int64_t n_groups, double *d_out, void *stream) {
+    if (int rc = check_geom(g)) return rc;
+    PE_CHECK_ARG(n >= 0 && n_groups >= 0, "pe_pair_metrics: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_groups == 0) return PE_OK;
+    PE_CHECK_ARG(d_out, "pe_pair_metrics: null output");
+    PE_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_groups * 8 * sizeof(double), st));
+    if (n == 0) return PE_OK;
+    PE_CHECK_ARG(d_rho_fo && d_rho_diff && d_crs, "pe_pair_metrics: null pointer");
+    PE_LAUNCH("pair_metrics_kernel", st, pair_metrics_kernel<0><<<grid_for(n), kClThreads, 0, st>>>(
+        *g, d_rho_fo, d_rho_diff, n, d_crs, d_label, d_take, n_groups, d_out));
+    PE_LAUNCH("pair_metrics_kernel", st, pair_metrics_kernel<1><<<grid_for(n), kClThreads, 0, st>>>(
+        *g, d_rho_fo, d_rho_diff, n, d_crs, d_label, d_take, n_groups, d_out));
     PE_LAUNCH_CHECK();
     return PE_OK;
 }

@@ -272,6 +272,23 @@ def crsStats(densityMatrix, crs, label=None, take=None, nClusters=1):
     return stats
 
 
+def pairMetrics(foMatrix, diffMatrix, crs, label=None, take=None, nGroups=1):
+    """Per-group RSCC / RSR sums on the Fo map and the on-the-fly Fc map (``pe_pair_metrics``) -> (nGroups, 8) tensor."""
+    fo, diff = deviceMap(foMatrix), deviceMap(diffMatrix)
+    if fo.rho.numel() != diff.rho.numel():
+        raise ValueError("the 2Fo-Fc and Fo-Fc maps must share one grid")
+    crs = _as_dev(crs, torch.int32, fo.device, (-1, 3))
+    label_t = _as_dev(label, torch.int32, fo.device, (-1,)) if label is not None else None
+    take_t = None
+    if take is not None:
+        take_t = take.to(device=fo.device, dtype=torch.uint8).contiguous() if isinstance(take, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(np.asarray(take, dtype=np.uint8))).to(fo.device)
+    out = torch.empty((int(nGroups), 8), dtype=torch.float64, device=fo.device)
+    check(fo.lib.pe_pair_metrics(ctypes.byref(fo.geom), _ptr(fo.rho), _ptr(diff.rho), crs.shape[0], _ptr(crs), _ptr(label_t),
+                                 _ptr(take_t), int(nGroups), _ptr(out), _stream()), "pe_pair_metrics")
+    return out
+
+
 def blobsFromCrsList(densityMatrix, crsList):
     """createBlobList (pdb_eda/ccp4.py:475-485): cluster + per-blob sums on the device."""
     crs = np.asarray(list(crsList), dtype=np.int32).reshape(-1, 3)

@@ -201,6 +201,52 @@ def residueAtomName(atom):
     return atom.parent.resname.strip() + "_" + atom.name
 
 
+def _median(t):
+    """np.median of a 1-D device tensor (mean of the two middle values for an even count)."""
+    n = t.numel()
+    if n == 0:
+        return float("nan")
+    s = torch.sort(t).values
+    return float(s[n // 2].item()) if n % 2 else float((s[n // 2 - 1].item() + s[n // 2].item()) / 2.0)
+
+
+class _FcMatrix(ccp4.DensityMatrix):
+    """The reference's ``fc`` object: a deep copy of the 2Fo-Fc DensityMatrix whose ``density`` is replaced
+    (pdb_eda/densityAnalysis.py:426-435) -- header, ``densityArray``, mean and standard deviation stay those of 2Fo-Fc."""
+
+    def __init__(self, densityObj, diffDensityObj):
+        self.pdbid = densityObj.pdbid
+        self.header = densityObj.header
+        self.origin = densityObj.origin
+        self._fo = densityObj
+        self._diff = diffDensityObj
+        self._density64 = None
+        self._hostDirty = False
+        self._totalAbsDensity = {}
+
+    @property
+    def densityArray(self):
+        return self._fo.densityArray
+
+    @property
+    def density(self):
+        if self._density64 is None:
+            self._density64 = np.asarray(self._fo.density) - np.asarray(self._diff.density) * 2
+        return self._density64
+
+    @property
+    def meanDensity(self):
+        return self._fo.meanDensity
+
+    @property
+    def stdDensity(self):
+        return self._fo.stdDensity
+
+    @property
+    def deviceMap(self):
+        raise NotImplementedError("the Fc map is formed on the fly from the 2Fo-Fc and Fo-Fc maps; use the RSCC / RSR methods")
+
+
 def _components(n, neighbours):
     """Connected components of an overlap graph, grown exactly like the reference grows them (Python sets, the same
     insertion sequence, pdb_eda/densityAnalysis.py:664-673 and :696-705), so that set iteration order -- which decides
@@ -285,11 +331,11 @@ class DensityAnalysis(object):
 
     @property
     def fc(self):
-        """Fc map = 2Fo-Fc - 2 (Fo-Fc) (pdb_eda/densityAnalysis.py:426-435)."""
+        """Fc map = 2Fo-Fc - 2 (Fo-Fc) (pdb_eda/densityAnalysis.py:426-435).  Like the reference's deep copy it keeps the
+        header, mean and standard deviation of the 2Fo-Fc object; only ``density`` (float64, not float32-representable)
+        differs.  The device kernels form it on the fly from the two resident maps (``pe_pair_metrics``)."""
         if self._fc is None:
-            values = np.asarray(self.densityObj.density) - np.asarray(self.diffDensityObj.density) * 2
-            self._fc = ccp4.DensityMatrix(self.densityObj.header, self.densityObj.origin, values.astype(np.float32).reshape(-1),
-                                          self.densityObj.pdbid)
+            self._fc = _FcMatrix(self.densityObj, self.diffDensityObj)
         return self._fc
 
     @property
@@ -589,6 +635,87 @@ class DensityAnalysis(object):
         atoms['corrected_density_electron_ratio'] = atoms['corrected_fraction'] * densityElectronRatio + densityElectronRatio
         medians.update(typeMedians(['domain_fraction', 'corrected_fraction', 'corrected_density_electron_ratio'], atoms))
         return atoms, medians
+
+    # ------------------------------------------------------------------------------------------ RSCC / RSR
+    def medianAbsFoFc(self):
+        """Median |Fo| and |Fc| over the voxels of the unique volume where both are below one sigma
+        (pdb_eda/densityAnalysis.py:783-800); masked selection and medians run on the device."""
+        fo, diff = self.densityObj.deviceMap, self.diffDensityObj.deviceMap
+        cut = self.densityObj.meanDensity + 1.0 * self.densityObj.stdDensity   # the Fc copy keeps the Fo statistics
+        g = fo.geom
+        ns, nr, nc = g.ncrs[2], g.ncrs[1], g.ncrs[0]
+        u = g.unique_ncrs
+        a = fo.rho.view(ns, nr, nc)[:u[2], :u[1], :u[0]].double()
+        b = a - diff.rho.view(ns, nr, nc)[:u[2], :u[1], :u[0]].double() * 2
+        keep = (a.abs() < cut) & (b.abs() < cut)
+        return (_median(a[keep].abs()), _median(b[keep].abs()))
+
+    residueMetricsHeaderList = ['chain', 'residue_number', 'residue_name', "rscc", "rsr", "mean_occupancy", "occupancy_weighted_mean_bfactor"]
+    atomMetricsHeaderList = ['chain', 'residue_number', 'residue_name', "atom_name", "symmetry", "xyz", "rscc", "rsr", "occupancy", "bfactor"]
+
+    def _metricsRadius(self):
+        resolution = self.biopdbObj.header['resolution']
+        radius = 0.7
+        if 0.6 <= resolution <= 3:
+            radius = (resolution - 0.6) / 3 + 0.7
+        elif resolution > 3:
+            radius = resolution * 0.5
+        return radius
+
+    def _groupMetrics(self, coords, groupOfAtom, nGroups, radius):
+        """RSCC / RSR of the set-union of the atoms' spheres per group: one sphere enumeration, one de-duplication and
+        one two-pass reduction over both maps for all groups."""
+        lists = utils.sphereLists(self.densityObj, coords, radius, 0.0)
+        crs = lists["crs"]
+        group = torch.from_numpy(np.asarray(groupOfAtom, dtype=np.int32)).to(crs.device)[lists["atom"].long()]
+        _, first, _ = utils.clusterCrs(crs, group, wantFirst=True)
+        out = utils.pairMetrics(self.densityObj, self.diffDensityObj, crs, group, first, nGroups).cpu().numpy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rscc = np.clip(out[:, 7] / np.sqrt(out[:, 5] * out[:, 6]), -1.0, 1.0)
+            rsr = out[:, 3] / out[:, 4]
+        return rscc, rsr
+
+    def residueMetrics(self, residueList=None):
+        """RSCC and RSR of every residue on the Fo / Fc maps (pdb_eda/densityAnalysis.py:803-829)."""
+        radius = self._metricsRadius()
+        if residueList is None:
+            residueList = list(self.biopdbObj.get_residues())
+        coords, groupOf = [], []
+        for k, residue in enumerate(residueList):
+            for atom in residue.child_list:
+                coords.append(atom.coord)
+                groupOf.append(k)
+        if not coords:
+            return []
+        rscc, rsr = self._groupMetrics(coords, groupOf, len(residueList), radius)
+        results = []
+        for k, residue in enumerate(residueList):
+            bfactorWeightedSum = occupancySum = 0.0
+            for atom in residue.child_list:
+                bfactorWeightedSum += atom.get_bfactor() * atom.get_occupancy()
+                occupancySum += atom.get_occupancy()
+            results.append([residue.parent.id, residue.id[1], residue.resname, rscc[k], rsr[k], occupancySum / len(residue.child_list),
+                            bfactorWeightedSum / occupancySum])
+        return results
+
+    def atomMetrics(self, atomList=None):
+        """RSCC and RSR of every atom (pdb_eda/densityAnalysis.py:831-858)."""
+        radius = self._metricsRadius()
+        if atomList is None:
+            atomList = self.asymmetryAtoms
+        if not atomList:
+            return []
+        rscc, rsr = self._groupMetrics([np.asarray(atom.coord, dtype=np.float64) for atom in atomList], list(range(len(atomList))),
+                                       len(atomList), radius)
+        return [[atom.parent.parent.id, atom.parent.id[1], atom.parent.resname, atom.name, atom.symmetry, atom.coord, rscc[k], rsr[k],
+                 atom.get_occupancy(), atom.get_bfactor()] for k, atom in enumerate(atomList)]
+
+    def calculateRsccRsrMetrics(self, crsList):
+        """(RSCC, RSR) over one voxel list (pdb_eda/densityAnalysis.py:860-882)."""
+        crs = np.asarray(list(crsList), dtype=np.int32).reshape(-1, 3)
+        out = utils.pairMetrics(self.densityObj, self.diffDensityObj, crs, None, None, 1).cpu().numpy()[0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return (float(np.clip(out[7] / np.sqrt(out[5] * out[6]), -1.0, 1.0)), float(out[3] / out[4]))
 
     # ------------------------------------------------------------------------------------------ symmetry atoms
     def _calculateSymmetryAtoms(self):

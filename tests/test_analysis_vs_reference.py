@@ -7,6 +7,7 @@ statistics, atom / residue / symmetry-atom region density and discrepancy incl. 
 Bars: counts, voxel sets, labels, orders bit-exact; float64 sums and statistics within 1e-9 relative.
 """
 import io
+import os
 
 import numpy as np
 import pytest
@@ -176,6 +177,51 @@ def test_region_density_and_discrepancy(pair):
     one = [a.coord for a in list(m.biopdbObj.get_atoms())[:4]]
     gc.close(m.calculateRegionDensity(one, 2.5), r.calculateRegionDensity(one, 2.5), rtol=1e-9, atol=1e-12)
     gc.close(m.calculateRegionDiscrepancy(one, 2.5), r.calculateRegionDiscrepancy(one, 2.5), rtol=1e-9, atol=1e-12)
+
+
+def test_rscc_rsr_metrics(pair):
+    """residueMetrics / atomMetrics / calculateRsccRsrMetrics / medianAbsFoFc."""
+    import warnings
+    r, m = pair
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rres = r.residueMetrics()
+        ratoms = r.atomMetrics(r.asymmetryAtoms[::7])
+        rmed = r.medianAbsFoFc()
+        crs = r.densityObj.getSphereCrsFromXyz(r.asymmetryAtoms[3].coord, 1.4, 0.0)
+        rone = r.calculateRsccRsrMetrics(crs)
+    mres = m.residueMetrics()
+    matoms = m.atomMetrics(m.asymmetryAtoms[::7])
+    assert [x[:3] for x in rres] == [x[:3] for x in mres]
+    ok = np.isfinite(np.array([x[3] for x in rres], dtype=np.float64))
+    assert ok.sum() > len(rres) // 2
+    gc.close(np.array([x[3:] for x in mres], dtype=np.float64)[ok], np.array([x[3:] for x in rres], dtype=np.float64)[ok], rtol=1e-8, atol=1e-9)
+    assert [x[:5] for x in ratoms] == [x[:5] for x in matoms]
+    gc.close([x[6:] for x in matoms], [x[6:] for x in ratoms], rtol=1e-8, atol=1e-9)
+    gc.close(m.medianAbsFoFc(), rmed, rtol=1e-9)
+    gc.close(m.calculateRsccRsrMetrics(crs), rone, rtol=1e-8, atol=1e-9)
+    assert np.array_equal(np.asarray(m.fc.density), r.fc.density)
+
+
+def test_from_pdbid_uses_the_cache(pair, tmp_path, monkeypatch):
+    """fromPDBid with the files already in ./ccp4_data and ./pdb_data (no network), pdb_eda/densityAnalysis.py:88-179."""
+    import gzip
+    from pdb_eda_b200 import densityAnalysis
+    name = [k for k in CASES][0]
+    st, d1, d2, pdb_text = _build(name)
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("ccp4_data")
+    os.makedirs("pdb_data")
+    open("ccp4_data/9xyz.ccp4", "wb").write(d1)
+    open("ccp4_data/9xyz_diff.ccp4", "wb").write(d2)
+    with gzip.open("pdb_data/pdb9xyz.ent.gz", "wt") as fh:
+        fh.write(pdb_text)
+    an = densityAnalysis.fromPDBid("9XYZ")
+    assert an != 0 and an.pdbid == "9xyz"
+    assert len(list(an.biopdbObj.get_atoms())) == len(list(st.get_atoms()))
+    assert an.densityObj.densityCutoff > 0 and len(an.pdbObj.header.rotationMats) == 4
+    assert densityAnalysis.fromPDBid("0000") == 0      # nothing cached, no network: the loader reports failure with 0
+    assert densityAnalysis.cleanPDBid("9xyz") and not os.path.exists("ccp4_data/9xyz.ccp4")
 
 
 def test_error_conventions(pair, ref):
