@@ -1,0 +1,68 @@
+"""CLI shims of the voxel path: argument surface on CPU, end-to-end runs on the GPU."""
+import gzip
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+
+def test_single_parser_surface():
+    from pdb_eda_b200 import singleStructure
+    p = singleStructure.buildParser()
+    a = p.parse_args(["1cbs", "-", "density", "--residue", "--radius", "2.5", "--atom-mask", "m.json", "--optimized-radii", "--out-format", "csv"])
+    assert a.submode == "density" and a.residue and a.radius == 2.5 and a.atom_mask == "m.json" and a.optimized_radii and a.out_format == "csv"
+    a = p.parse_args(["1cbs", "out.json", "blob", "--green", "--red", "--num-sd", "3.5", "--include-pdbid"])
+    assert a.green and a.red and a.num_sd == 3.5 and a.include_pdbid
+    with pytest.raises(SystemExit):
+        p.parse_args(["1cbs", "-", "nosuchmode"])
+    assert singleStructure.numpyConverter(np.float64(1.5)) == 1.5 and singleStructure.numpyConverter(np.arange(3)) == [0, 1, 2]
+
+
+def _write_entry(folder, pdbid, seed):
+    from pdb_eda_b200 import structure, synthetic
+    cell, n = (24.0, 24.0, 24.0, 90, 90, 90), (48, 48, 48)
+    st = synthetic.polyAlaStructure(45, (0, 0, 0), cell[:3], seed=seed)
+    a, b = synthetic.mapPair(st, n, cell, seed=seed + 1)
+    open(os.path.join(folder, pdbid + ".ccp4"), "wb").write(synthetic.ccp4Bytes(a, cell, n))
+    open(os.path.join(folder, pdbid + "_diff.ccp4"), "wb").write(synthetic.ccp4Bytes(b, cell, n))
+    text = structure.formatPDB(st, remark290=synthetic.cartesianOperators("P 21 21 21", cell), cell=cell, spaceGroup="P 21 21 21")
+    with gzip.open(os.path.join(folder, "pdb" + pdbid + ".ent.gz"), "wt") as fh:
+        fh.write(text)
+    return text
+
+
+@pytest.mark.gpu
+def test_single_and_multiple_end_to_end(tmp_path):
+    from pdb_eda_b200 import densityAnalysis, multipleStructures, singleStructure, synthetic
+    densityAnalysis.setGlobals(synthetic.defaultParams())
+    folder = str(tmp_path)
+    ids = ["1aaa", "2bbb", "3ccc"]
+    for k, pdbid in enumerate(ids):
+        _write_entry(folder, pdbid, 10 + 3 * k)
+    files = ["--pdb-file", os.path.join(folder, "pdb1aaa.ent.gz"), "--density-file", os.path.join(folder, "1aaa.ccp4"), "--diff-file",
+             os.path.join(folder, "1aaa_diff.ccp4")]
+    out = os.path.join(folder, "blob.json")
+    singleStructure.main(["1AAA", out, "blob", "--green", "--red", "--include-pdbid"] + files)
+    rows = json.load(open(out))
+    an = densityAnalysis.fromFile(files[1], files[3], files[5])
+    want = an.calculateAtomSpecificBlobStatistics(an.greenBlobList + an.redBlobList)
+    assert len(rows) == len(want) > 0 and rows[0]["pdbid"] == "1aaa"
+    assert [r["num_voxels"] for r in rows] == [w[3] for w in want]
+    np.testing.assert_allclose([r["distance_to_atom"] for r in rows], [w[0] for w in want], rtol=1e-12)
+    out = os.path.join(folder, "res.csv")
+    singleStructure.main(["1aaa", out, "difference", "--residue", "--type", "ALA", "--out-format", "csv"] + files)
+    lines = open(out).read().strip().splitlines()
+    assert lines[0].split(",")[:5] == ["model", "chain", "residue_number", "residue_name", "mean_occupancy"] and len(lines) == 46
+    out = os.path.join(folder, "cloud.json")
+    singleStructure.main(["1aaa", out, "cloud", "--atom"] + files)
+    assert len(json.load(open(out))) == len(an.atomCloudDescriptions)
+    # multiple mode over a directory of cached entries, one of which is missing
+    idfile = os.path.join(folder, "ids.txt")
+    open(idfile, "w").write(" ".join(ids + ["9zzz"]))
+    out = os.path.join(folder, "multi.json")
+    multipleStructures.main([idfile, out, "--data-dir", folder])
+    res = json.load(open(out))
+    assert sorted(res["entries"]) == ids and res["cumulative"]["structures"] == 3
+    np.testing.assert_allclose(res["entries"]["1aaa"]["stats"]["density_electron_ratio"], an.densityElectronRatio, rtol=1e-12)
