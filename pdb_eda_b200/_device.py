@@ -109,10 +109,17 @@ class DeviceMap:
         self._sum_abs = {}
 
     @classmethod
-    def from_host(cls, header, values, origin=None, device="cuda"):
-        """``values``: anything numpy can view as the flat float32 payload (column fastest)."""
-        arr = np.ascontiguousarray(np.asarray(values, dtype=np.float32)).reshape(-1)
-        rho = torch.from_numpy(arr).to(device)
+    def from_host(cls, header, values, origin=None, device="cuda", pinned=None):
+        """``values``: anything numpy can view as the flat float32 payload (column fastest).  ``pinned``: the page-locked
+        uint8 tensor that backs ``values`` (set by ``ccp4.parse``): the upload is then a single asynchronous DMA."""
+        require_cuda()
+        if pinned is not None:
+            rho = pinned.view(torch.float32).to(device, non_blocking=True)
+        else:
+            arr = np.ascontiguousarray(np.asarray(values, dtype=np.float32)).reshape(-1)
+            if not arr.flags.writeable:
+                arr = arr.copy()
+            rho = torch.from_numpy(arr).to(device)
         return cls(geom_from_header(header, origin), rho)
 
     # ------------------------------------------------------------------------------------------ whole-map sums

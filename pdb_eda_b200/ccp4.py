@@ -51,16 +51,38 @@ def parse(handle, pdbid, verbose=False):
     (pdb_eda/ccp4.py:123-124), which is what lets 384^3 and 1024^3 maps load at all.
     """
     header = DensityHeader.fromFileHeader(handle.read(HEADER_BYTES))
-    payload = handle.read()
-    if len(payload) != header.symmetryBytes + header.mapSize:
-        # the reference's size assertions all fail once the lengths disagree (pdb_eda/ccp4.py:95-100)
-        raise AssertionError("Error: file holds %d bytes after the header, expected %d symmetry + %d map bytes"
-                             % (len(payload), header.symmetryBytes, header.mapSize))
     assert header.xlength != 0.0 or header.ylength != 0.0 or header.zlength != 0.0, \
         "Error: Cell dimensions are all 0, Map file will not align with other structures"
-    header.symmetry = payload[0:header.symmetryBytes]
-    voxels = np.frombuffer(payload, dtype=np.dtype(header.endian + "f4"), offset=header.symmetryBytes)
+    header.symmetry = handle.read(header.symmetryBytes) if header.symmetryBytes > 0 else b""
+    staging = _pinnedBuffer(header.mapSize) if header.endian == "<" else None
+    if staging is not None and hasattr(handle, "readinto"):
+        # the voxels go from the file straight into page-locked memory, from where one DMA takes them to HBM
+        view = staging.numpy()
+        got = handle.readinto(memoryview(view).cast("B"))
+        extra = handle.read(1)
+        if got != header.mapSize or extra:
+            raise AssertionError("Error: file holds %s map bytes, the header promises %d" % ("more than %d" % got if extra else got, header.mapSize))
+        matrix = DensityMatrix(header, header.origin, view.view(np.float32), pdbid)
+        matrix._pinned = staging
+        return matrix
+    payload = handle.read()
+    if len(payload) != header.mapSize:
+        # the reference's size assertions all fail once the lengths disagree (pdb_eda/ccp4.py:95-100)
+        raise AssertionError("Error: file holds %d bytes after the header, expected %d symmetry + %d map bytes"
+                             % (len(payload) + header.symmetryBytes, header.symmetryBytes, header.mapSize))
+    voxels = np.frombuffer(payload, dtype=np.dtype(header.endian + "f4"))
     return DensityMatrix(header, header.origin, voxels, pdbid)
+
+
+def _pinnedBuffer(nbytes):
+    """A page-locked uint8 staging tensor when a CUDA device is present (else None)."""
+    try:
+        import torch
+        if nbytes > 0 and torch.cuda.is_available():
+            return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    except Exception:
+        pass
+    return None
 
 
 class DensityHeader(object):
@@ -204,6 +226,7 @@ class DensityMatrix:
         if flat.size != n:
             raise ValueError("map payload holds %d values, header says %d" % (flat.size, n))
         self._raw32 = flat
+        self._pinned = None
         self._density64 = None
         self._hostDirty = False
         self._device = None
@@ -238,6 +261,7 @@ class DensityMatrix:
         if self._hostDirty:
             self._raw32 = np.ascontiguousarray(np.asarray(self._density64), dtype=np.float32).reshape(-1)
             self._hostDirty = False
+            self._pinned = None
             self._device = None
             self._totalAbsDensity = {}
 
@@ -247,7 +271,7 @@ class DensityMatrix:
         self._syncHost()
         if self._device is None:
             from ._device import DeviceMap
-            self._device = DeviceMap.from_host(self.header, self._raw32, self.origin)
+            self._device = DeviceMap.from_host(self.header, self._raw32, self.origin, pinned=self._pinned)
         return self._device
 
     # ---- statistics -----------------------------------------------------------------------------------------

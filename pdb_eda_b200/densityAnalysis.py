@@ -293,6 +293,13 @@ class DensityAnalysis(object):
                      "atomTypeOverlapCompleteness", "atomTypeOverlapIncompleteness"):
             setattr(self, "_" + name, None)
 
+    def resetCloud(self):
+        """Forgets the cloud-aggregation results (after ``setGlobals`` changed the radii); maps stay resident in HBM."""
+        for name in ("medians", "atomCloudDescriptions", "residueCloudDescriptions", "domainCloudDescriptions", "densityElectronRatio",
+                     "numVoxelsAggregated", "totalAggregatedElectrons", "totalAggregatedDensity", "atomTypeOverlapCompleteness",
+                     "atomTypeOverlapIncompleteness"):
+            setattr(self, "_" + name, None)
+
     # ------------------------------------------------------------------------------------------ lazy properties
     def _symmetry(self, name):
         if self._symmetryAtoms is None:

@@ -155,3 +155,45 @@ def runMultipleStructures(items, loader, costs=None, atomTypes=None, device=None
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     return gatherResults(results, mine, len(items), atomTypes, device, group)
+
+
+class OptimizeService:
+    """The inner loop of parameter optimisation as a persistent service (pdb_eda/optimizeParams.py:341-448): the reference
+    re-downloads nothing but re-parses and re-analyses every entry in a fresh Pool task per iteration; here every rank
+    loads its share of the structures ONCE, the maps stay resident in HBM, and an iteration only changes the radii table
+    (``setGlobals``) and re-runs the cloud aggregation on the GPU, followed by the two collectives of ``gatherResults``."""
+
+    def __init__(self, items, loader, costs=None, device=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n = len(items)
+        self.mine = shardStructures([1.0] * self.n if costs is None else costs, self.world)[self.rank]
+        self.analyzers = {}
+        for idx in self.mine:
+            try:
+                self.analyzers[idx] = loader(items[idx])
+            except Exception:
+                self.analyzers[idx] = 0
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = device
+
+    def evaluate(self, params):
+        """One optimiser iteration: (medianDiffs, meanDiffs, overallStdDevDiffs, medianSlopes, sizeDiffs,
+        atomTypeOverlapCompleteness), the tuple of ``calculateMedianDiffsSlopes``."""
+        from . import densityAnalysis
+        densityAnalysis.setGlobals(params)
+        types = list(params["radii"])
+        results = {}
+        for idx, analyzer in self.analyzers.items():
+            if not analyzer:
+                results[idx] = 0
+                continue
+            analyzer.resetCloud()
+            try:
+                results[idx] = analyzeStructure(analyzer, types)
+            except Exception:
+                results[idx] = 0
+        s = gatherResults(results, self.mine, self.n, types, self.device, self.group)
+        return (s["medianDiffs"], s["meanDiffs"], s["overallStdDevDiffs"], s["medianSlopes"], s["sizeDiffs"], s["atomTypeOverlapCompleteness"])

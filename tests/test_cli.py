@@ -66,3 +66,34 @@ def test_single_and_multiple_end_to_end(tmp_path):
     res = json.load(open(out))
     assert sorted(res["entries"]) == ids and res["cumulative"]["structures"] == 3
     np.testing.assert_allclose(res["entries"]["1aaa"]["stats"]["density_electron_ratio"], an.densityElectronRatio, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_optimize_service_and_pinned_loader(tmp_path):
+    """Persistent optimiser inner loop and the pinned load path (8f-1)."""
+    import copy
+    from pdb_eda_b200 import ccp4, densityAnalysis, multi, multipleStructures, synthetic
+    folder = str(tmp_path)
+    ids = ["1aaa", "2bbb"]
+    for k, pdbid in enumerate(ids):
+        _write_entry(folder, pdbid, 20 + 3 * k)
+    dm = ccp4.read(os.path.join(folder, "1aaa.ccp4"))
+    assert dm._pinned is not None and dm._pinned.is_pinned()                 # file -> page-locked memory -> one DMA
+    ref = ccp4.parse(io.BytesIO(open(os.path.join(folder, "1aaa.ccp4"), "rb").read()), "x")
+    assert np.array_equal(dm.densityArray, ref.densityArray) and dm.meanDensity == ref.meanDensity
+    with pytest.raises(AssertionError):
+        ccp4.parse(io.BytesIO(open(os.path.join(folder, "1aaa.ccp4"), "rb").read()[:-8]), "x")
+    params = synthetic.defaultParams()
+    service = multi.OptimizeService(ids, multipleStructures.makeLoader(folder))
+    first = service.evaluate(params)
+    bigger = copy.deepcopy(params)
+    bigger["radii"] = {t: r * 1.25 for t, r in params["radii"].items()}
+    second = service.evaluate(bigger)
+    assert first[0] != second[0]                                             # the radii matter
+    again = service.evaluate(params)
+    assert again[0] == first[0] and again[5] == first[5]                     # and the service is stateless across iterations
+    densityAnalysis.setGlobals(bigger)
+    fresh = multi.gatherResults({i: multi.analyzeStructure(multipleStructures.makeLoader(folder)(p), list(bigger["radii"])) for i, p in enumerate(ids)},
+                                [0, 1], 2, list(bigger["radii"]), "cpu")
+    assert fresh["medianDiffs"] == second[0]
+    densityAnalysis.setGlobals(params)
