@@ -25,6 +25,7 @@ _HEADER_WORDS = (
 )
 _HEADER_FORMAT = "".join(code * count for _, count, code in _HEADER_WORDS)
 HEADER_BYTES = 1024
+PINNED_MIN_BYTES = 32 << 20
 
 
 def readFromPDBID(pdbid, verbose=False):
@@ -54,7 +55,8 @@ def parse(handle, pdbid, verbose=False):
     assert header.xlength != 0.0 or header.ylength != 0.0 or header.zlength != 0.0, \
         "Error: Cell dimensions are all 0, Map file will not align with other structures"
     header.symmetry = handle.read(header.symmetryBytes) if header.symmetryBytes > 0 else b""
-    staging = _pinnedBuffer(header.mapSize) if header.endian == "<" else None
+    # page-locking costs a few ms per call: worth it from a few tens of MB up, where the pageable copy would dominate
+    staging = _pinnedBuffer(header.mapSize) if (header.endian == "<" and header.mapSize >= PINNED_MIN_BYTES) else None
     if staging is not None and hasattr(handle, "readinto"):
         # the voxels go from the file straight into page-locked memory, from where one DMA takes them to HBM
         view = staging.numpy()

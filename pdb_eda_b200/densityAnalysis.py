@@ -432,57 +432,63 @@ class DensityAnalysis(object):
         delta = coords[cloudAtom] - cCentroid
         cDist = np.sqrt((delta * delta).sum(axis=1))              # np.linalg.norm(atom.coord - cloud.centroid)
         # allAtomClouds is keyed by the coordinate tuple (:606): a later atom with identical coordinates replaces the entry
-        lastWithCoord = {}
-        for i in range(nAtoms):
-            lastWithCoord[coords32[i].tobytes()] = i
-        src = np.array([lastWithCoord[coords32[i].tobytes()] for i in range(nAtoms)], dtype=np.int64) if nAtoms else np.zeros(0, np.int64)
+        if nAtoms:
+            _, inverse = np.unique(coords32 + np.float32(0.0), axis=0, return_inverse=True)   # -0.0 and 0.0 are one key
+            inverse = np.asarray(inverse).reshape(-1)
+            lastOfGroup = np.zeros(int(inverse.max()) + 1, dtype=np.int64)
+            lastOfGroup[inverse] = np.arange(nAtoms)             # later assignments win: the last atom with these coordinates
+            src = lastOfGroup[inverse]
+        else:
+            src = np.zeros(0, np.int64)
         centroidDistances = np.minimum.reduceat(cDist, cloudStartH[:-1][nCloudsH > 0]) if totalClouds else []
         if len(centroidDistances):
             centroidDistanceCutoff = np.nanmedian(centroidDistances) + 2.5 * np.nanstd(centroidDistances)
         else:
             centroidDistanceCutoff = np.nan
 
-        # ---- pass 2, host part: which atoms contribute, their best cloud, the residue pools (:611-643)
+        # ---- pass 2, host part: which atoms contribute, their best cloud, the residue pools (:611-643), vectorised
+        # per candidate: the clouds it uses are those stored under its coordinates (those of atom src[k])
+        nC = nCloudsH[src] if nAtoms else np.zeros(0, np.int64)
+        lo = cloudStartH[:-1][src] if nAtoms else np.zeros(0, np.int64)
+        # first minimum of the centroid distances per cloud owner (distances.index(min(distances)), :630-634)
+        minD = np.full(nAtoms, np.inf)
+        firstArg = np.zeros(nAtoms, dtype=np.int64)
+        if totalClouds:
+            owners = np.flatnonzero(nCloudsH > 0)
+            minD[owners] = centroidDistances
+            isMin = cDist == minD[cloudAtom]
+            firstArg[owners] = np.minimum.reduceat(np.where(isMin, np.arange(totalClouds), totalClouds), cloudStartH[:-1][owners])
+        accepted = (nC > 0) & ((nC == 1) | ~(minD[src] > centroidDistanceCutoff)) if nAtoms else np.zeros(0, bool)
+        best = np.where(nC == 1, lo, firstArg[src]) if nAtoms else lo
+        accIdx = np.flatnonzero(accepted)
+        candResidue = np.array([c[0] for c in cand], dtype=np.int64) if nAtoms else np.zeros(0, np.int64)
+        # pool entries: every cloud of every accepted atom, in traversal order
+        accN = nC[accIdx]
+        poolAtomA = np.repeat(accIdx, accN)
+        poolStartOfAtom = np.cumsum(accN) - accN
+        poolCloudA = np.repeat(lo[accIdx], accN) + (np.arange(int(accN.sum())) - np.repeat(poolStartOfAtom, accN))
+        poolResidueA = candResidue[poolAtomA]
+        nPool = len(poolCloudA)
+        poolAtom = poolAtomA.tolist()
+        poolResidue = poolResidueA.tolist()
+        resPoolStart = np.searchsorted(poolResidueA, np.arange(len(residues) + 1)).tolist()
+        # atom table rows
+        bestAcc = best[accIdx]
+        rowDensity = cTotal[bestAcc].tolist()
+        rowCount = cCount[bestAcc].tolist()
+        rowDist = cDist[bestAcc].tolist()
+        rowCentroid = cCentroid[bestAcc].tolist()
         atomList = []
-        poolCloud = []          # global cloud id of every pool entry, in pool order
-        poolResidue = []        # residue index of every pool entry
-        poolAtom = []           # candidate index of the atom the cloud is attached to
-        resPoolStart = [0]
-        resAtomClouds = []      # per residue: {resAtom: [local pool indices]}
-        byResidue = collections.defaultdict(list)
-        for k, (ridx, atom, resAtom) in enumerate(cand):
-            byResidue[ridx].append(k)
-        for ridx, residue in enumerate(residues):
-            indices = {}
-            local = 0
-            for k in byResidue.get(ridx, ()):
-                _, atom, resAtom = cand[k]
-                s = src[k]
-                lo, hi = cloudStartH[s], cloudStartH[s + 1]
-                if hi == lo:
-                    continue
-                if hi - lo == 1:
-                    best = lo
-                else:
-                    dist = np.sqrt(((coords[k] - cCentroid[lo:hi]) ** 2).sum(axis=1)).tolist()
-                    minDistance = min(dist)
-                    if minDistance > centroidDistanceCutoff:
-                        continue
-                    best = lo + dist.index(minDistance)
-                indices[resAtom] = [local + j for j in range(hi - lo)]
-                local += hi - lo
-                for c in range(lo, hi):
-                    poolCloud.append(c)
-                    poolResidue.append(ridx)
-                    poolAtom.append(k)
-                bdelta = coords[k] - cCentroid[best]
-                atomList.append([residue.parent.id, residue.id[1], atom.parent.resname, atom.name, types[resAtom],
-                                 cTotal[best] / electronsOf[resAtom] / atom.get_occupancy(), int(cCount[best]), electronsOf[resAtom],
-                                 atom.get_bfactor(), np.sqrt((bdelta * bdelta).sum()), cCentroid[best].tolist()])
-            resAtomClouds.append(indices)
-            resPoolStart.append(len(poolCloud))
-        nPool = len(poolCloud)
-        poolCloudA = np.asarray(poolCloud, dtype=np.int64)
+        resAtomClouds = [dict() for _ in residues]      # per residue: {resAtom: [local pool indices]}
+        for j, k in enumerate(accIdx.tolist()):
+            ridx, atom, resAtom = cand[k]
+            residue = residues[ridx]
+            first = int(poolStartOfAtom[j]) - resPoolStart[ridx]
+            resAtomClouds[ridx][resAtom] = list(range(first, first + int(accN[j])))
+            electrons = electronsOf[resAtom]
+            atomList.append([residue.parent.id, residue.id[1], atom.parent.resname, atom.name, types[resAtom],
+                             rowDensity[j] / electrons / atom.get_occupancy(), rowCount[j], electrons, atom.get_bfactor(),
+                             rowDist[j], rowCentroid[j]])
 
         # ---- the voxels of the pool, in pool order (a cloud shared by two atoms with equal coordinates appears twice)
         order = torch.argsort(vCloud, stable=True)
@@ -495,7 +501,7 @@ class DensityAnalysis(object):
             offs = torch.arange(int(lens.sum().item()), device=dev) - torch.repeat_interleave(torch.cumsum(lens, 0) - lens, lens)
             pIdx = order[cloudVoxStart[pc][pOwner] + offs]
             pCrs = vCrs[pIdx].contiguous()
-            pRes = torch.from_numpy(np.asarray(poolResidue, dtype=np.int64)).to(dev)[pOwner]
+            pRes = torch.from_numpy(poolResidueA).to(dev)[pOwner]
         else:
             pOwner = torch.zeros(0, dtype=torch.int64, device=dev)
             pCrs = torch.zeros((0, 3), dtype=torch.int32, device=dev)
@@ -569,8 +575,12 @@ class DensityAnalysis(object):
         for currCluster in _components(nDomPool, _neighbourLists(nDomPool, dpairs.tolist())):
             base = currCluster.pop()
             atoms = list(domainAtoms[base])
-            for idx in currCluster:
-                atoms = atoms + [k for k in domainAtoms[idx] if k not in atoms]
+            seen = set(atoms)
+            for idx in currCluster:                      # atoms + [atom for atom in other.atoms if atom not in atoms] (ccp4.py:582)
+                for k in domainAtoms[idx]:
+                    if k not in seen:
+                        seen.add(k)
+                        atoms.append(k)
             st = dStats[int(dLabelH[domFirstVoxel[base]])]
             atom = cand[atoms[0]][1]
             domainElectrons = sum([electronCache[k] for k in atoms])
@@ -617,17 +627,23 @@ class DensityAnalysis(object):
         if not np.isnan(atoms['centroid_distance']).all():
             centroidCutoff = np.nanmedian(atoms['centroid_distance']) + np.nanstd(atoms['centroid_distance']) * 2
             atoms = atoms[atoms['centroid_distance'] < centroidCutoff]
-        atom_types = np.unique(atoms['atom_type'])
+        atom_types, typeIndex = np.unique(atoms['atom_type'], return_inverse=True)
+        typeIndex = np.asarray(typeIndex).reshape(-1)
+
+        masks = [typeIndex == i for i in range(len(atom_types))]      # atoms['atom_type'] == t, once per type
 
         def typeMedians(columns, table):
-            return {column: {t: np.nanmedian(table[column][table['atom_type'] == t]) for t in atom_types} for column in columns}
+            return {column: {t: np.nanmedian(table[column][m]) for t, m in zip(atom_types, masks)} for column in columns}
 
         medians = typeMedians(['num_voxels'], atoms)
-        lookup = np.vectorize(lambda column, atom_type: medians[column][atom_type])
+
+        def lookup(column, _types):
+            """medians[column][atom type] for every row (the reference uses np.vectorize over a dict lookup)."""
+            return np.array([medians[column][t] for t in atom_types])[typeIndex]
         atoms['adj_density_electron_ratio'] = atoms['density_electron_ratio'] / atoms['num_voxels'] * lookup('num_voxels', atoms['atom_type'])
         atoms['volume'] = atoms['num_voxels'] * unitVolume
         medians.update(typeMedians(['density_electron_ratio', 'centroid_distance', 'adj_density_electron_ratio', 'volume'], atoms))
-        medians['bfactor'] = {t: np.nanmedian(atoms['bfactor'][(atoms['atom_type'] == t) & (atoms['bfactor'] > 0)]) for t in atom_types}
+        medians['bfactor'] = {t: np.nanmedian(atoms['bfactor'][m & (atoms['bfactor'] > 0)]) for t, m in zip(atom_types, masks)}
         atoms['bfactor'][atoms['bfactor'] <= 0] = lookup('bfactor', atoms['atom_type'])[atoms['bfactor'] <= 0]
 
         def calcSlope(data, atom_type):
@@ -636,7 +652,7 @@ class DensityAnalysis(object):
             fit = stats.linregress(np.log(data['bfactor']), (data['adj_density_electron_ratio'] - densityElectronRatio) / densityElectronRatio)
             return currentSlopes[atom_type] if fit[3] > 0.05 else fit[0]
 
-        medians['slopes'] = {t: calcSlope(atoms[atoms['atom_type'] == t], t) for t in atom_types}
+        medians['slopes'] = {t: calcSlope(atoms[m], t) for t, m in zip(atom_types, masks)}
         atoms['domain_fraction'] = (atoms['adj_density_electron_ratio'] - densityElectronRatio) / densityElectronRatio
         atoms['corrected_fraction'] = atoms['domain_fraction'] - (np.log(atoms['bfactor']) - np.log(lookup('bfactor', atoms['atom_type']))) * lookup('slopes', atoms['atom_type'])
         atoms['corrected_density_electron_ratio'] = atoms['corrected_fraction'] * densityElectronRatio + densityElectronRatio

@@ -77,6 +77,7 @@ def test_optimize_service_and_pinned_loader(tmp_path):
     ids = ["1aaa", "2bbb"]
     for k, pdbid in enumerate(ids):
         _write_entry(folder, pdbid, 20 + 3 * k)
+    ccp4.PINNED_MIN_BYTES = 1024
     dm = ccp4.read(os.path.join(folder, "1aaa.ccp4"))
     assert dm._pinned is not None and dm._pinned.is_pinned()                 # file -> page-locked memory -> one DMA
     ref = ccp4.parse(io.BytesIO(open(os.path.join(folder, "1aaa.ccp4"), "rb").read()), "x")
