@@ -21,6 +21,7 @@
 // Skewed cells (and boxes wider than kDMax) take a generic path that evaluates the reference's 3x3 mat-vec per
 // candidate in the host BLAS's accumulation order.
 #include <limits.h>
+#include <type_traits>
 #include "pe_common.cuh"
 
 namespace pe {
@@ -316,7 +317,13 @@ __device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int
         const double B = (MODE == 0) ? sr : ss;
         const double T = sh.T[j];
         const double *sqc = sh.sqC[j];
-        const int km = sh.kMin[j];
+        // the column nearest the atom: the box's centre column or, after rounding, one of its neighbours
+        int km = sh.kMin[j];
+        {
+            const int nCj = sh.nC[j];
+            if (km > 0 && sqc[km - 1] < sqc[km]) --km;
+            else if (km + 1 < nCj && sqc[km + 1] < sqc[km]) ++km;
+        }
         if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
         int lo = 0, hi = km;  // smallest k in [0, km] inside
         while (lo < hi) {
@@ -366,6 +373,84 @@ __device__ __forceinline__ void union_mark_generic(const pe_geom &g, const AtomB
     }
 }
 
+// Phase 2 of the union kernel.  A warp owns tile rows rl = warp, warp + 4, ...; per 32 sections every lane fetches
+// "its" (row, section) bitmap word(s), a ballot finds the non-empty ones, and they are consumed eight at a time, two
+// per quarter-warp: a quarter-warp walks its rows in windows of 8 consecutive columns starting at the lowest set bit
+// (the set bits of a row are one or two short runs), so nearly every lane of every load carries a voxel and the 8
+// lanes of a window read one 32-byte sector; four loads are in flight per lane before any is consumed.
+template <bool WIDE, bool CHECKED, bool HASNEG>
+__device__ __forceinline__ void union_gather(UnionShared &sh, const float *__restrict__ rho, SphereAcc &acc, float cp, float cn,
+                                             int warp, int lane, int tR, int tS) {
+    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type word_t;
+    const int sg = lane >> 3, lr = lane & 7;
+    for (int rl = warp; rl < tR; rl += kUnionWarps) {
+        const int orow = sh.offR[rl];
+        uint32_t *rowbits = sh.bits + 2 * rl * kTileS;
+        for (int sl0 = 0; sl0 < tS; sl0 += 32) {
+            uint2 mine = make_uint2(0u, 0u);
+            if (sl0 + lane < tS) mine = *reinterpret_cast<const uint2 *>(rowbits + 2 * (sl0 + lane));
+            unsigned nz = __ballot_sync(kFull, (mine.x | mine.y) != 0u);
+            if (nz == 0u) continue;  // warp-uniform
+            if ((mine.x | mine.y) != 0u)  // leave the bitmap clear for the next tile
+                *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
+            while (nz) {
+                int src[2] = {-1, -1};  // the next (up to) eight non-empty sections, two per quarter-warp
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int f = nz ? (__ffs(nz) - 1) : -1;
+                    if (nz) nz &= nz - 1;
+                    if ((q >> 1) == sg) src[q & 1] = f;
+                }
+                word_t w[2];
+                int ors[2];
+                unsigned srs[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t lo = __shfl_sync(kFull, mine.x, src[u] < 0 ? 0 : src[u]);
+                    word_t full = lo;
+                    if (WIDE) full = (word_t)(((unsigned long long)__shfl_sync(kFull, mine.y, src[u] < 0 ? 0 : src[u]) << 32) | lo);
+                    w[u] = src[u] < 0 ? (word_t)0 : full;
+                    const int os = src[u] < 0 ? (CHECKED ? kInvalidOff : 0) : sh.offS[sl0 + src[u]];
+                    ors[u] = orow | os;
+                    srs[u] = (unsigned)orow + (unsigned)os;
+                }
+                while (__any_sync(kFull, (w[0] | w[1]) != (word_t)0)) {
+                    float v[4];
+                    bool bit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        word_t &ww = w[u >> 1];
+                        int first;
+                        if (WIDE)
+                            first = ww ? (__ffsll((long long)ww) - 1) : 0;
+                        else
+                            first = ww ? (__ffs((int)ww) - 1) : 0;
+                        const int col = first + lr;
+                        bit[u] = col < (WIDE ? 64 : 32) && ((ww >> col) & (word_t)1);
+                        v[u] = 0.f;
+                        if (CHECKED) {
+                            const int oc = bit[u] ? sh.offC[col] : kInvalidOff;
+                            const bool ok = (ors[u >> 1] | oc) >= 0;
+                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs[u >> 1] + (unsigned)oc));
+                            acc.bad |= (bit[u] && !ok) ? 1 : 0;
+                        } else {
+                            if (bit[u]) v[u] = __ldg(rho + (int)(srs[u >> 1] + (unsigned)sh.offC[col]));
+                        }
+                        ww &= ~(((word_t)0xff) << first);  // no-op when ww == 0 (first = 0)
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (HASNEG)
+                            acc.add(bit[u], v[u], cp, cn);
+                        else
+                            acc.add_pos(bit[u], v[u], cp);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Diagnostic: SM cycles spent per phase, summed over all CTAs of the launches since the last read
 // (prologue, membership, gather, epilogue); read and reset with pe_sphere_union_cycles().
 __device__ unsigned long long g_union_cycles[4];
@@ -379,13 +464,16 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
     __shared__ UnionShared sh;
     __shared__ double red_d[kUnionWarps][3];
     __shared__ int red_i[kUnionWarps][4];
-    const int grp = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int a0 = group_start[grp], a1 = group_start[grp + 1];
     long long t_mark = clock64();
     long long t_phase[4] = {0, 0, 0, 0};
     cp = eff_pos(cp);
     cn = eff_neg(cn);
+    // persistent CTAs: the bitmap is cleared once (the gather leaves it clear), then groups are taken round robin
+    for (int i = tid; i < kTileR * kTileS * 2; i += blockDim.x) sh.bits[i] = 0u;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int a0 = group_start[grp], a1 = group_start[grp + 1];
+    __syncthreads();  // the previous group's reduction scratch has been consumed
     // the group's bounding box
     int ulo0 = INT_MAX, ulo1 = INT_MAX, ulo2 = INT_MAX, uhi0 = INT_MIN, uhi1 = INT_MIN, uhi2 = INT_MIN;
     double candidates = 0.0;
@@ -402,7 +490,6 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
         uhi2 = max(uhi2, bx[2] + d2);
     }
     SphereAcc acc;
-    for (int i = tid; i < kTileR * kTileS * 2; i += blockDim.x) sh.bits[i] = 0u;
     if (uhi0 > ulo0) {
         for (int ts0 = ulo2; ts0 < uhi2; ts0 += kTileS)
             for (int tr0 = ulo1; tr0 < uhi1; tr0 += kTileR)
@@ -435,6 +522,8 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                                 sh.sLo[tid] = sl - ts0;
                                 sh.nS[tid] = hit ? shh - sl : 0;
                                 sh.T[tid] = thr[c0 + tid];
+                                // centre column of the box (range(c - R - 1, c + R + 1): c = lo + dim / 2), clamped into the tile part
+                                sh.kMin[tid] = hit ? min(max(bx[0] + bx[3] / 2 - cl, 0), ch - cl - 1) : 0;
                             }
                             __syncthreads();
                             if (tid == 0) {
@@ -460,19 +549,6 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                                 }
                             }
                             __syncthreads();
-                            if (tid < nchunk) {  // exact argmin of the column squares
-                                int km = 0;
-                                double best = sh.nC[tid] > 0 ? sh.sqC[tid][0] : 0.0;
-                                for (int k = 1; k < sh.nC[tid]; ++k) {
-                                    const double v = sh.sqC[tid][k];
-                                    if (v < best) {
-                                        best = v;
-                                        km = k;
-                                    }
-                                }
-                                sh.kMin[tid] = km;
-                            }
-                            __syncthreads();
                             union_mark_rows<MODE>(sh, nchunk, tid, blockDim.x);
                             __syncthreads();  // tables are reused by the next chunk
                         }
@@ -495,73 +571,26 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                         t_phase[1] += now - t_mark;
                         t_mark = now;
                     }
-                    // phase 2: gather every voxel of the union once.  A warp owns tile rows rl = warp, warp + 4, ...;
-                    // per 32 sections every lane fetches "its" (row, section) bitmap words, a ballot finds the
-                    // non-empty ones, and they are consumed four at a time: each quarter-warp walks one of them in
-                    // windows of 8 consecutive columns starting at its lowest set bit (the set bits of a row are
-                    // one or two short runs), so nearly every lane of every load carries a voxel and the 8 lanes
-                    // of a window read one 32-byte sector.
+                    // phase 2: gather every voxel of the union once (union_gather), specialised on the tile width
+                    // (32- or 64-bit bitmap rows), on whether every index of the tile is covered by the stored map
+                    // (no validity logic in the loop) and on whether the negative class is in use.
                     {
-                        const int sg = lane >> 3, lr = lane & 7;
+                        const bool wide = tC > 32;
                         const bool has_neg = cn > __int_as_float(0xff800000);
-                        for (int rl = warp; rl < tR; rl += kUnionWarps) {
-                            const int orow = sh.offR[rl];
-                            uint32_t *rowbits = sh.bits + 2 * rl * kTileS;
-                            for (int sl0 = 0; sl0 < tS; sl0 += 32) {
-                                uint2 mine = make_uint2(0u, 0u);
-                                if (sl0 + lane < tS) mine = *reinterpret_cast<const uint2 *>(rowbits + 2 * (sl0 + lane));
-                                unsigned nz = __ballot_sync(kFull, (mine.x | mine.y) != 0u);
-                                if (nz == 0u) continue;  // warp-uniform
-                                if ((mine.x | mine.y) != 0u)  // leave the bitmap clear for the next tile
-                                    *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
-                                while (nz) {
-                                    // the next (up to) eight non-empty sections, two per quarter-warp
-                                    int src[2] = {-1, -1};
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const int f = nz ? (__ffs(nz) - 1) : -1;
-                                        if (nz) nz &= nz - 1;
-                                        if ((q >> 1) == sg) src[q & 1] = f;
-                                    }
-                                    unsigned long long w[2];
-                                    int ors[2];
-                                    unsigned srs[2];
-#pragma unroll
-                                    for (int u = 0; u < 2; ++u) {
-                                        const uint32_t lo = __shfl_sync(kFull, mine.x, src[u] < 0 ? 0 : src[u]);
-                                        const uint32_t hi = __shfl_sync(kFull, mine.y, src[u] < 0 ? 0 : src[u]);
-                                        w[u] = src[u] < 0 ? 0ull : (((unsigned long long)hi << 32) | lo);
-                                        const int os = src[u] < 0 ? kInvalidOff : sh.offS[sl0 + src[u]];
-                                        ors[u] = orow | os;
-                                        srs[u] = (unsigned)orow + (unsigned)os;
-                                    }
-                                    while (__any_sync(kFull, (w[0] | w[1]) != 0ull)) {
-                                        // four windows per trip (two per row): all loads are issued before any is consumed
-                                        float v[4];
-                                        bool bit[4];
-#pragma unroll
-                                        for (int u = 0; u < 4; ++u) {
-                                            unsigned long long &ww = w[u >> 1];
-                                            const int first = ww ? (__ffsll((long long)ww) - 1) : 0;
-                                            const int col = first + lr;
-                                            bit[u] = ww != 0ull && col < 64 && ((ww >> col) & 1ull);
-                                            const int oc = bit[u] ? sh.offC[col] : kInvalidOff;
-                                            const bool ok = (ors[u >> 1] | oc) >= 0;
-                                            v[u] = 0.f;
-                                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs[u >> 1] + (unsigned)oc));
-                                            acc.bad |= (bit[u] && !ok) ? 1 : 0;
-                                            if (ww) ww &= ~(0xffull << first);
-                                        }
-                                        if (has_neg) {
-#pragma unroll
-                                            for (int u = 0; u < 4; ++u) acc.add(bit[u], v[u], cp, cn);
-                                        } else {
-#pragma unroll
-                                            for (int u = 0; u < 4; ++u) acc.add_pos(bit[u], v[u], cp);
-                                        }
-                                    }
-                                }
-                            }
+                        int invalid = 0;
+                        for (int k = tid; k < tC + tR + tS; k += blockDim.x)
+                            invalid |= (k < tC ? sh.offC[k] : (k < tC + tR ? sh.offR[k - tC] : sh.offS[k - tC - tR])) < 0 ? 1 : 0;
+                        const bool checked = __syncthreads_or(invalid) != 0;
+                        const int sel = (wide ? 4 : 0) | (checked ? 2 : 0) | (has_neg ? 1 : 0);
+                        switch (sel) {
+                            case 0: union_gather<false, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 1: union_gather<false, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 2: union_gather<false, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 3: union_gather<false, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 4: union_gather<true, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 5: union_gather<true, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 6: union_gather<true, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            default: union_gather<true, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
                         }
                     }
                     __syncthreads();
@@ -601,7 +630,14 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
         o[5] = sd[2];
         o[6] = ni[3] ? 0.0 : 1.0;
         o[7] = candidates;
-        t_phase[3] = clock64() - t_mark;
+    }
+    {
+        const long long now = clock64();
+        t_phase[3] += now - t_mark;
+        t_mark = now;
+    }
+    }  // next group
+    if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) atomicAdd(g_union_cycles + k, (unsigned long long)t_phase[k]);
     }
@@ -864,14 +900,15 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     }
     if (n_groups > 0) {
         const int mode = g->map2xyz[2] == 1 ? 0 : (g->map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
+        const int ugrid = min(n_groups, sm_count() * 7);                           // persistent: 7 CTAs fit an SM
         if (mode == 0)
-            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<0><<<n_groups, kUnionWarps * 32, 0, st>>>(
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<0><<<ugrid, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
         else if (mode == 1)
-            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<1><<<n_groups, kUnionWarps * 32, 0, st>>>(
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<1><<<ugrid, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
         else
-            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<2><<<n_groups, kUnionWarps * 32, 0, st>>>(
+            PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<2><<<ugrid, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
     }
     PE_LAUNCH_CHECK();
