@@ -206,3 +206,51 @@ def test_blob_properties_at_scale():
         # every blob is connected: re-clustering its voxels as an arbitrary list gives the same partition
         lab2, ncl = _device.cluster_crs(crs)
         assert ncl == nb and torch.equal(lab2.long(), label)
+
+
+def test_sphere_properties_at_scale():
+    """BASELINE.json config 2 size (384^3, 40,000 atoms / 8,000 residues): size-independent properties of the sphere
+    kernels plus an oracle check on a random sample of atoms and residues of the full-size problem."""
+    import torch
+    from oracle import orc
+    from pdb_eda_b200 import _blas, _device, ccp4, synthetic
+    n, nres = 384, 8000
+    cell = n * 0.5
+    vol = synthetic.smoothNoiseMapDevice(n, seed=11)
+    hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), (cell,) * 3 + (90, 90, 90), (n, n, n)))
+    dev = _device.DeviceMap(_device.geom_from_header(hdr), vol.reshape(-1))
+    rng = np.random.default_rng(12)
+    ca = rng.uniform(-2, cell + 2, (nres, 3))                                   # some residues hang over the cell edge (wrap)
+    offs = np.array([o for _, o, _ in synthetic._ALA_ATOMS])
+    xyz = np.round((ca[:, None, :] + offs[None, :, :]).reshape(-1, 3), 3).astype(np.float32).astype(np.float64)
+    start = np.arange(0, 5 * nres + 1, 5, dtype=np.int32)
+    r35 = np.full(len(xyz), 3.5, dtype=np.float32)
+    per_atom = dev.sphere_sums(xyz, r35, None, 1.0, -1.0).cpu().numpy()
+    per_res = dev.sphere_sums(xyz, r35, start, 1.0, -1.0).cpu().numpy()
+    # union bounds: max over atoms <= union <= sum over atoms, for counts of all three classes
+    for col in (0, 2, 4):
+        a = per_atom[:, col].reshape(nres, 5)
+        assert (per_res[:, col] <= a.sum(axis=1)).all() and (per_res[:, col] >= a.max(axis=1)).all()
+    assert np.array_equal(per_res[:, 6], per_atom[:, 6].reshape(nres, 5).min(axis=1))     # valid iff every atom is valid
+    assert np.array_equal(per_res[:, 7], per_atom[:, 7].reshape(nres, 5).sum(axis=1))     # candidates add up
+    # singleton groups == ungrouped; a repeated atom changes nothing (set semantics); deterministic across runs
+    single = dev.sphere_sums(xyz[:5000], r35[:5000], np.arange(5001, dtype=np.int32), 1.0, -1.0).cpu().numpy()
+    assert np.array_equal(single[:, (0, 2, 4, 6, 7)], per_atom[:5000][:, (0, 2, 4, 6, 7)])
+    gc.close(single[:, (1, 3, 5)], per_atom[:5000][:, (1, 3, 5)], rtol=1e-9, atol=1e-9)
+    dup_xyz = np.concatenate((xyz[:500], xyz[:500])).reshape(2, 100, 5, 3).transpose(1, 0, 2, 3).reshape(-1, 3)
+    dup = dev.sphere_sums(dup_xyz, np.full(len(dup_xyz), 3.5, np.float32), np.arange(0, 1001, 10, dtype=np.int32), 1.0, -1.0).cpu().numpy()
+    assert np.array_equal(dup[:, :7], per_res[:100, :7])
+    again = dev.sphere_sums(xyz, r35, start, 1.0, -1.0).cpu().numpy()
+    assert np.array_equal(again, per_res)
+    # the oracle on a random sample of the full-size problem
+    g = orc.geom(hdr, hdr.origin, mv=_blas.probe())
+    rho = vol.cpu().numpy()
+    pick = rng.choice(nres, 40, replace=False)
+    for k in pick:
+        want = orc.sphere_union_sums(g, rho, xyz[5 * k:5 * k + 5], r35[:5], 1.0, -1.0)
+        assert np.array_equal(per_res[k, (0, 2, 4, 6)], want[[0, 2, 4, 6]])
+        gc.close(per_res[k, (1, 3, 5)], want[[1, 3, 5]], rtol=1e-9, atol=1e-9)
+    atoms = rng.choice(len(xyz), 200, replace=False)
+    want = orc.sphere_sums_batch(g, rho, xyz[atoms], r35[:200], 0.0)
+    assert np.array_equal(per_atom[atoms, 0], want[:, 0])
+    gc.close(per_atom[atoms, 1], want[:, 1], rtol=1e-9, atol=1e-9)
