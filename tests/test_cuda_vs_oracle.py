@@ -254,3 +254,57 @@ def test_sphere_properties_at_scale():
     want = orc.sphere_sums_batch(g, rho, xyz[atoms], r35[:200], 0.0)
     assert np.array_equal(per_atom[atoms, 0], want[:, 0])
     gc.close(per_atom[atoms, 1], want[:, 1], rtol=1e-9, atol=1e-9)
+
+
+def test_blob_edge_cases():
+    """Empty foreground, a single class, every voxel foreground (one giant blob: worst case for the union-find),
+    capacity overflow with automatic retry, and a map whose stored grid is narrower than a vector load."""
+    import torch
+    from impl_cuda import CudaImpl
+    from impl_oracle import OracleImpl
+    from pdb_eda_b200 import ccp4, synthetic
+    vol = synthetic.smoothNoiseMap(40, seed=5, sigma=1.0)
+    dm = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(vol[:, :37, :35], (20.0,) * 3 + (90, 90, 90), (40, 40, 40))), "edge")
+    cuda, orc = CudaImpl(dm), OracleImpl(dm)
+    dev = dm.deviceMap
+    none = dev.blob_label(50.0, -50.0)                               # nothing beyond the cutoffs
+    assert all(p["n_voxels"] == 0 and p["n_blobs"] == 0 and len(p["crs"]) == 0 for p in none)
+    only_green = dev.blob_label(1.5, 0.0)
+    assert only_green[1] is None and only_green[0]["n_voxels"] > 0
+    assert dm.createFullBlobList(-50.0) == []
+    assert dev.blob_label(0.0, 0.0) == [None, None]
+    # everything is foreground: one blob holding the whole unique volume
+    lo = float(np.float32(vol.min())) - 1.0
+    shifted = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(vol[:, :37, :35] - lo, (20.0,) * 3 + (90, 90, 90), (40, 40, 40))), "dense")
+    full = shifted.deviceMap.blob_label(0.5, 0.0)[0]                  # all values >= 1 > 0.5
+    assert full["n_voxels"] == 40 * 37 * 35 and full["n_blobs"] == 1 and int(full["label"].max()) == 0
+    gc.close(full["stats"][0, 0].item(), 40 * 37 * 35)
+    # capacity overflow -> the wrapper grows the buffers and retries; results equal the roomy run
+    roomy = dev.blob_label(1.2, -1.2)
+    tight = dev.blob_label(1.2, -1.2, cap_voxels=64, cap_blobs=8)
+    for a, b in zip(roomy, tight):
+        assert torch.equal(a["crs"], b["crs"]) and torch.equal(a["label"], b["label"]) and torch.equal(a["stats"], b["stats"])
+    for (c1, l1, s1), (c2, l2, s2) in zip(cuda.full_blobs(1.2, -1.2), orc.full_blobs(1.2, -1.2)):
+        assert np.array_equal(c1, c2) and np.array_equal(l1, l2)
+        gc.close(s1, s2, rtol=1e-9, atol=1e-9)
+
+
+def test_empty_inputs_everywhere():
+    from pdb_eda_b200 import _device, ccp4, cutils, synthetic
+    dm = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(np.zeros((8, 8, 8), np.float32), (4.0,) * 3 + (90, 90, 90), (8, 8, 8))), "z")
+    dev = dm.deviceMap
+    assert dm.meanDensity == 0.0 and dm.stdDensity == 0.0
+    a, i, x = dev.symmetry_expand(np.zeros((0, 3)), np.zeros((2, 12)), np.zeros((27, 3)), [0, 0, 0], [1, 1, 1])
+    assert len(a) == 0 and len(i) == 0 and x.shape == (0, 3)
+    idx, dist = _device.nearest_atom(np.zeros((0, 3)), np.zeros((5, 3)))
+    assert len(idx) == 0 and len(dist) == 0
+    label, n = _device.cluster_crs(np.zeros((0, 3), np.int32))
+    assert n == 0 and len(label) == 0
+    assert len(cutils.overlapPairs(np.zeros((0, 3), np.int32), np.zeros(0, np.int32))) == 0
+    assert cutils.crsStats(dm, np.zeros((0, 3), np.int32), None, None, 0).shape == (0, 8)
+    assert cutils.createCrsLists([]) == [] and dm.createBlobList([]) == []
+    assert cutils.getSphereCrsFromXyzList(dm, [], 1.0) == set() and cutils.testValidXyzList(dm, [], 1.0)
+    assert cutils.sumOfAbs([], 0.5) == 0
+    assert cutils.getSphereCrsFromXyz(dm, [1.0, 1.0, 1.0], 0.0) in ([], [(2, 2, 2)])
+    with pytest.raises(Exception):
+        _device.nearest_atom(np.zeros((2, 3)), np.zeros((0, 3)))      # np.argmin of an empty row raises in the reference too
