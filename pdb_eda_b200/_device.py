@@ -13,8 +13,6 @@ from . import _blas
 from . import _lib
 from ._lib import PE_SPHERE_NOUT, PdbEdaLibError, PeGeom, check
 
-_F64P = ctypes.POINTER(ctypes.c_double)
-
 
 def geom_from_header(header, origin=None):
     """Packs a (duck-typed) ``DensityHeader`` into ``pe_geom``.

@@ -7,19 +7,20 @@
 //   DensityMatrix.getTotalDensityFromXyz                 pdb_eda/ccp4.py:418-435
 //   findAberrantBlobs(atom) clustering (createCrsLists)  pdb_eda/ccp4.py:437-461, pdb_eda/cutils.pyx:44-70
 //
-// Design (B200): the work per in-sphere voxel is one 4-byte gather, so the kernel is bounded by instruction
-// issue long before HBM; everything is arranged to keep the per-candidate instruction count minimal:
-//   * lanes run along the column axis (the contiguous one in memory) so every gather of a warp is a few
-//     contiguous segments; small boxes pack several box rows into one warp (rows-per-iteration = 32 / pow2(D0));
+// Design (B200): the work per in-sphere voxel is one 4-byte gather, so these kernels are bounded by instruction
+// issue (float64 membership tests, float64 accumulation) and L2 gathers long before HBM; everything is arranged to
+// keep the per-candidate instruction count minimal:
 //   * in orthogonal cells the squared distance separates per axis:  d2 = fl(fl(X2 + Y2) + Z2)  where each term
 //     is the already-rounded square the reference forms, so the per-axis squares and the wrapped memory offsets
-//     are tabulated once per atom in shared memory and a candidate costs one DADD + one DSETP; the loop nest is
-//     ordered so that fl(X2 + Y2) is hoisted out of the innermost loop;
+//     are tabulated once per atom in shared memory and a candidate costs one DADD + one DSETP;
 //   * sqrt is never evaluated:  sqrt_rn(d2) <= r  <=>  d2 <= T(r)  (sphere_threshold);
-//   * gathers are predicated, not branched, and the inner loop is unrolled for memory-level parallelism;
-//   * warp-shuffle reductions in a fixed order make the float64 sums run-to-run deterministic.
-// Skewed cells (and boxes wider than kDMax) take a generic path that evaluates the reference's 3x3 mat-vec per
-// candidate in the host BLAS's accumulation order.
+//   * per-atom kernel (one warp per atom): lanes run along the column axis (contiguous in memory), small boxes
+//     pack several box rows into one warp, gathers are predicated and the inner loop is unrolled;
+//   * union kernel (one persistent CTA walks the groups): membership by exact interval search per box row into a
+//     shared-memory bitmap, then one coalesced gather per voxel of the union (see sphere_union_kernel);
+//   * warp-shuffle / fixed-order block reductions make the float64 sums run-to-run deterministic.
+// Skewed cells take generic passes that evaluate the reference's 3x3 mat-vec per candidate in the host BLAS's
+// accumulation order.
 #include <limits.h>
 #include <type_traits>
 #include "pe_common.cuh"
@@ -95,20 +96,6 @@ __device__ __forceinline__ void fill_tables(const pe_geom &g, const AtomBox &b, 
         tab[1].off[k] = axis_off(g, 2, b.lo[2] + k);
     }
     __syncwarp();
-}
-
-// Is voxel (c, r, s) already owned by an earlier atom of the same group?  (set-union semantics)
-__device__ __forceinline__ bool claimed_by_earlier(const pe_geom &g, int first, int self, const int32_t *__restrict__ box,
-                                                   const double *__restrict__ thr, const double *__restrict__ xyz,
-                                                   int c, int r, int s) {
-    double vx, vy, vz;
-    crs2xyz(g, c, r, s, vx, vy, vz);
-    for (int e = first; e < self; ++e) {
-        const int32_t *b = box + 6 * e;
-        if (c < b[0] || c >= b[0] + b[3] || r < b[1] || r >= b[1] + b[4] || s < b[2] || s >= b[2] + b[5]) continue;
-        if (dist2(xyz[3 * e], xyz[3 * e + 1], xyz[3 * e + 2], vx, vy, vz) <= thr[e]) return true;
-    }
-    return false;
 }
 
 // Exact float -> double widening on the integer pipe.  (F2F.F64.F32 is a slow-rate conversion and was the top
