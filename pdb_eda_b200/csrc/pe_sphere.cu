@@ -98,16 +98,11 @@ __device__ __forceinline__ void fill_tables(const pe_geom &g, const AtomBox &b, 
     __syncwarp();
 }
 
-// Exact float -> double widening on the integer pipe.  (F2F.F64.F32 is a slow-rate conversion and was the top
-// stall of the gather loops in the first ncu capture, profiles/r01a_first_path.md.)
-__device__ __forceinline__ double widen(float v) {
-    const unsigned u = __float_as_uint(v);
-    const unsigned e = u & 0x7f800000u;
-    if (e == 0x7f800000u || (e == 0u && (u & 0x007fffffu) != 0u)) return (double)v;  // inf, nan, denormal: rare
-    const unsigned hi = (u & 0x80000000u) | (((u >> 3) & 0x0fffffffu) + 0x38000000u);
-    const double d = __hiloint2double((int)hi, (int)(u << 29));
-    return e == 0u ? 0.0 : d;
-}
+// float -> double widening.  An integer-pipe bit-twiddling version was tried when F2F.F64.F32 showed up as the top
+// stall of the first capture (profiles/r01a_first_path.md); once the gather loops kept four independent loads in
+// flight the plain conversion (one issue slot, its latency hidden) became the faster one again: 257 -> 231 us on
+// the C2 region pass.
+__device__ __forceinline__ double widen(float v) { return (double)v; }
 
 // Effective cutoffs: a class whose cutoff is 0 is switched off by an unreachable threshold.
 __device__ __forceinline__ float eff_pos(float cp) { return cp > 0.f ? cp : __int_as_float(0x7f800000); }
