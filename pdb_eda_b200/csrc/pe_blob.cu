@@ -236,7 +236,7 @@ __device__ __forceinline__ void neighbours_in_column(const uint32_t *__restrict_
     }
 }
 
-__global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __grid_constant__ pe_geom g, const SparseArgs a) {
+__global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __grid_constant__ pe_geom g, const SparseArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t smem[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -265,25 +265,68 @@ __global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __
     grid.sync();
     stamp(1);
 
-    // ---- S1b + S2: positions, then key / value / initial parent of every foreground voxel
+    // ---- S1b + S2 (one pass): position of every word's first voxel, then key / initial parent of every foreground
+    // voxel.  Keys go to a temporary array indexed by the combined position (the rank buffer, free until S5), because
+    // the class-1 output offset needs n0, which is only known grid-wide after the next barrier.  Words are fetched
+    // four iterations ahead so that the L2 latency of the loads overlaps.
     uint32_t before, n_all;
     grid_prefix(a.sums, nb, b, smem, before, n_all);
-    // class 0 count = positions below the first word of plane 1; found by whoever owns that word (see below)
     uint32_t run = before;
     for (int i = 0; i < warp; ++i) run += warp_cnts[i];
-    __shared__ int s_overflow;
-    for (int64_t i0 = w_begin; i0 < w_end; i0 += 32) {
-        const int64_t widx = i0 + lane;
-        const uint32_t word = widx < w_end ? a.bmp[widx] : 0u;
-        const int c0 = __popc(word);
-        const uint32_t p0 = run + (uint32_t)warp_excl_scan(c0, lane);
-        run += (uint32_t)__shfl_sync(kFull, (int)(p0 - run) + c0, 31);
-        if (widx < w_end) {
-            a.base[widx] = p0;
-            if (widx == a.nwords_pad) a.counts[0] = (int64_t)p0;  // everything before plane 1 is class 0
+    uint32_t *keyc = a.rank;
+    const uint32_t pcap = (uint32_t)(2 * a.cap);
+    uint32_t carry = (w_begin > 0 && w_begin < w_end) ? a.bmp[w_begin - 1] : 0u;  // the word before the current one (lane 0's predecessor)
+    for (int64_t i0 = w_begin; i0 < w_end; i0 += 128) {
+        uint32_t wq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t widx = i0 + 32 * q + lane;
+            wq[q] = widx < w_end ? a.bmp[widx] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t widx = i0 + 32 * q + lane;
+            const uint32_t word = wq[q];
+            const int c0 = __popc(word);
+            const uint32_t p_first = run + (uint32_t)warp_excl_scan(c0, lane);
+            run += (uint32_t)__shfl_sync(kFull, (int)(p_first - run) + c0, 31);
+            uint32_t prev = __shfl_up_sync(kFull, word, 1);
+            if (lane == 0) prev = carry;
+            carry = __shfl_sync(kFull, word, 31);
+            if (widx >= w_end) continue;
+            a.base[widx] = p_first;
+            if (widx == a.nwords_pad) a.counts[0] = (int64_t)p_first;  // everything before plane 1 is class 0
+            if (!word) continue;
+            const int k = widx >= a.nwords_pad ? 1 : 0;
+            const int64_t local = widx - (k ? a.nwords_pad : 0);
+            const int w = (int)(local % a.W);
+            const int64_t colrow = local / a.W;
+            const bool prev_last = (w > 0) && (prev >> 31);
+            // bits that start a run of consecutive sections inside this word (a run entering from the previous word
+            // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
+            const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
+            const uint32_t keybase = (uint32_t)(colrow * a.U2 + (int64_t)w * 32);
+            uint32_t rest = word, p = p_first;
+            while (rest) {
+                const int bit = __ffs(rest) - 1;
+                rest &= rest - 1;
+                // parent = first voxel of the run (path-compressed chaining: finds stay O(1) instead of O(run length))
+                const uint32_t below = starts & ((2u << bit) - 1u);
+                uint32_t par;
+                if (below) {
+                    const int sb = 31 - __clz(below);
+                    par = p_first + (uint32_t)__popc(word & ((1u << sb) - 1u));
+                } else {
+                    par = p_first - 1;  // the run continues from the previous word (prev_last is set)
+                }
+                if (p < pcap) {  // beyond the capacity the overflow flag is raised after the barrier
+                    keyc[p] = keybase + (uint32_t)bit;
+                    a.parent[p] = par;
+                }
+                ++p;
+            }
         }
     }
-    if (b == 0 && threadIdx.x == 0) a.counts[2] = (int64_t)n_all;  // provisional: total; fixed up after the barrier
     grid.sync();
     stamp(2);
     const int64_t n0 = a.counts[0];
@@ -295,44 +338,6 @@ __global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __
         if (overflow) a.counts[4] = 1;
     }
     if (overflow) return;  // grid-uniform
-    (void)s_overflow;
-    for (int64_t i0 = w_begin; i0 < w_end; i0 += 32) {
-        const int64_t widx = i0 + lane;
-        if (widx >= w_end) continue;
-        uint32_t word = a.bmp[widx];
-        if (!word) continue;
-        const int k = widx >= a.nwords_pad ? 1 : 0;
-        const int64_t local = widx - (k ? a.nwords_pad : 0);
-        const int w = (int)(local % a.W);
-        const int64_t colrow = local / a.W;
-        const int r = (int)(colrow % a.U1), c = (int)(colrow / a.U1);
-        const bool prev_last = (w > 0) && (a.bmp[widx - 1] >> 31);
-        // bits that start a run of consecutive sections inside this word (a run entering from the previous word
-        // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
-        const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
-        const uint32_t p_first = a.base[widx];
-        uint32_t p = p_first;
-        const uint32_t keybase = (uint32_t)(colrow * a.U2 + (int64_t)w * 32);
-        const int64_t out0 = (int64_t)k * a.cap - (k ? n0 : 0);
-        const uint32_t all = word;
-        while (word) {
-            const int bit = __ffs(word) - 1;
-            word &= word - 1;
-            a.key[out0 + p] = keybase + (uint32_t)bit;
-            // parent = first voxel of the run (path-compressed chaining: finds stay O(1) instead of O(run length))
-            const uint32_t below = starts & ((2u << bit) - 1u);
-            uint32_t par;
-            if (below) {
-                const int sb = 31 - __clz(below);
-                par = p_first + (uint32_t)__popc(all & ((1u << sb) - 1u));
-            } else {
-                par = p_first - 1;  // the run continues from the previous word (prev_last is set)
-            }
-            a.parent[p] = par;
-            ++p;
-        }
-    }
-    grid.sync();
     stamp(3);
 
     // ---- S3: hook the 12 predecessor neighbours outside the voxel's own column
@@ -341,7 +346,8 @@ __global__ void __launch_bounds__(kSparseThreads, 2) blob_sparse_kernel(const __
     for (int64_t i = gtid; i < n; i += gstride) {
         const int k = i >= n0 ? 1 : 0;
         const uint32_t p = (uint32_t)i;
-        const uint32_t kk = a.key[(int64_t)k * a.cap + (i - (k ? n0 : 0))];
+        const uint32_t kk = a.rank[i];  // the key parked by S2
+        a.key[(int64_t)k * a.cap + (i - (k ? n0 : 0))] = kk;
         const int s = (int)(kk % (uint32_t)a.U2);
         const uint32_t colrow = kk / (uint32_t)a.U2;
         const int r = (int)(colrow % (uint32_t)a.U1), c = (int)(colrow / (uint32_t)a.U1);
@@ -548,7 +554,7 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, blob_sparse_kernel, kSparseThreads, 0));
         PE_CHECK_ARG(blocks_per_sm > 0, "pe_blob_label: the sparse kernel does not fit an SM");
     }
-    int nblocks = sm_count() * (blocks_per_sm < 2 ? blocks_per_sm : 2);
+    int nblocks = sm_count() * (blocks_per_sm < 3 ? blocks_per_sm : 3);
     if (nblocks > kSparseMaxBlocks) nblocks = kSparseMaxBlocks;
     pe_geom geom = *g;
     void *args[] = {(void *)&geom, (void *)&a};

@@ -114,22 +114,26 @@ struct SphereAcc {
     // v must be 0 when the voxel is not taken; cp / cn are the effective cutoffs (cp > 0 > cn).
     __device__ __forceinline__ void add(bool take, float v, float cp, float cn) {
         const double d = widen(v);
-        const bool p = v > cp, q = v < cn;
-        n_all += take ? 1 : 0;
         s_all += d;
-        n_pos += p ? 1 : 0;
-        s_pos += p ? d : 0.0;
-        n_neg += q ? 1 : 0;
-        s_neg += q ? d : 0.0;
+        if (take) ++n_all;
+        if (v > cp) {
+            ++n_pos;
+            s_pos += d;
+        }
+        if (v < cn) {
+            ++n_neg;
+            s_neg += d;
+        }
     }
     // the same with the negative class switched off (cn == -inf): a third less work per voxel
     __device__ __forceinline__ void add_pos(bool take, float v, float cp) {
         const double d = widen(v);
-        const bool p = v > cp;
-        n_all += take ? 1 : 0;
         s_all += d;
-        n_pos += p ? 1 : 0;
-        s_pos += p ? d : 0.0;
+        if (take) ++n_all;
+        if (v > cp) {
+            ++n_pos;
+            s_pos += d;
+        }
     }
 };
 
