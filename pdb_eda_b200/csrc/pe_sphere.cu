@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
 constexpr int kUnionWarps = 4;
 constexpr int kTileC = 64, kTileR = 48, kTileS = 48;
 
-constexpr int kUnionChunk = 8;  // atoms whose tables are resident at once
+constexpr int kUnionChunk = 8;       // atoms whose tables are resident at once
+constexpr int kRowsPerQuarter = 4;   // bitmap rows a quarter-warp gathers concurrently (= loads in flight per lane)
 
 struct UnionShared {
     uint32_t bits[kTileR * kTileS * 2];
@@ -272,7 +273,6 @@ struct UnionShared {
     int offC[kTileC], offR[kTileR], offS[kTileS];  // wrapped element offsets of the tile's indices
     int cLo[kUnionChunk], nC[kUnionChunk], rLo[kUnionChunk], nR[kUnionChunk], sLo[kUnionChunk], nS[kUnionChunk];
     int kMin[kUnionChunk];             // column (index into sqC) nearest the atom: the minimum of its sqC
-    int itemStart[kUnionChunk + 1];    // prefix sums of nR * nS: one work item per box row
 };
 
 // MODE 0: z is carried by the row axis, 1: by the section axis, 2: by the column axis.
@@ -289,53 +289,60 @@ __device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, dou
 // columns of a box row the squared distance falls to the column nearest the atom and rises again (every rounding
 // step is monotone), so the in-sphere columns are one interval around that column and two binary searches with
 // the EXACT predicate find its ends -- ~8 float64 tests per box row instead of one per candidate voxel.
-template <int MODE>
+template <int MODE, bool WIDE>
 __device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int tid, int nthreads) {
-    const int total = sh.itemStart[nchunk];
-    for (int item = tid; item < total; item += nthreads) {
-        int j = 0;
-        while (item >= sh.itemStart[j + 1]) ++j;
-        const int li = item - sh.itemStart[j];
-        const int nS = sh.nS[j];
-        const int ir = li / nS, is = li - ir * nS;
-        const double sr = sh.sqR[j][ir], ss = sh.sqS[j][is];
-        const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
-        const double B = (MODE == 0) ? sr : ss;
+    for (int j = 0; j < nchunk; ++j) {  // block-uniform
+        const int nR = sh.nR[j], nS = sh.nS[j], nC = sh.nC[j];
+        if (nR <= 0) continue;
+        // items of this atom: its box rows, laid out with the section count padded to a power of two (no division)
+        const int shift = nS > 1 ? 32 - __clz(nS - 1) : 0;
+        const int total = nR << shift;
         const double T = sh.T[j];
         const double *sqc = sh.sqC[j];
         // the column nearest the atom: the box's centre column or, after rounding, one of its neighbours
         int km = sh.kMin[j];
-        {
-            const int nCj = sh.nC[j];
-            if (km > 0 && sqc[km - 1] < sqc[km]) --km;
-            else if (km + 1 < nCj && sqc[km + 1] < sqc[km]) ++km;
+        if (km > 0 && sqc[km - 1] < sqc[km]) --km;
+        else if (km + 1 < nC && sqc[km + 1] < sqc[km]) ++km;
+        const int cbit = sh.cLo[j];
+        uint32_t *rows = sh.bits + 2 * (sh.rLo[j] * kTileS + sh.sLo[j]);
+        for (int li = tid; li < total; li += nthreads) {
+            const int is = li & ((1 << shift) - 1), ir = li >> shift;
+            if (is >= nS) continue;
+            const double sr = sh.sqR[j][ir], ss = sh.sqS[j][is];
+            const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
+            const double B = (MODE == 0) ? sr : ss;
+            if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
+            int lo = 0, hi = km;  // smallest k in [0, km] inside
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (row_pred<MODE>(sqc, mid, A, B, T))
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            const int kl = lo;
+            lo = km;
+            hi = nC - 1;  // largest k in [km, nC) inside
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (row_pred<MODE>(sqc, mid, A, B, T))
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const int count = lo - kl + 1;
+            uint32_t *word = rows + 2 * (ir * kTileS + is);
+            if (WIDE) {
+                const unsigned long long run = count >= 64 ? ~0ull : ((1ull << count) - 1ull);
+                const unsigned long long wide = run << (cbit + kl);
+                const uint32_t wlo = (uint32_t)wide, whi = (uint32_t)(wide >> 32);
+                if (wlo) atomicOr(word, wlo);
+                if (whi) atomicOr(word + 1, whi);
+            } else {  // the tile is at most 32 columns wide
+                const uint32_t run = count >= 32 ? ~0u : ((1u << count) - 1u);
+                atomicOr(word, run << (cbit + kl));
+            }
         }
-        if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
-        int lo = 0, hi = km;  // smallest k in [0, km] inside
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (row_pred<MODE>(sqc, mid, A, B, T))
-                hi = mid;
-            else
-                lo = mid + 1;
-        }
-        const int kl = lo;
-        lo = km;
-        hi = sh.nC[j] - 1;  // largest k in [km, nC) inside
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (row_pred<MODE>(sqc, mid, A, B, T))
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        const int count = lo - kl + 1;
-        const unsigned long long run = count >= 64 ? ~0ull : ((1ull << count) - 1ull);
-        const unsigned long long wide = run << (sh.cLo[j] + kl);
-        uint32_t *word = sh.bits + 2 * ((sh.rLo[j] + ir) * kTileS + (sh.sLo[j] + is));
-        const uint32_t wlo = (uint32_t)wide, whi = (uint32_t)(wide >> 32);
-        if (wlo) atomicOr(word, wlo);
-        if (whi) atomicOr(word + 1, whi);
     }
 }
 
@@ -380,32 +387,38 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
             if ((mine.x | mine.y) != 0u)  // leave the bitmap clear for the next tile
                 *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
             while (nz) {
-                int src[2] = {-1, -1};  // the next (up to) eight non-empty sections, two per quarter-warp
+                int src[kRowsPerQuarter];  // the next (up to) 4 * kRowsPerQuarter non-empty sections
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int u = 0; u < kRowsPerQuarter; ++u) src[u] = -1;
+#pragma unroll
+                for (int q = 0; q < 4 * kRowsPerQuarter; ++q) {
                     const int f = nz ? (__ffs(nz) - 1) : -1;
                     if (nz) nz &= nz - 1;
-                    if ((q >> 1) == sg) src[q & 1] = f;
+                    if ((q / kRowsPerQuarter) == sg) src[q % kRowsPerQuarter] = f;
                 }
-                word_t w[2];
-                int ors[2];
-                unsigned srs[2];
+                word_t w[kRowsPerQuarter];
+                int ors[kRowsPerQuarter];
+                unsigned srs[kRowsPerQuarter];
+                word_t any = 0;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < kRowsPerQuarter; ++u) {
                     const uint32_t lo = __shfl_sync(kFull, mine.x, src[u] < 0 ? 0 : src[u]);
                     word_t full = lo;
                     if (WIDE) full = (word_t)(((unsigned long long)__shfl_sync(kFull, mine.y, src[u] < 0 ? 0 : src[u]) << 32) | lo);
                     w[u] = src[u] < 0 ? (word_t)0 : full;
+                    any |= w[u];
                     const int os = src[u] < 0 ? (CHECKED ? kInvalidOff : 0) : sh.offS[sl0 + src[u]];
                     ors[u] = orow | os;
                     srs[u] = (unsigned)orow + (unsigned)os;
                 }
-                while (__any_sync(kFull, (w[0] | w[1]) != (word_t)0)) {
-                    float v[4];
-                    bool bit[4];
+                while (__any_sync(kFull, any != (word_t)0)) {
+                    // one window per row and trip: kRowsPerQuarter independent loads in flight per lane
+                    float v[kRowsPerQuarter];
+                    bool bit[kRowsPerQuarter];
+                    any = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        word_t &ww = w[u >> 1];
+                    for (int u = 0; u < kRowsPerQuarter; ++u) {
+                        word_t &ww = w[u];
                         int first;
                         if (WIDE)
                             first = ww ? (__ffsll((long long)ww) - 1) : 0;
@@ -416,16 +429,17 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
                         v[u] = 0.f;
                         if (CHECKED) {
                             const int oc = bit[u] ? sh.offC[col] : kInvalidOff;
-                            const bool ok = (ors[u >> 1] | oc) >= 0;
-                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs[u >> 1] + (unsigned)oc));
+                            const bool ok = (ors[u] | oc) >= 0;
+                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs[u] + (unsigned)oc));
                             acc.bad |= (bit[u] && !ok) ? 1 : 0;
                         } else {
-                            if (bit[u]) v[u] = __ldg(rho + (int)(srs[u >> 1] + (unsigned)sh.offC[col]));
+                            if (bit[u]) v[u] = __ldg(rho + (int)(srs[u] + (unsigned)sh.offC[col]));
                         }
                         ww &= ~(((word_t)0xff) << first);  // no-op when ww == 0 (first = 0)
+                        any |= ww;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kRowsPerQuarter; ++u) {
                         if (HASNEG)
                             acc.add(bit[u], v[u], cp, cn);
                         else
@@ -512,14 +526,6 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                                 sh.kMin[tid] = hit ? min(max(bx[0] + bx[3] / 2 - cl, 0), ch - cl - 1) : 0;
                             }
                             __syncthreads();
-                            if (tid == 0) {
-                                int run = 0;
-                                for (int j = 0; j < nchunk; ++j) {
-                                    sh.itemStart[j] = run;
-                                    run += sh.nR[j] * sh.nS[j];
-                                }
-                                sh.itemStart[nchunk] = run;
-                            }
                             for (int idx = tid; idx < nchunk * (kTileC + kTileR + kTileS); idx += blockDim.x) {
                                 const int j = idx / (kTileC + kTileR + kTileS), e = idx - j * (kTileC + kTileR + kTileS);
                                 const int a = c0 + j;
@@ -535,7 +541,10 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                                 }
                             }
                             __syncthreads();
-                            union_mark_rows<MODE>(sh, nchunk, tid, blockDim.x);
+                            if (tC > 32)
+                                union_mark_rows<MODE, true>(sh, nchunk, tid, blockDim.x);
+                            else
+                                union_mark_rows<MODE, false>(sh, nchunk, tid, blockDim.x);
                             __syncthreads();  // tables are reused by the next chunk
                         }
                     } else {
