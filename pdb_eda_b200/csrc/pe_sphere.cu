@@ -159,18 +159,21 @@ __device__ __forceinline__ void sums_ortho(const pe_geom &g, const float *__rest
         const int c = b.lo[0] + ic;
         const double sqc = act ? axis_sq(g, 0, c, ax, ay, az) : 0.0;
         const int offc = act ? axis_off(g, 0, c) : kInvalidOff;
-        for (int ko = lrow; ko < Do; ko += rpi) {
-            const double sqo = to.sq[ko];
-            const int offo = to.off[ko];
+        for (int ko0 = 0; ko0 < Do; ko0 += rpi) {  // warp-uniform trip count (the ballot below needs every lane)
+            const int ko = ko0 + lrow;
+            const bool rowact = act && ko < Do;
+            const double sqo = rowact ? to.sq[ko] : 0.0;
+            const int offo = rowact ? to.off[ko] : kInvalidOff;
             const double P = __dadd_rn(sqc, sqo);  // fl(X2 + Y2) when !CASEB
             const int offco = offc | offo;
             const int sumco = (int)((unsigned)offc + (unsigned)offo);
-#pragma unroll 4
+#pragma unroll 2
             for (int ki = 0; ki < Di; ++ki) {
                 const double sqi = ti.sq[ki];
                 const int offi = ti.off[ki];
                 const double d2 = CASEB ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
-                bool inside = act && (d2 <= T);
+                const bool inside = rowact && (d2 <= T);
+                if (!__any_sync(kFull, inside)) continue;  // most of a box lies outside its sphere: nothing to gather
                 const bool ok = (offco | offi) >= 0;
                 float v = 0.f;
                 if (inside && ok) v = __ldg(rho + (int)((unsigned)sumco + (unsigned)offi));
