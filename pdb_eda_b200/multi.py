@@ -137,9 +137,30 @@ def gatherResults(results, indices, nStructures, atomTypes, device="cpu", group=
             "sizeDiffs": sizeDiffs, "atomTypeOverlapCompleteness": completeness}
 
 
-def runMultipleStructures(items, loader, costs=None, atomTypes=None, device=None, group=None):
+def _workerInit(deviceIndex, params):
+    """Initialiser of a host worker process: its own CUDA context on the rank's GPU, the parent's parameter set."""
+    from . import densityAnalysis
+    if torch.cuda.is_available():
+        torch.cuda.set_device(deviceIndex)
+    densityAnalysis.setGlobals(params)
+
+
+def _workerAnalyze(args):
+    loader, item, atomTypes = args
+    try:
+        return analyzeStructure(loader(item), atomTypes)
+    except Exception:
+        return 0
+
+
+def runMultipleStructures(items, loader, costs=None, atomTypes=None, device=None, group=None, workers=1):
     """Multiple-structures mode: ``loader(item)`` returns a DensityAnalysis (or 0); structures are sharded over the
-    ranks of the default process group, analysed on this rank's GPU, and summarised collectively."""
+    ranks of the default process group, analysed on this rank's GPU, and summarised collectively.
+
+    ``workers`` > 1: the per-structure host work (file parsing, the reference's set-growth bookkeeping, the numpy
+    statistics block) is what bounds throughput, not the kernels, so a rank may spread its share over a pool of
+    host processes that all drive the rank's GPU -- the reference's ``multiprocessing.Pool`` (pdb_eda/multipleStructures.py:167)
+    with the voxel loops on the device.  ``loader`` must then be picklable (a module-level function or functools.partial)."""
     from . import densityAnalysis
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -147,11 +168,20 @@ def runMultipleStructures(items, loader, costs=None, atomTypes=None, device=None
     costs = [1.0] * len(items) if costs is None else costs
     mine = shardStructures(costs, world)[rank]
     results = {}
-    for idx in mine:
-        try:
-            results[idx] = analyzeStructure(loader(items[idx]), atomTypes)
-        except Exception:
-            results[idx] = 0                     # a bad structure yields no row; the run continues
+    if workers > 1 and len(mine) > 1:
+        import torch.multiprocessing as mp
+        index = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        order = sorted(mine, key=lambda i: -float(costs[i]))                       # longest first, one task per structure
+        with mp.get_context("spawn").Pool(min(workers, len(mine)), initializer=_workerInit,
+                                          initargs=(index, densityAnalysis.paramsGlobal)) as pool:
+            for idx, res in zip(order, pool.map(_workerAnalyze, [(loader, items[i], atomTypes) for i in order], chunksize=1)):
+                results[idx] = res
+    else:
+        for idx in mine:
+            try:
+                results[idx] = analyzeStructure(loader(items[idx]), atomTypes)
+            except Exception:
+                results[idx] = 0                     # a bad structure yields no row; the run continues
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     return gatherResults(results, mine, len(items), atomTypes, device, group)

@@ -1,7 +1,7 @@
 """``multiple`` mode command line: many PDB entries, sharded over the GPUs of the node (pdb_eda/multipleStructures.py:61-194).
 
 Usage:
-    python -m pdb_eda_b200 multiple <pdbid-file> <out-result-file> [--out-format json|csv] [--params FILE] [--data-dir DIR]
+    python -m pdb_eda_b200 multiple <pdbid-file> <out-result-file> [--out-format json|csv] [--params FILE] [--data-dir DIR] [--workers W]
     torchrun --nproc-per-node N -m pdb_eda_b200 multiple ...        (one rank per GPU; rank 0 writes the result)
 
 <pdbid-file>: JSON list or whitespace-separated text of PDB ids.  --data-dir: analyse DIR/<id>.ccp4, DIR/<id>_diff.ccp4,
@@ -10,6 +10,7 @@ DIR/pdb<id>.ent(.gz) instead of downloading.  Result: per-entry ``stats`` and ``
 """
 import argparse
 import csv
+import functools
 import json
 import os
 import sys
@@ -32,18 +33,21 @@ def readIds(path):
     return [str(i).lower() for i in ids]
 
 
+def loadEntry(dataDir, pdbid):
+    """DensityAnalysis of one entry: downloaded (``dataDir`` empty) or read from DIR/<id>.ccp4, DIR/<id>_diff.ccp4, DIR/pdb<id>.ent(.gz)."""
+    if not dataDir:
+        return densityAnalysis.fromPDBid(pdbid)
+    pdb = os.path.join(dataDir, "pdb" + pdbid + ".ent.gz")
+    if not os.path.isfile(pdb):
+        pdb = os.path.join(dataDir, "pdb" + pdbid + ".ent")
+    an = densityAnalysis.fromFile(pdb, os.path.join(dataDir, pdbid + ".ccp4"), os.path.join(dataDir, pdbid + "_diff.ccp4"))
+    if an:
+        an.pdbid = pdbid
+    return an
+
+
 def makeLoader(dataDir):
-    def loader(pdbid):
-        if not dataDir:
-            return densityAnalysis.fromPDBid(pdbid)
-        pdb = os.path.join(dataDir, "pdb" + pdbid + ".ent.gz")
-        if not os.path.isfile(pdb):
-            pdb = os.path.join(dataDir, "pdb" + pdbid + ".ent")
-        an = densityAnalysis.fromFile(pdb, os.path.join(dataDir, pdbid + ".ccp4"), os.path.join(dataDir, pdbid + "_diff.ccp4"))
-        if an:
-            an.pdbid = pdbid
-        return an
-    return loader
+    return functools.partial(loadEntry, dataDir)     # picklable: usable by the host worker pool
 
 
 def main(argv=None):
@@ -53,6 +57,7 @@ def main(argv=None):
     p.add_argument("--out-format", default="json", choices=["json", "csv"])
     p.add_argument("--params", default="")
     p.add_argument("--data-dir", default="")
+    p.add_argument("--workers", type=int, default=1, help="host worker processes per rank (all drive the rank's GPU)")
     args = p.parse_args(argv)
     if args.params:
         densityAnalysis.setGlobals(json.load(open(args.params)))
@@ -63,7 +68,7 @@ def main(argv=None):
     rank = dist.get_rank() if dist.is_initialized() else 0
     ids = readIds(args.pdbid_file)
     types = sorted(densityAnalysis.paramsGlobal["radii"])
-    summary = multi.runMultipleStructures(ids, makeLoader(args.data_dir), None, types)
+    summary = multi.runMultipleStructures(ids, makeLoader(args.data_dir), None, types, workers=args.workers)
     if rank == 0:
         cols = summary["columns"]
         full = {}

@@ -65,6 +65,11 @@ def test_single_and_multiple_end_to_end(tmp_path):
     multipleStructures.main([idfile, out, "--data-dir", folder])
     res = json.load(open(out))
     assert sorted(res["entries"]) == ids and res["cumulative"]["structures"] == 3
+    out2 = os.path.join(folder, "multi_workers.json")
+    multipleStructures.main([idfile, out2, "--data-dir", folder, "--workers", "2"])        # host worker pool on the same GPU
+    res2 = json.load(open(out2))
+    assert sorted(res2["entries"]) == ids and res2["cumulative"]["num_voxels_aggregated"] == res["cumulative"]["num_voxels_aggregated"]
+    assert res2["entries"]["2bbb"]["stats"]["density_electron_ratio"] == res["entries"]["2bbb"]["stats"]["density_electron_ratio"]
     np.testing.assert_allclose(res["entries"]["1aaa"]["stats"]["density_electron_ratio"], an.densityElectronRatio, rtol=1e-12)
 
 
