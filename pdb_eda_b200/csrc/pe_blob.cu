@@ -72,16 +72,16 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
 // bit planes no longer fit L2 (768^3 ran at 28 % of the HBM peak, tune log in profiles/r01_threshold_tuning.md).
 constexpr int kWordsPerThread = 4;
 
-template <int VEC, int TY, int MINB>
-__global__ void __launch_bounds__(kBmpTx *TY, MINB)
+template <int VEC>
+__global__ void __launch_bounds__(384)
     threshold_bitmap_kernel(const float *__restrict__ rho, int NC, int NR, int U0, int U1, int U2, int W, float cpos,
                             float cneg, bool use_pos, bool use_neg, uint32_t *__restrict__ bmp_pos,
                             uint32_t *__restrict__ bmp_neg) {
-    const int c = (blockIdx.y * kBmpTx + threadIdx.x) * VEC;
-    const int r = blockIdx.z * TY + threadIdx.y;
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+    const int r = blockIdx.z * blockDim.y + threadIdx.y;
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0) {  // padding between / after the planes
         const int64_t nwords = (int64_t)U0 * U1 * W;
-        for (int64_t i = nwords + threadIdx.x; i < nwords + 64; i += kBmpTx) {
+        for (int64_t i = nwords + threadIdx.x; i < nwords + 64; i += blockDim.x) {
             if (i < (nwords + 63) / 64 * 64) {
                 bmp_pos[i] = 0u;
                 bmp_neg[i] = 0u;
@@ -514,14 +514,15 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     {
         const bool vec4 = (NC % 4 == 0) && (((uintptr_t)d_rho & 15u) == 0);
         const int vec = vec4 ? 4 : 1;
-        dim3 block(kBmpTx, kBmpTy, 1);
-        dim3 grid(p.W / kWordsPerThread, (p.U0 + kBmpTx * vec - 1) / (kBmpTx * vec), (p.U1 + kBmpTy - 1) / kBmpTy);
+        const int tx = kBmpTx, ty = kBmpTy;  // block shape makes no measurable difference (profiles/r01_threshold_tuning.md)
+        dim3 block(tx, ty, 1);
+        dim3 grid(p.W / kWordsPerThread, (p.U0 + tx * vec - 1) / (tx * vec), (p.U1 + ty - 1) / ty);
         PE_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "pe_blob_label: map too large for the launch grid");
         if (vec4)
-            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4, kBmpTy, 1><<<grid, block, 0, st>>>(
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(
                 d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
         else
-            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1, kBmpTy, 1><<<grid, block, 0, st>>>(
+            PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(
                 d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
         PE_LAUNCH_CHECK();
     }
