@@ -56,6 +56,9 @@ __device__ __forceinline__ void atom_box(const pe_geom &g, double ax, double ay,
     thr = sphere_threshold(r);
 }
 
+// Boxes and distance thresholds of a batch of atoms, one thread per atom.  Kept as its own (8 us) launch for the
+// per-atom kernel: computing them in that kernel's prologue put a float64 divide / sqrt chain in front of every
+// warp (49 -> 60-72 us); the union kernel, which is persistent, does compute them itself.
 __global__ void sphere_params_kernel(pe_geom g, int n, const double *__restrict__ xyz, const float *__restrict__ radius,
                                      int32_t *__restrict__ box, double *__restrict__ thr) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -462,7 +465,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kUnionWarps * 32, 7)
     sphere_union_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_groups,
                         const int32_t *__restrict__ group_start, const double *__restrict__ xyz,
-                        const int32_t *__restrict__ box, const double *__restrict__ thr, float cp, float cn,
+                        const float *__restrict__ radius, int32_t *box, double *thr, float cp, float cn,
                         double *__restrict__ out /* n_groups x PE_SPHERE_NOUT */) {
     __shared__ UnionShared sh;
     __shared__ double red_d[kUnionWarps][3];
@@ -476,7 +479,19 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
     for (int i = tid; i < kTileR * kTileS * 2; i += blockDim.x) sh.bits[i] = 0u;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const int a0 = group_start[grp], a1 = group_start[grp + 1];
-    __syncthreads();  // the previous group's reduction scratch has been consumed
+    // boxes and distance thresholds of the group's atoms (into the workspace arrays: any group size)
+    for (int a = a0 + tid; a < a1; a += blockDim.x) {
+        AtomBox bb;
+        double tt;
+        atom_box(g, xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2], radius[a], bb, tt);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            box[6 * a + k] = bb.lo[k];
+            box[6 * a + 3 + k] = bb.dim[k];
+        }
+        thr[a] = tt;
+    }
+    __syncthreads();  // boxes visible block-wide; the previous group's reduction scratch has been consumed
     // the group's bounding box
     int ulo0 = INT_MAX, ulo1 = INT_MAX, ulo2 = INT_MAX, uhi0 = INT_MIN, uhi1 = INT_MIN, uhi2 = INT_MIN;
     double candidates = 0.0;
@@ -886,13 +901,11 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     double *thr = (double *)ws;
     ws += align_up((int64_t)n_atoms * 8, 256);
     const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
-    if (n_atoms > 0) {
-        PE_LAUNCH("sphere_params_kernel", st, sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr));
-        PE_LAUNCH_CHECK();
-    }
     if (d_group_start == nullptr) {
-        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr, cut_pos,
-                                                                        cut_neg, d_out));
+        if (n_atoms > 0)
+            PE_LAUNCH("sphere_params_kernel", st, sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr));
+        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+                                                                                             cut_pos, cut_neg, d_out));
         PE_LAUNCH_CHECK();
         return PE_OK;
     }
@@ -901,13 +914,13 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
         const int ugrid = min(n_groups, sm_count() * 7);                           // persistent: 7 CTAs fit an SM
         if (mode == 0)
             PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<0><<<ugrid, kUnionWarps * 32, 0, st>>>(
-                *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
+                *g, d_rho, n_groups, d_group_start, d_xyz, d_radius, box, thr, cut_pos, cut_neg, d_out));
         else if (mode == 1)
             PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<1><<<ugrid, kUnionWarps * 32, 0, st>>>(
-                *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
+                *g, d_rho, n_groups, d_group_start, d_xyz, d_radius, box, thr, cut_pos, cut_neg, d_out));
         else
             PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<2><<<ugrid, kUnionWarps * 32, 0, st>>>(
-                *g, d_rho, n_groups, d_group_start, d_xyz, box, thr, cut_pos, cut_neg, d_out));
+                *g, d_rho, n_groups, d_group_start, d_xyz, d_radius, box, thr, cut_pos, cut_neg, d_out));
     }
     PE_LAUNCH_CHECK();
     return PE_OK;
