@@ -51,3 +51,24 @@ def random_atoms(dm, n, seed, margin=2.0):
     crs = np.stack([rng.uniform(-margin, h.ncrs[a] + margin, n) for a in range(3)], axis=1)
     xyz = np.array([np.asarray(h.crs2xyzCoord([float(c) for c in row]), dtype=np.float64) for row in crs])
     return np.round(xyz, 3).astype(np.float32)
+
+
+def random_geometry(seed):
+    """A random cell (orthogonal / monoclinic / triclinic by seed % 3), axis order, start and stored extent (fewer or more
+    voxels than intervals).  Returns (ccp4 bytes, values)."""
+    import itertools
+    rng = np.random.default_rng(1000 + seed)
+    intervals = tuple(int(v) for v in rng.integers(20, 44, 3))
+    cell_len = [iv * float(rng.uniform(0.35, 0.8)) for iv in intervals]
+    if seed % 3 == 0:
+        angles = (90.0, 90.0, 90.0)
+    elif seed % 3 == 1:
+        angles = (90.0, float(rng.uniform(95, 120)), 90.0)
+    else:
+        angles = tuple(float(v) for v in rng.uniform(70, 115, 3))
+    order = list(itertools.permutations((1, 2, 3)))[int(rng.integers(6))]
+    axes = [a - 1 for a in order]
+    ncrs = [int(intervals[axes[k]] * rng.uniform(0.6, 1.3)) for k in range(3)]
+    start = tuple(int(v) for v in rng.integers(-9, 10, 3))
+    values = _noise((ncrs[2], ncrs[1], ncrs[0]), 2000 + seed)
+    return synthetic.ccp4Bytes(values, tuple(cell_len) + angles, intervals, crsStart=start, axisOrder=order), values

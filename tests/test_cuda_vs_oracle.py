@@ -308,3 +308,45 @@ def test_empty_inputs_everywhere():
     assert cutils.getSphereCrsFromXyz(dm, [1.0, 1.0, 1.0], 0.0) in ([], [(2, 2, 2)])
     with pytest.raises(Exception):
         _device.nearest_atom(np.zeros((2, 3)), np.zeros((0, 3)))      # np.argmin of an empty row raises in the reference too
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_geometries(seed):
+    """Random cells (orthogonal and skewed), axis orders, starts, partially stored / over-sampled maps: spheres, unions,
+    per-atom clusters, blobs, symmetry images and point lookups against the oracle."""
+    import itertools
+    from impl_cuda import CudaImpl
+    from impl_oracle import OracleImpl
+    from pdb_eda_b200 import ccp4, synthetic
+    rng = np.random.default_rng(3000 + seed)
+    data, _ = cases.random_geometry(seed)
+    dm = ccp4.parse(io.BytesIO(data), "fuzz%d" % seed)
+    cuda, orc = CudaImpl(dm), OracleImpl(dm)
+    atoms = cases.random_atoms(dm, 14, seed=seed + 50, margin=4.0).astype(np.float64)
+    radii = rng.uniform(0.4, 2.6, len(atoms)).astype(np.float32)
+    m, s = cuda.mean_std()
+    cut = m + 1.1 * s
+    for c in (0.0, cut, -cut):
+        a, b = cuda.sphere_lists(atoms, radii, c), orc.sphere_lists(atoms, radii, c)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+    gstart = np.array([0, 3, 3, 8, 14], dtype=np.int32)
+    _cmp_sums(cuda.sphere_sums(atoms, radii, gstart, cut, -cut), orc.sphere_sums(atoms, radii, gstart, cut, -cut))
+    _cmp_sums(cuda.sphere_sums(atoms, radii, None, cut, -cut), orc.sphere_sums(atoms, radii, None, cut, -cut))
+    ca, cb = cuda.sphere_clouds(atoms, radii, cut), orc.sphere_clouds(atoms, radii, cut)
+    assert np.array_equal(ca[0], cb[0]) and np.array_equal(ca[1], cb[1])
+    gc.close(ca[2], cb[2])
+    for (c1, l1, s1), (c2, l2, s2) in zip(cuda.full_blobs(m + 2.2 * s, -(m + 2.2 * s)), orc.full_blobs(m + 2.2 * s, -(m + 2.2 * s))):
+        assert np.array_equal(c1, c2) and np.array_equal(l1, l2)
+        gc.close(s1, s2, rtol=1e-9, atol=1e-9)
+    crs = np.stack([rng.integers(-2 * dm.header.crsInterval[k], 3 * dm.header.crsInterval[k], 300) for k in range(3)], axis=1).astype(np.int32)
+    va, oka = cuda.point_density(crs)
+    vb, okb = orc.point_density(crs)
+    assert np.array_equal(va, vb) and np.array_equal(oka, okb.astype(bool))
+    assert np.array_equal(cuda.xyz2crs(atoms), orc.xyz2crs(atoms))
+    ops = [np.concatenate((np.round(np.linalg.qr(rng.normal(size=(3, 3)))[0], 6), rng.uniform(-20, 20, (3, 1))), axis=1) for _ in range(3)]
+    ops[0] = np.concatenate((np.eye(3), np.zeros((3, 1))), axis=1)
+    shift = np.array([np.dot(dm.header.orthoMat, v) for v in itertools.product((-1, 0, 1), repeat=3)])
+    lo, hi = atoms.min(axis=0) - 6, atoms.max(axis=0) + 6
+    sa, sb = cuda.symmetry(atoms, ops, shift, lo, hi), orc.symmetry(atoms, ops, shift, lo, hi)
+    assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+    gc.close(sa[2], sb[2], rtol=1e-12, atol=1e-11)

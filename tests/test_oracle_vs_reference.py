@@ -53,3 +53,36 @@ def test_oracle_matches_live_reference(ref, name, seed):
     assert np.allclose(xyz, np.array([np.asarray(s.coord, dtype=np.float64) for s in sym]), rtol=1e-12, atol=1e-10)
     nops = len(ops)
     assert [s.symmetry for s in sym] == [(int(i // nops) // 9 - 1, (int(i // nops) // 3) % 3 - 1, int(i // nops) % 3 - 1, int(i % nops)) for i in img]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 5, 8])
+def test_oracle_matches_live_reference_on_random_geometries(ref, seed):
+    """The geometries of the GPU fuzz test (tests/test_cuda_vs_oracle.py::test_fuzz_random_geometries), oracle vs reference."""
+    ref_ccp4, _, ref_cutils, _ = ref
+    from pdb_eda_b200 import ccp4 as my_ccp4
+    data, _ = cases.random_geometry(seed)
+    rdm = cases.parse_with(ref_ccp4, data)
+    mdm = cases.parse_with(my_ccp4, data)
+    assert np.array_equal(np.asarray(rdm.header.origin, float), np.asarray(mdm.header.origin, float))
+    assert np.array_equal(rdm.header.deOrthoMat, mdm.header.deOrthoMat) and rdm.header.uniqueNcrs == mdm.header.uniqueNcrs
+    orc = OracleImpl(mdm)
+    rng = np.random.default_rng(seed)
+    atoms = cases.random_atoms(rdm, 6, seed=seed + 50, margin=4.0)
+    radii = rng.uniform(0.4, 2.6, len(atoms))
+    cut = float(rdm.meanDensity + 1.1 * rdm.stdDensity)
+    for c in (0.0, cut, -cut):
+        want = [rdm.getSphereCrsFromXyz(a, r, c) for a, r in zip(atoms, radii)]
+        crs, off = orc.sphere_lists(atoms, radii, c)
+        assert [len(w) for w in want] == np.diff(off).tolist()
+        assert np.array_equal(crs.reshape(-1, 3), np.array([x for w in want for x in w], dtype=np.int32).reshape(-1, 3))
+    bcut = float(rdm.meanDensity + 2.2 * rdm.stdDensity)
+    for c, part in zip((bcut, -bcut), orc.full_blobs(bcut, -bcut)):
+        blobs = rdm.createFullBlobList(c)
+        crs, label, stats = part
+        assert len(blobs) == len(stats)
+        for b, blob in enumerate(blobs):
+            assert set(map(tuple, crs[label == b].tolist())) == blob.crsList
+    pts = np.stack([rng.integers(-2 * rdm.header.crsInterval[k], 3 * rdm.header.crsInterval[k], 60) for k in range(3)], axis=1)
+    val, ok = orc.point_density(pts)
+    assert [float(ref_cutils.getPointDensityFromCrs(rdm, [int(v) for v in p])) for p in pts] == val.tolist()
+    assert [bool(ref_cutils.testValidCrs(rdm, [int(v) for v in p])) for p in pts] == ok.astype(bool).tolist()
