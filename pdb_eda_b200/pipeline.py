@@ -84,17 +84,36 @@ class VoxelPass:
         self.blobs()
 
     # ---- results (synchronise) ----------------------------------------------------------------------------------------
+    def _host_buffers(self):
+        if getattr(self, "_h", None) is None:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._h = {"cloud": pin(self.cloud_out), "region": pin(self.region_out), "counts": pin(self.blob_counts),
+                       "key": pin(self.blob_key), "label": pin(self.blob_label), "stats": pin(self.blob_stats)}
+        return self._h
+
     def results(self):
-        """Device -> host read of everything one step produced."""
-        counts = self.blob_counts.cpu().numpy()
+        """Device -> host read of everything one step produced: asynchronous copies into page-locked buffers, two
+        synchronisations (the blob counts decide how much of the blob arrays is read)."""
+        h = self._host_buffers()
+        h["cloud"].copy_(self.cloud_out, non_blocking=True)
+        h["region"].copy_(self.region_out, non_blocking=True)
+        h["counts"].copy_(self.blob_counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        counts = h["counts"].numpy().copy()
         if counts[4]:
             raise RuntimeError("blob capacities too small: %s voxels / %s blobs needed" % (max(counts[0], counts[2]), max(counts[1], counts[3])))
-        out = {"cloud": self.cloud_out.cpu().numpy(), "region": self.region_out.cpu().numpy(), "blob_counts": counts}
-        for k, tag in ((0, "green"), (1, "red")):
+        spans = []
+        for k in range(2):
             nfg, nb = int(counts[2 * k]), int(counts[2 * k + 1])
-            out[tag] = {"key": self.blob_key[k * self.cap_voxels:k * self.cap_voxels + nfg].cpu().numpy(),
-                        "label": self.blob_label[k * self.cap_voxels:k * self.cap_voxels + nfg].cpu().numpy(),
-                        "stats": self.blob_stats[k * self.cap_blobs:k * self.cap_blobs + nb].cpu().numpy()}
+            v0, b0 = k * self.cap_voxels, k * self.cap_blobs
+            h["key"][v0:v0 + nfg].copy_(self.blob_key[v0:v0 + nfg], non_blocking=True)
+            h["label"][v0:v0 + nfg].copy_(self.blob_label[v0:v0 + nfg], non_blocking=True)
+            h["stats"][b0:b0 + nb].copy_(self.blob_stats[b0:b0 + nb], non_blocking=True)
+            spans.append((v0, nfg, b0, nb))
+        torch.cuda.current_stream().synchronize()
+        out = {"cloud": h["cloud"].numpy(), "region": h["region"].numpy(), "blob_counts": counts}
+        for (v0, nfg, b0, nb), tag in zip(spans, ("green", "red")):
+            out[tag] = {"key": h["key"].numpy()[v0:v0 + nfg], "label": h["label"].numpy()[v0:v0 + nfg], "stats": h["stats"].numpy()[b0:b0 + nb]}
         return out
 
     def unit_counts(self):
