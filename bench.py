@@ -276,27 +276,9 @@ def main_gpu(args, rank, world, local_rank):
     ms_plain = e0.elapsed_time(e1)
 
     # ---- end to end through the public API with host buffers
-    copy_stream = torch.cuda.Stream(device=device)
-    ev_dens, ev_diff, ev_free = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-
     def e2e_step():
-        """Host buffers in, host results out.  The two map uploads run on a copy stream; the sphere passes start as soon
-        as the 2Fo-Fc map has landed and overlap the upload of the Fo-Fc map, which the blob pass then waits for."""
-        main = torch.cuda.current_stream()
-        ev_free.record(main)                       # the previous step no longer reads the device maps
-        copy_stream.wait_event(ev_free)
-        with torch.cuda.stream(copy_stream):
-            d_dens.copy_(h_dens, non_blocking=True)
-            vp.xyz.copy_(h_xyz, non_blocking=True)
-            ev_dens.record(copy_stream)
-            d_diff.copy_(h_diff, non_blocking=True)
-            ev_diff.record(copy_stream)
-        main.wait_event(ev_dens)
-        vp.cloud()
-        vp.region()
-        main.wait_event(ev_diff)
-        vp.blobs()
-        return vp.results()
+        """The public end-to-end call: pinned host maps + atoms in, host results out (VoxelPass.stepFromHost)."""
+        return vp.stepFromHost(h_dens, h_diff, h_xyz)
 
     for _ in range(2):
         out = e2e_step()

@@ -83,6 +83,31 @@ class VoxelPass:
         self.region()
         self.blobs()
 
+    def stepFromHost(self, hostDensity, hostDiff, hostXyz=None):
+        """One pass with HOST inputs (pinned float32 map payloads as read from the CCP4 files, optional float64 atom
+        coordinates) and host results: the uploads run on a copy stream, the sphere passes start as soon as the 2Fo-Fc map
+        has landed and overlap the upload of the Fo-Fc map, which the blob pass then waits for.  Returns ``results()``."""
+        if getattr(self, "_copy", None) is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+            self._ev = [torch.cuda.Event() for _ in range(3)]
+        ev_free, ev_dens, ev_diff = self._ev
+        main = torch.cuda.current_stream()
+        ev_free.record(main)                       # the previous pass no longer reads the device maps
+        self._copy.wait_event(ev_free)
+        with torch.cuda.stream(self._copy):
+            self.dens.rho.copy_(hostDensity.view(-1), non_blocking=True)
+            if hostXyz is not None:
+                self.xyz.copy_(hostXyz, non_blocking=True)
+            ev_dens.record(self._copy)
+            self.diff.rho.copy_(hostDiff.view(-1), non_blocking=True)
+            ev_diff.record(self._copy)
+        main.wait_event(ev_dens)
+        self.cloud()
+        self.region()
+        main.wait_event(ev_diff)
+        self.blobs()
+        return self.results()
+
     # ---- results (synchronise) ----------------------------------------------------------------------------------------
     def _host_buffers(self):
         if getattr(self, "_h", None) is None:
