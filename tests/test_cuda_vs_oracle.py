@@ -350,3 +350,40 @@ def test_fuzz_random_geometries(seed):
     sa, sb = cuda.symmetry(atoms, ops, shift, lo, hi), orc.symmetry(atoms, ops, shift, lo, hi)
     assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
     gc.close(sa[2], sb[2], rtol=1e-12, atol=1e-11)
+
+
+def test_voxel_pass_matches_the_individual_calls():
+    """pipeline.VoxelPass (what bench.py times): device-resident step and the host-in / host-out call give the results
+    of the separate entry points, and the blob part agrees with the oracle."""
+    import torch
+    from impl_oracle import OracleImpl
+    from pdb_eda_b200 import ccp4, synthetic
+    from pdb_eda_b200.pipeline import VoxelPass
+    cell, n = (32.0, 32.0, 32.0, 90, 90, 90), (64, 64, 64)
+    st = synthetic.polyAlaStructure(60, (0, 0, 0), cell[:3], seed=8)
+    a, b = synthetic.mapPair(st, n, cell, seed=9)
+    dens = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(a, cell, n)), "d")
+    diff = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(b, cell, n)), "f")
+    xyz = np.array([at.coord for at in st.get_atoms()], dtype=np.float64)
+    radii = np.tile(np.array([0.78, 0.72, 0.66, 0.81, 0.84], dtype=np.float32), 60)
+    start = np.arange(0, 301, 5, dtype=np.int32)
+    vp = VoxelPass(dens.deviceMap, diff.deviceMap, xyz, radii, start, 3.5)
+    vp.step()
+    res = vp.results()
+    cut = vp.density_cut
+    want_cloud = dens.deviceMap.sphere_sums(xyz, radii, None, cut, 0.0).cpu().numpy()
+    want_region = dens.deviceMap.sphere_sums(xyz, np.full(300, 3.5, np.float32), start, cut, 0.0).cpu().numpy()
+    assert np.array_equal(res["cloud"], want_cloud) and np.array_equal(res["region"], want_region)
+    orc = OracleImpl(diff)
+    for tag, (crs, label, stats) in zip(("green", "red"), orc.full_blobs(vp.diff_cut, -vp.diff_cut)):
+        key = (crs[:, 0].astype(np.int64) * 64 + crs[:, 1]) * 64 + crs[:, 2]
+        assert np.array_equal(res[tag]["key"].astype(np.int64) & 0xFFFFFFFF, key) and np.array_equal(res[tag]["label"], label)
+        gc.close(res[tag]["stats"], stats, rtol=1e-9, atol=1e-9)
+    h_dens = torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).pin_memory()
+    h_diff = torch.from_numpy(np.ascontiguousarray(b).reshape(-1)).pin_memory()
+    h_xyz = torch.from_numpy(xyz).pin_memory()
+    vp.dens.rho.zero_()
+    vp.diff.rho.zero_()                                             # the host call must bring the maps back itself
+    again = vp.stepFromHost(h_dens, h_diff, h_xyz)
+    assert np.array_equal(again["cloud"], want_cloud) and np.array_equal(again["region"], want_region)
+    assert np.array_equal(again["green"]["label"], res["green"]["label"]) and np.array_equal(again["red"]["stats"], res["red"]["stats"])
