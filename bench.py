@@ -189,6 +189,42 @@ def run_cpu_sample(steps, warmup):
     return value, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}, total / len(times) * 1e3
 
 
+def api_timing(work):
+    """Wall-clock of the public DensityAnalysis calls on the full C2 structure (context for the kernel-level numbers;
+    not part of the timed step): the reference cannot run these at this size at all."""
+    import io
+    import torch
+    from pdb_eda_b200 import ccp4, densityAnalysis, pdbParser, structure
+    cell, n = work["cell"], work["n"]
+    densityAnalysis.setGlobals(synthetic.defaultParams())
+    out = {}
+
+    def timed(label, fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        out[label] = round(time.perf_counter() - t, 4)
+        return res
+
+    def load():
+        dens = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc2"], cell, (n, n, n))), "c2")
+        diff = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc"], cell, (n, n, n))), "c2")
+        densityAnalysis._attachCutoffs(dens, diff)
+        text = structure.formatPDB(work["structure"], remark290=synthetic.cartesianOperators("P 1", cell), cell=cell, spaceGroup="P 1")
+        return densityAnalysis.DensityAnalysis("c2", dens, diff, work["structure"], pdbParser.readPDBfile(io.StringIO(text)))
+
+    an = timed("load_parse_upload_meanstd_s", load)
+    timed("aggregateCloud_s", an.aggregateCloud)
+    blobs = timed("green_red_blob_lists_s", lambda: (an.greenBlobList, an.redBlobList))
+    timed("blob_statistics_s", lambda: an.calculateAtomSpecificBlobStatistics(blobs[0] + blobs[1]))
+    timed("residue_region_density_s", lambda: an.calculateResidueRegionDensity(REGION_RADIUS))
+    out.update({"atoms_analysed": len(an.atomCloudDescriptions), "residue_clouds": len(an.residueCloudDescriptions),
+                "domain_clouds": len(an.domainCloudDescriptions), "green_blobs": len(blobs[0]), "red_blobs": len(blobs[1]),
+                "density_electron_ratio": an.densityElectronRatio})
+    return out
+
+
 def main_reference(args, rank, world):
     if rank != 0:
         return
@@ -359,6 +395,7 @@ def main_gpu(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             _, cpu, _ = run_cpu_sample(1, 0)
             line["cpu_baseline"] = cpu
+            line["api_c2"] = api_timing(work)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
