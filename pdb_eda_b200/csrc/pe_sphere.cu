@@ -279,6 +279,7 @@ struct UnionShared {
     int offC[kTileC], offR[kTileR], offS[kTileS];  // wrapped element offsets of the tile's indices
     int cLo[kUnionChunk], nC[kUnionChunk], rLo[kUnionChunk], nR[kUnionChunk], sLo[kUnionChunk], nS[kUnionChunk];
     int kMin[kUnionChunk];             // column (index into sqC) nearest the atom: the minimum of its sqC
+    float xC[kUnionChunk];             // the atom's fractional column, as an index into sqC (interval guess only)
 };
 
 // MODE 0: z is carried by the row axis, 1: by the section axis, 2: by the column axis.
@@ -293,10 +294,15 @@ __device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, dou
 
 // Membership of one chunk of atoms in one tile: a work item is one box row (row, section) of one atom.  Along the
 // columns of a box row the squared distance falls to the column nearest the atom and rises again (every rounding
-// step is monotone), so the in-sphere columns are one interval around that column and two binary searches with
-// the EXACT predicate find its ends -- ~8 float64 tests per box row instead of one per candidate voxel.
+// step is monotone), so the in-sphere columns are one interval [kl, kh] around that column.  The interval is
+// GUESSED in float32 from the chord of the sphere along the row (half-width sqrt(T - A - B) in columns around the
+// atom's fractional column xC) and then VERIFIED with the exact float64 predicate: inside at kl and kh, outside at
+// kl - 1 and kh + 1 -- four independent tests that, by unimodality, prove the guess.  A guess that fails (an end
+// within ~1e-5 columns of a grid point, or a row that only just misses the sphere) falls back to two binary searches
+// with the same exact predicate.  Rows that miss the sphere leave after one exact test without touching the tables:
+// every rounding step is monotone and the column term is >= 0, so d2 >= fl(A + B) for every column of the row.
 template <int MODE, bool WIDE>
-__device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int tid, int nthreads) {
+__device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int tid, int nthreads, float inv_gl) {
     for (int j = 0; j < nchunk; ++j) {  // block-uniform
         const int nR = sh.nR[j], nS = sh.nS[j], nC = sh.nC[j];
         if (nR <= 0) continue;
@@ -309,6 +315,7 @@ __device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int
         int km = sh.kMin[j];
         if (km > 0 && sqc[km - 1] < sqc[km]) --km;
         else if (km + 1 < nC && sqc[km + 1] < sqc[km]) ++km;
+        const float xc = sh.xC[j];
         const int cbit = sh.cLo[j];
         uint32_t *rows = sh.bits + 2 * (sh.rLo[j] * kTileS + sh.sLo[j]);
         for (int li = tid; li < total; li += nthreads) {
@@ -317,26 +324,38 @@ __device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int
             const double sr = sh.sqR[j][ir], ss = sh.sqS[j][is];
             const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
             const double B = (MODE == 0) ? sr : ss;
-            if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
-            int lo = 0, hi = km;  // smallest k in [0, km] inside
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (row_pred<MODE>(sqc, mid, A, B, T))
-                    hi = mid;
-                else
-                    lo = mid + 1;
+            const double AB = (MODE == 2) ? A : __dadd_rn(A, B);
+            if (!(AB <= T)) continue;  // exact: the row misses the sphere
+            const float rem = (float)__dsub_rn(T, AB);
+            const float h = rem > 0.f ? rem * rsqrtf(rem) * inv_gl : 0.f;
+            int kl = min(max((int)ceilf(xc - h), 0), km);
+            int kh = max(min((int)floorf(xc + h), nC - 1), km);
+            const bool in_l = row_pred<MODE>(sqc, kl, A, B, T), in_h = row_pred<MODE>(sqc, kh, A, B, T);
+            const bool out_l = kl == 0 || !row_pred<MODE>(sqc, kl - 1, A, B, T);
+            const bool out_h = kh == nC - 1 || !row_pred<MODE>(sqc, kh + 1, A, B, T);
+            if (!(in_l && in_h && out_l && out_h)) {
+                if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
+                int lo = 0, hi = km;  // smallest k in [0, km] inside
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (row_pred<MODE>(sqc, mid, A, B, T))
+                        hi = mid;
+                    else
+                        lo = mid + 1;
+                }
+                kl = lo;
+                lo = km;
+                hi = nC - 1;  // largest k in [km, nC) inside
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (row_pred<MODE>(sqc, mid, A, B, T))
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                kh = lo;
             }
-            const int kl = lo;
-            lo = km;
-            hi = nC - 1;  // largest k in [km, nC) inside
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (row_pred<MODE>(sqc, mid, A, B, T))
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const int count = lo - kl + 1;
+            const int count = kh - kl + 1;
             uint32_t *word = rows + 2 * (ir * kTileS + is);
             if (WIDE) {
                 const unsigned long long run = count >= 64 ? ~0ull : ((1ull << count) - 1ull);
@@ -475,6 +494,7 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
     long long t_phase[4] = {0, 0, 0, 0};
     cp = eff_pos(cp);
     cn = eff_neg(cn);
+    const float inv_gl = (float)(1.0 / g.grid_length[g.map2crs[0]]);  // columns per Angstrom (interval guess only)
     // persistent CTAs: the bitmap is cleared once (the gather leaves it clear), then groups are taken round robin
     for (int i = tid; i < kTileR * kTileS * 2; i += blockDim.x) sh.bits[i] = 0u;
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -542,6 +562,9 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                                 sh.T[tid] = thr[c0 + tid];
                                 // centre column of the box (range(c - R - 1, c + R + 1): c = lo + dim / 2), clamped into the tile part
                                 sh.kMin[tid] = hit ? min(max(bx[0] + bx[3] / 2 - cl, 0), ch - cl - 1) : 0;
+                                const int ic = g.map2crs[0];  // xyz axis carried by the columns
+                                sh.xC[tid] = (float)((sel3(xyz[3 * (c0 + tid)], xyz[3 * (c0 + tid) + 1], xyz[3 * (c0 + tid) + 2], ic) -
+                                                      g.origin[ic]) / g.grid_length[ic] - (double)cl);
                             }
                             __syncthreads();
                             for (int idx = tid; idx < nchunk * (kTileC + kTileR + kTileS); idx += blockDim.x) {
@@ -560,9 +583,9 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                             }
                             __syncthreads();
                             if (tC > 32)
-                                union_mark_rows<MODE, true>(sh, nchunk, tid, blockDim.x);
+                                union_mark_rows<MODE, true>(sh, nchunk, tid, blockDim.x, inv_gl);
                             else
-                                union_mark_rows<MODE, false>(sh, nchunk, tid, blockDim.x);
+                                union_mark_rows<MODE, false>(sh, nchunk, tid, blockDim.x, inv_gl);
                             __syncthreads();  // tables are reused by the next chunk
                         }
                     } else {

@@ -12,6 +12,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pdb_eda_b200 import _device, _lib, ccp4, synthetic  # noqa: E402
 from pdb_eda_b200.pipeline import VoxelPass  # noqa: E402
 
+if os.environ.get("PE_LIB"):  # A/B runs of two builds of the library (tuning only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["PE_LIB"])
+
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 384
 nres = int(sys.argv[3]) if len(sys.argv) > 3 else 8000
