@@ -22,6 +22,7 @@
 // Skewed cells take generic passes that evaluate the reference's 3x3 mat-vec per candidate in the host BLAS's
 // accumulation order.
 #include <limits.h>
+#include <stddef.h>
 #include <type_traits>
 #include "pe_common.cuh"
 
@@ -261,14 +262,13 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
 //   1. membership: every warp walks its share of every atom's box rows and ORs the in-sphere columns of a box row
 //      into a shared-memory bitmap (two 32-bit words per (row, section)) -- one ballot and one or two atomicOr per
 //      warp iteration, no global memory traffic.  OR is commutative, so no ordering between atoms is needed.
-//   2. gather: the warps walk the bitmap rows; a lane owns a column, loads rho where its bit is set (a warp reads
-//      one contiguous run of the map row) and accumulates.  Each voxel of the union is read exactly once however
-//      many spheres hold it, and the float64 summation order is fixed, so results are run-to-run deterministic.
+//   2. gather: the set bits are compacted into a list of map offsets, which the warps then walk densely
+//      (union_gather).  Each voxel of the union is read exactly once however many spheres hold it, and the float64
+//      summation order is fixed, so results are run-to-run deterministic.
 constexpr int kUnionWarps = 4;
 constexpr int kTileC = 64, kTileR = 48, kTileS = 48;
 
 constexpr int kUnionChunk = 8;       // atoms whose tables are resident at once
-constexpr int kRowsPerQuarter = 4;   // bitmap rows a quarter-warp gathers concurrently (= loads in flight per lane)
 
 struct UnionShared {
     uint32_t bits[kTileR * kTileS * 2];
@@ -391,86 +391,93 @@ __device__ __forceinline__ void union_mark_generic(const pe_geom &g, const AtomB
     }
 }
 
-// Phase 2 of the union kernel.  A warp owns tile rows rl = warp, warp + 4, ...; per 32 sections every lane fetches
-// "its" (row, section) bitmap word(s), a ballot finds the non-empty ones, and they are consumed eight at a time, two
-// per quarter-warp: a quarter-warp walks its rows in windows of 8 consecutive columns starting at the lowest set bit
-// (the set bits of a row are one or two short runs), so nearly every lane of every load carries a voxel and the 8
-// lanes of a window read one 32-byte sector; four loads are in flight per lane before any is consumed.
+// Phase 2 of the union kernel: compact, then gather densely.  The bitmap rows of the tile are taken 32 at a time, one
+// (row, section) per lane.  Compaction: a warp prefix sum of the popcounts gives every row its place in a per-warp
+// list in shared memory, and each lane writes the map offsets of its set bits there -- consecutive entries are
+// consecutive columns of a row, then the next row.  Gather: the warp walks the list with every lane busy and
+// kGatherLoads independent loads in flight per lane, each load covering a few contiguous runs of the map.  The voxel
+// count comes from the popcounts, so the per-voxel work is one conversion, the float64 additions and the class tests.
+// The list lives in the storage of the (now dead) membership tables; when a batch holds more voxels than the list,
+// its rows are taken in as many rounds as needed (a word never exceeds the list).  64-column tiles pass each batch
+// twice, once per 32-column half.  The summation order is fixed, so results are run-to-run deterministic.
+// (Tried: 64 bitmap rows per warp iteration -- the warps of a block finish further apart, 173 -> 185 us; batches handed
+// out on demand through a shared counter -- no faster, and the summation order is no longer fixed.)
+constexpr int kGatherLoads = 8;
+constexpr int kListCap = kUnionChunk * (kTileC + kTileR + kTileS) * 2 / kUnionWarps;  // ints per warp
+
 template <bool WIDE, bool CHECKED, bool HASNEG>
 __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__restrict__ rho, SphereAcc &acc, float cp, float cn,
-                                             int warp, int lane, int tR, int tS) {
-    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type word_t;
-    const int sg = lane >> 3, lr = lane & 7;
-    for (int rl = warp; rl < tR; rl += kUnionWarps) {
-        const int orow = sh.offR[rl];
-        uint32_t *rowbits = sh.bits + 2 * rl * kTileS;
-        for (int sl0 = 0; sl0 < tS; sl0 += 32) {
-            uint2 mine = make_uint2(0u, 0u);
-            if (sl0 + lane < tS) mine = *reinterpret_cast<const uint2 *>(rowbits + 2 * (sl0 + lane));
-            unsigned nz = __ballot_sync(kFull, (mine.x | mine.y) != 0u);
-            if (nz == 0u) continue;  // warp-uniform
-            if ((mine.x | mine.y) != 0u)  // leave the bitmap clear for the next tile
-                *reinterpret_cast<uint2 *>(rowbits + 2 * (sl0 + lane)) = make_uint2(0u, 0u);
-            while (nz) {
-                int src[kRowsPerQuarter];  // the next (up to) 4 * kRowsPerQuarter non-empty sections
+                                             int warp, int lane, int tR, int tS, bool contig) {
+    static_assert(offsetof(UnionShared, sqR) == offsetof(UnionShared, sqC) + sizeof(double) * kUnionChunk * kTileC, "table layout");
+    static_assert(offsetof(UnionShared, sqS) == offsetof(UnionShared, sqR) + sizeof(double) * kUnionChunk * kTileR, "table layout");
+    static_assert(kListCap >= 32, "a word must fit the list");
+    int *list = reinterpret_cast<int *>(&sh.sqC[0][0]) + warp * kListCap;
+    const int nwords = tR * tS;
+    for (int w0 = warp * 32; w0 < nwords; w0 += kUnionWarps * 32) {
+        const int wi = w0 + lane;
+        const int rl = wi / tS, sl = wi - rl * tS;
+        uint2 mine = make_uint2(0u, 0u);
+        uint32_t *wordp = sh.bits + 2 * (rl * kTileS + sl);
+        if (wi < nwords) mine = *reinterpret_cast<const uint2 *>(wordp);
+        if (!__any_sync(kFull, (mine.x | mine.y) != 0u)) continue;
+        if ((mine.x | mine.y) != 0u) *reinterpret_cast<uint2 *>(wordp) = make_uint2(0u, 0u);  // leave the bitmap clear
+        int orr = 0, osum = 0;
+        if (wi < nwords) {
+            const int o1 = sh.offR[rl], o2 = sh.offS[sl];
+            orr = o1 | o2;
+            osum = (int)((unsigned)o1 + (unsigned)o2);
+        }
 #pragma unroll
-                for (int u = 0; u < kRowsPerQuarter; ++u) src[u] = -1;
-#pragma unroll
-                for (int q = 0; q < 4 * kRowsPerQuarter; ++q) {
-                    const int f = nz ? (__ffs(nz) - 1) : -1;
-                    if (nz) nz &= nz - 1;
-                    if ((q / kRowsPerQuarter) == sg) src[q % kRowsPerQuarter] = f;
+        for (int half = 0; half < (WIDE ? 2 : 1); ++half) {
+            uint32_t w = half ? mine.y : mine.x;
+            if (WIDE && !__any_sync(kFull, w != 0u)) continue;
+            const int *offc = sh.offC + 32 * half;
+            const int oc0 = offc[0];
+            const int c = __popc(w);
+            bool pending = c > 0;
+            while (true) {  // one round unless the batch overflows the list
+                const int cc = pending ? c : 0;
+                const int excl = warp_excl_scan(cc, lane);
+                const bool fits = excl + cc <= kListCap;
+                const int total = __reduce_max_sync(kFull, fits ? excl + cc : 0);
+                if (pending && fits) {
+                    int pos = excl;
+                    while (w) {
+                        const int bcol = __ffs((int)w) - 1;
+                        w &= w - 1u;
+                        const int oc = contig ? oc0 + bcol : offc[bcol];  // contig: the tile's columns are adjacent in memory
+                        int e = (int)((unsigned)osum + (unsigned)oc);
+                        if (CHECKED) e = ((orr | oc) < 0) ? -1 : e;
+                        list[pos++] = e;
+                    }
+                    pending = false;
                 }
-                word_t w[kRowsPerQuarter];
-                int ors[kRowsPerQuarter];
-                unsigned srs[kRowsPerQuarter];
-                word_t any = 0;
+                __syncwarp();
+                if (lane == 0) acc.n_all += total;
+                for (int i0 = 0; i0 < total; i0 += 32 * kGatherLoads) {
+                    int e[kGatherLoads];
+                    float v[kGatherLoads];
 #pragma unroll
-                for (int u = 0; u < kRowsPerQuarter; ++u) {
-                    const uint32_t lo = __shfl_sync(kFull, mine.x, src[u] < 0 ? 0 : src[u]);
-                    word_t full = lo;
-                    if (WIDE) full = (word_t)(((unsigned long long)__shfl_sync(kFull, mine.y, src[u] < 0 ? 0 : src[u]) << 32) | lo);
-                    w[u] = src[u] < 0 ? (word_t)0 : full;
-                    any |= w[u];
-                    const int os = src[u] < 0 ? (CHECKED ? kInvalidOff : 0) : sh.offS[sl0 + src[u]];
-                    ors[u] = orow | os;
-                    srs[u] = (unsigned)orow + (unsigned)os;
-                }
-                while (__any_sync(kFull, any != (word_t)0)) {
-                    // one window per row and trip: kRowsPerQuarter independent loads in flight per lane
-                    float v[kRowsPerQuarter];
-                    bool bit[kRowsPerQuarter];
-                    any = 0;
+                    for (int u = 0; u < kGatherLoads; ++u) {
+                        const int idx = i0 + 32 * u + lane;
+                        e[u] = idx < total ? list[idx] : -2;
+                    }
 #pragma unroll
-                    for (int u = 0; u < kRowsPerQuarter; ++u) {
-                        word_t &ww = w[u];
-                        int first;
-                        if (WIDE)
-                            first = ww ? (__ffsll((long long)ww) - 1) : 0;
-                        else
-                            first = ww ? (__ffs((int)ww) - 1) : 0;
-                        const int col = first + lr;
-                        bit[u] = col < (WIDE ? 64 : 32) && ((ww >> col) & (word_t)1);
+                    for (int u = 0; u < kGatherLoads; ++u) {
                         v[u] = 0.f;
-                        if (CHECKED) {
-                            const int oc = bit[u] ? sh.offC[col] : kInvalidOff;
-                            const bool ok = (ors[u] | oc) >= 0;
-                            if (bit[u] && ok) v[u] = __ldg(rho + (int)(srs[u] + (unsigned)oc));
-                            acc.bad |= (bit[u] && !ok) ? 1 : 0;
-                        } else {
-                            if (bit[u]) v[u] = __ldg(rho + (int)(srs[u] + (unsigned)sh.offC[col]));
-                        }
-                        ww &= ~(((word_t)0xff) << first);  // no-op when ww == 0 (first = 0)
-                        any |= ww;
+                        if (e[u] >= 0) v[u] = __ldg(rho + e[u]);
+                        if (CHECKED) acc.bad |= (e[u] == -1) ? 1 : 0;
                     }
 #pragma unroll
-                    for (int u = 0; u < kRowsPerQuarter; ++u) {
+                    for (int u = 0; u < kGatherLoads; ++u) {
                         if (HASNEG)
-                            acc.add(bit[u], v[u], cp, cn);
+                            acc.add(false, v[u], cp, cn);
                         else
-                            acc.add_pos(bit[u], v[u], cp);
+                            acc.add_pos(false, v[u], cp);
                     }
                 }
+                __syncwarp();  // the list is rewritten by the next round / half / batch
+                if (!__any_sync(kFull, pending)) break;
             }
         }
     }
@@ -614,19 +621,22 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 7)
                         const bool wide = tC > 32;
                         const bool has_neg = cn > __int_as_float(0xff800000);
                         int invalid = 0;
-                        for (int k = tid; k < tC + tR + tS; k += blockDim.x)
+                        for (int k = tid; k < tC + tR + tS; k += blockDim.x) {
                             invalid |= (k < tC ? sh.offC[k] : (k < tC + tR ? sh.offR[k - tC] : sh.offS[k - tC - tR])) < 0 ? 1 : 0;
-                        const bool checked = __syncthreads_or(invalid) != 0;
+                            if (k > 0 && k < tC) invalid |= (sh.offC[k] != sh.offC[k - 1] + 1) ? 1 : 0;
+                        }
+                        // tiles that straddle the periodic boundary (columns not adjacent in memory) take the checked path too
+                        const bool checked = __syncthreads_or(invalid) != 0, contig = !checked;
                         const int sel = (wide ? 4 : 0) | (checked ? 2 : 0) | (has_neg ? 1 : 0);
                         switch (sel) {
-                            case 0: union_gather<false, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            case 1: union_gather<false, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            case 2: union_gather<false, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            case 3: union_gather<false, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            case 4: union_gather<true, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            case 5: union_gather<true, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            case 6: union_gather<true, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
-                            default: union_gather<true, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 0: union_gather<false, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 1: union_gather<false, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 2: union_gather<false, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 3: union_gather<false, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 4: union_gather<true, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 5: union_gather<true, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 6: union_gather<true, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            default: union_gather<true, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
                         }
                     }
                     __syncthreads();
