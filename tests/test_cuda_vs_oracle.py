@@ -62,6 +62,34 @@ def test_union_wide_boxes(name, radius):
     _cmp_sums(cuda.sphere_sums(xyz[:2], radii[:2], None, 0.5, -0.5), orc.sphere_sums(xyz[:2], radii[:2], None, 0.5, -0.5))
 
 
+@pytest.mark.parametrize("name", ["ortho", "perm"])
+def test_union_borderline_chords(name):
+    """Atoms on grid points (and within a few ulp / 1e-4 columns of them) with radii that are whole multiples of the
+    grid spacing and Pythagorean combinations of it: many voxels lie at distance == r or within rounding of it, and
+    the chord ends of the union kernel's float32 interval guess fall on grid points -- the cases where the guess must
+    not be trusted and the exact float64 predicate decides."""
+    dm, cuda, orc = _impls(name)
+    h = dm.header
+    rng = np.random.default_rng(21)
+    gl = np.array([h.gridLength[i] for i in range(3)], dtype=np.float64)
+    origin = np.array([h.origin[i] for i in range(3)], dtype=np.float64)
+    base = []
+    for _ in range(40):
+        idx = rng.integers(8, 30, 3)
+        p = origin + idx * gl
+        jitter = rng.choice([0.0, 1e-7, -1e-7, 5e-5, -5e-5, 4e-4, -4e-4, 6e-4], 3) * gl
+        base.append(p + jitter)
+    xyz = np.array(base, dtype=np.float64)  # float64 coordinates (as symmetry images are): keeps the tiny offsets
+    g0 = float(gl.min())
+    rads = [g0 * k for k in (1, 2, 3, 5, 7)] + [g0 * np.sqrt(k) for k in (2, 3, 5, 13, 25, 50)]
+    radii = np.array([rads[i % len(rads)] for i in range(len(xyz))], dtype=np.float32)
+    for per in (1, 4):
+        start = np.arange(0, len(xyz) + 1, per, dtype=np.int32)
+        m, s = cuda.mean_std()
+        cut = m + 0.5 * s
+        _cmp_sums(cuda.sphere_sums(xyz, radii, start, cut, -cut), orc.sphere_sums(xyz, radii, start, cut, -cut))
+
+
 @pytest.mark.parametrize("name", ["ortho", "tric"])
 def test_degenerate_radii_and_empty_batches(name):
     dm, cuda, orc = _impls(name)
