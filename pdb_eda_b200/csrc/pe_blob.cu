@@ -12,8 +12,10 @@
 //   * union-find over those positions with "smaller id wins" makes every blob's root its first voxel in that
 //     order, so ranking the roots yields the reference's blob order directly (canonical min-index relabelling).
 // Everything after the streaming kernel touches only the bit planes (N/8 bytes) and the sparse foreground.
-// Runs of set bits along the section axis are linked at initialisation (parent = predecessor), the remaining
-// 12 predecessor neighbours are merged with lock-free atomicMin hooking.
+// Runs of set bits along the section axis are linked at initialisation (parent = first voxel of the run), the
+// remaining 12 predecessor neighbours are merged with lock-free atomicMin hooking.  The streaming kernel also
+// counts the foreground per 512-word segment of the planes, so the sparse stage knows every voxel's list position
+// (and both class totals) without a counting pass of its own.
 //
 // The transposition (memory order is column-fastest, bit order is section-fastest) costs nothing: a thread owns
 // 4 adjacent columns of one row and walks 32 sections, so the 32 loads it issues are independent 16-byte loads
@@ -29,15 +31,21 @@ namespace pe {
 constexpr int kBmpTx = 32;         // threads along columns (x VEC columns each)
 constexpr int kBmpTy = 8;          // threads along rows
 constexpr int kSparseThreads = 512;
-constexpr int kSparseMaxBlocks = 1024;  // size of the per-block partial-sum arrays
+constexpr int kSegShift = 9;       // words per counting segment of the bit planes: 512
+constexpr int kSegWords = 1 << kSegShift;
+constexpr int kChunkShift = 9;     // voxels per root-ranking chunk: 512 (= kSparseThreads)
+constexpr int kChunkSmem = 4096;   // chunks whose prefix fits the shared-memory table (2 M voxels)
+static_assert((1 << kChunkShift) == kSparseThreads, "a ranking chunk is one block of voxels");
 
 struct BlobPlan {
     int U0, U1, U2, W;    // unique columns, rows, sections; words per (column,row)
     int64_t nwords;       // U0*U1*W words per class
-    int64_t nwords_pad;   // the same rounded up to 64: distance between the two bit planes
+    int64_t nwords_pad;   // the same rounded up to a whole segment: distance between the two bit planes
+    int64_t nseg;         // counting segments over both planes
     int64_t cap;          // foreground capacity per class
+    int64_t nchunk_cap;   // ranking chunks at capacity
     // workspace carve-up
-    int64_t off_bmp, off_base, off_parent, off_rank, off_sums, total;
+    int64_t off_bmp, off_base, off_parent, off_flags, off_coarse, off_seg, total;
 };
 
 static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
@@ -47,8 +55,10 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
     p.U2 = g->unique_ncrs[2];
     p.W = ((p.U2 + 31) / 32 + 7) / 8 * 8;  // padded: see threshold_bitmap_kernel
     p.nwords = (int64_t)p.U0 * p.U1 * p.W;
-    p.nwords_pad = align_up(p.nwords, 64);
+    p.nwords_pad = align_up(p.nwords, kSegWords);
+    p.nseg = 2 * p.nwords_pad / kSegWords;
     p.cap = cap;
+    p.nchunk_cap = (2 * cap + kSparseThreads - 1) / kSparseThreads + 1;
     int64_t o = 0;
     p.off_bmp = o;
     o += align_up(2 * p.nwords_pad * 4, 256);
@@ -56,10 +66,12 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
     o += align_up(2 * p.nwords_pad * 4, 256);
     p.off_parent = o;
     o += align_up(2 * cap * 4, 256);
-    p.off_rank = o;
-    o += align_up(2 * cap * 4, 256);
-    p.off_sums = o;
-    o += align_up(2 * kSparseMaxBlocks * 4, 256);
+    p.off_flags = o;  // per 32 voxels: root flags + roots before the word inside its chunk
+    o += align_up((2 * cap / 32 + 2 * (kSparseThreads / 32)) * 8, 256);  // the last chunk is written whole
+    p.off_coarse = o;  // per chunk: roots; then (maps beyond kChunkSmem chunks) their exclusive prefix
+    o += align_up(2 * p.nchunk_cap * 4, 256);
+    p.off_seg = o;
+    o += align_up(p.nseg * 4, 256);
     p.total = o;
     return p;
 }
@@ -68,7 +80,8 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
 // W (words per (column, row)) is padded to a multiple of 8, so the kWordsPerThread = 4 words a thread produces for
 // one (column, row) are one aligned 16-byte store, and the two thread blocks that share a 32-byte sector are
 // neighbours in launch order (the word-group index is blockIdx.x, the fastest-varying block index): every bit-plane
-// sector reaches DRAM as one full write.  Scattered 4-byte word stores cost a read-modify-write per sector once the
+// sector reaches DRAM as one full write.  The kernel also counts the foreground voxels of every 512-word segment of the
+// planes (segcount, zeroed by the caller), which is all the sparse stage needs to place every voxel in the list.  Scattered 4-byte word stores cost a read-modify-write per sector once the
 // bit planes no longer fit L2 (768^3 ran at 28 % of the HBM peak, tune log in profiles/r01_threshold_tuning.md).
 constexpr int kWordsPerThread = 4;
 
@@ -76,16 +89,14 @@ template <int VEC>
 __global__ void __launch_bounds__(384)
     threshold_bitmap_kernel(const float *__restrict__ rho, int NC, int NR, int U0, int U1, int U2, int W, float cpos,
                             float cneg, bool use_pos, bool use_neg, uint32_t *__restrict__ bmp_pos,
-                            uint32_t *__restrict__ bmp_neg) {
+                            uint32_t *__restrict__ bmp_neg, int64_t nwords_pad, uint32_t *__restrict__ segcount) {
     const int c = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
     const int r = blockIdx.z * blockDim.y + threadIdx.y;
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0) {  // padding between / after the planes
         const int64_t nwords = (int64_t)U0 * U1 * W;
-        for (int64_t i = nwords + threadIdx.x; i < nwords + 64; i += blockDim.x) {
-            if (i < (nwords + 63) / 64 * 64) {
-                bmp_pos[i] = 0u;
-                bmp_neg[i] = 0u;
-            }
+        for (int64_t i = nwords + threadIdx.x; i < nwords_pad; i += blockDim.x) {
+            bmp_pos[i] = 0u;
+            bmp_neg[i] = 0u;
         }
     }
     if (c >= U0 || r >= U1) return;
@@ -152,6 +163,12 @@ __global__ void __launch_bounds__(384)
             const int64_t widx = ((int64_t)(c + i) * U1 + r) * W + w_begin;  // multiple of 4 words: 16-byte aligned
             *reinterpret_cast<uint4 *>(bmp_pos + widx) = make_uint4(accp[i][0], accp[i][1], accp[i][2], accp[i][3]);
             *reinterpret_cast<uint4 *>(bmp_neg + widx) = make_uint4(accn[i][0], accn[i][1], accn[i][2], accn[i][3]);
+            // foreground per segment of the concatenated planes (four aligned words never straddle a segment);
+            // at +/-3 sigma one store in twenty carries a voxel, so these atomics are rare
+            const int np = __popc(accp[i][0]) + __popc(accp[i][1]) + __popc(accp[i][2]) + __popc(accp[i][3]);
+            const int nn = __popc(accn[i][0]) + __popc(accn[i][1]) + __popc(accn[i][2]) + __popc(accn[i][3]);
+            if (np) atomicAdd(segcount + (widx >> kSegShift), (uint32_t)np);
+            if (nn) atomicAdd(segcount + ((nwords_pad + widx) >> kSegShift), (uint32_t)nn);
         }
     }
 }
@@ -159,11 +176,22 @@ __global__ void __launch_bounds__(384)
 // ------------------------------------------------------------------------------------------------ sparse stage
 // Everything after the streaming kernel touches only the bit planes and the sparse foreground, for BOTH signs at
 // once: the planes are scanned as one concatenated word array, so green voxels occupy positions [0, n0) and red
-// voxels [n0, n0 + n1) of one index space, and one union-find / one root ranking serves both.  The stages are
-// separated by grid-wide barriers inside ONE cooperative kernel (grid = resident blocks, cg::grid_group::sync)
-// instead of ten tiny launches per sign.
-// Stage boundaries of the last blob_sparse_kernel launch (globaltimer ns, written by block 0): a cheap built-in
-// diagnostic, read with pe_blob_stage_times().
+// voxels [n0, n0 + n1) of one index space, and one union-find / one root ranking serves both.  ONE cooperative kernel
+// (grid = resident blocks), four phases separated by three grid-wide barriers:
+//   P1  list positions from the segment counts of K1 (every block sums the few thousand counts itself: no barrier),
+//       then keys and initial parents of every foreground voxel -- a voxel points at the first voxel of
+//       its run of consecutive sections;
+//   P2  density gather and union-find hooking of the 12 predecessor neighbours outside the voxel's own column (all bit-plane and
+//       position loads of a voxel are issued together, then hooked with lock-free atomicMin, "smaller id wins", the
+//       voxel's current root carried from one hook to the next); the per-blob sums are zeroed on the side;
+//   P3  flatten; root flags (one ballot word per 32 voxels) with the root count before each word inside its 512-voxel
+//       chunk, and the root count of each chunk;
+//   P4  every block scans the chunk counts into shared memory, so that the rank of any root -- the reference's blob
+//       number, because a root is its blob's first voxel in scan order -- is two loads and a popcount; labels and
+//       per-blob sums (DensityBlob.fromCrsList, pdb_eda/ccp4.py:534-545) with a segmented warp reduction in front of
+//       the float64 atomics.
+// Barriers were 35 % of the stall samples of the seven-barrier version (profiles/r01_final_c2_step.md).
+// Phase boundaries of the last launch (globaltimer ns, written by block 0): pe_blob_stage_times().
 __device__ unsigned long long g_stage_ns[12];
 __device__ __forceinline__ void stamp(int i) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -176,18 +204,20 @@ __device__ __forceinline__ void stamp(int i) {
 struct SparseArgs {
     const float *rho;
     int NC, NR, U1, U2, W;
-    int64_t nwords, nwords_pad, cap, cap_blobs;
-    const uint32_t *bmp;   // two planes, nwords_pad apart
-    uint32_t *base;        // per word: position of its first set bit in the concatenated voxel list
-    uint32_t *parent;      // 2 * cap
-    uint32_t *rank;        // 2 * cap (valid at roots)
-    uint32_t *sums;        // 2 * kSparseMaxBlocks block partials
-    int64_t *counts;       // n_fg0, n_blobs0, n_fg1, n_blobs1, overflow
-    uint32_t *key;         // outputs, class k at k * cap
+    int64_t nwords_pad, cap, cap_blobs;
+    int nseg;
+    const uint32_t *bmp;       // two planes, nwords_pad apart
+    const uint32_t *segcount;  // foreground voxels per segment (K1)
+    uint32_t *base;            // per non-empty word: position of its first set bit in the concatenated voxel list
+    uint32_t *parent;          // 2 * cap
+    uint2 *flags;              // per 32 voxels: (root flags, roots before this word inside its chunk)
+    uint32_t *coarse;          // per chunk: roots; [nchunk_cap ...): exclusive prefix when it does not fit shared memory
+    int64_t nchunk_cap;
+    int64_t *counts;           // n_fg0, n_blobs0, n_fg1, n_blobs1, overflow
+    uint32_t *key;             // outputs, class k at k * cap
     float *value;
     int32_t *label;
-    double *stats;         // class k at k * cap_blobs * 8
-    bool use_pos, use_neg;
+    double *stats;             // class k at k * cap_blobs * 8
 };
 
 __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *smem /* >= 32 */) {
@@ -201,247 +231,323 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *smem /* 
     return t;
 }
 
-// Exclusive prefix of sums[0 .. nb) at index b (every block scans the few hundred partials itself).
-__device__ __forceinline__ void grid_prefix(const uint32_t *sums, int nb, int b, uint32_t *smem, uint32_t &before, uint32_t &total) {
-    uint32_t mine = 0, all = 0;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-        const uint32_t v = sums[i];
-        all += v;
-        if (i < b) mine += v;
+// union that returns the root of the merged set (the smaller of the two roots), starting from a known ancestor
+__device__ __forceinline__ uint32_t uf_union_root(uint32_t *parent, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find_halve(parent, a);
+        b = uf_find_halve(parent, b);
+        if (a == b) return a;
+        if (a < b) {
+            const uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        const uint32_t old = atomicMin(parent + a, b);  // hook the larger root under the smaller
+        if (old == a) return b;
+        a = old;
     }
-    before = block_sum_u32(mine, smem);
-    total = block_sum_u32(all, smem);
 }
 
-// Positions of the voxels of neighbour column `nwidx` (same class) that are 26-adjacent to section bit b of word w:
-// the voxel at the same section if set (its s-1 / s+1 neighbours are chained to it already), else those at s-1 and s+1.
-__device__ __forceinline__ void neighbours_in_column(const uint32_t *__restrict__ bmp, const uint32_t *__restrict__ base,
-                                                     int64_t nwidx, int w, int b, int W, uint32_t *nb, int &cnt) {
-    const uint32_t B = bmp[nwidx];
-    if ((B >> b) & 1u) {
-        nb[cnt++] = base[nwidx] + (uint32_t)__popc(B & ((1u << b) - 1u));
-        return;
-    }
-    if (b > 0) {  // section s-1
-        if ((B >> (b - 1)) & 1u) nb[cnt++] = base[nwidx] + (uint32_t)__popc(B & ((1u << (b - 1)) - 1u));
-    } else if (w > 0) {
-        const uint32_t Bm = bmp[nwidx - 1];
-        if (Bm >> 31) nb[cnt++] = base[nwidx - 1] + (uint32_t)__popc(Bm & 0x7fffffffu);
-    }
-    if (b < 31) {  // section s+1
-        if ((B >> (b + 1)) & 1u) nb[cnt++] = base[nwidx] + (uint32_t)__popc(B & ((1u << (b + 1)) - 1u));
-    } else if (w + 1 < W) {
-        const uint32_t Bp = bmp[nwidx + 1];
-        if (Bp & 1u) nb[cnt++] = base[nwidx + 1];
-    }
+// number of roots with a list position below x (x < n): the rank of x when x is a root
+__device__ __forceinline__ uint32_t roots_below(const uint2 *__restrict__ flags, const uint32_t *cpre, uint32_t x) {
+    const uint2 f = __ldcg(flags + (x >> 5));
+    return cpre[x >> kChunkShift] + f.y + (uint32_t)__popc(f.x & ((1u << (x & 31u)) - 1u));
 }
 
 __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __grid_constant__ pe_geom g, const SparseArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t smem[32];
+    __shared__ uint32_t cpre_s[kChunkSmem];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = gridDim.x, b = blockIdx.x;
-    const int warps_per_block = blockDim.x >> 5;
-    const int64_t total_words = 2 * a.nwords_pad;
-    // contiguous word segment of this warp (multiple of 32 words)
-    const int64_t nwarps = (int64_t)nb * warps_per_block;
-    const int64_t seg = (((total_words + nwarps - 1) / nwarps) + 31) / 32 * 32;
-    const int64_t gw = (int64_t)b * warps_per_block + warp;
-    const int64_t w_begin = min(gw * seg, total_words), w_end = min(w_begin + seg, total_words);
+    const int warps_per_block = kSparseThreads >> 5;
     stamp(0);
 
-    // ---- S1a: popcount of every warp segment -> block partials
-    uint32_t cnt = 0;
-    for (int64_t i = w_begin + lane; i < w_end; i += 32) cnt += (uint32_t)__popc(a.bmp[i]);
-    const uint32_t warp_cnt = (uint32_t)warp_sum((int)cnt);
-    __shared__ uint32_t warp_cnts[32];
-    if (lane == 0) warp_cnts[warp] = warp_cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int i = 0; i < warps_per_block; ++i) t += warp_cnts[i];
-        a.sums[b] = t;
-    }
-    grid.sync();
-    stamp(1);
-
-    // ---- S1b + S2 (one pass): position of every word's first voxel, then key / initial parent of every foreground
-    // voxel.  Keys go to a temporary array indexed by the combined position (the rank buffer, free until S5), because
-    // the class-1 output offset needs n0, which is only known grid-wide after the next barrier.  Words are fetched
-    // four iterations ahead so that the L2 latency of the loads overlaps.
-    uint32_t before, n_all;
-    grid_prefix(a.sums, nb, b, smem, before, n_all);
-    uint32_t run = before;
-    for (int i = 0; i < warp; ++i) run += warp_cnts[i];
-    uint32_t *keyc = a.rank;
-    const uint32_t pcap = (uint32_t)(2 * a.cap);
-    uint32_t carry = (w_begin > 0 && w_begin < w_end) ? a.bmp[w_begin - 1] : 0u;  // the word before the current one (lane 0's predecessor)
-    for (int64_t i0 = w_begin; i0 < w_end; i0 += 128) {
-        uint32_t wq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t widx = i0 + 32 * q + lane;
-            wq[q] = widx < w_end ? a.bmp[widx] : 0u;
+    // ---- P1: positions, keys, densities, initial parents
+    // contiguous run of segments per warp; the voxels before it are the segment counts before it
+    const int nwarps = nb * warps_per_block;
+    const int spw = (a.nseg + nwarps - 1) / nwarps;  // segments per warp
+    const int seg_class1 = (int)(a.nwords_pad >> kSegShift);
+    const int sb = min(b * warps_per_block * spw, a.nseg);  // first segment of this block
+    uint32_t before, n0, n_all;
+    {
+        uint32_t s_before = 0, s0 = 0, s_all = 0;
+        for (int i = threadIdx.x; i < a.nseg; i += kSparseThreads) {
+            const uint32_t v = a.segcount[i];
+            s_all += v;
+            if (i < sb) s_before += v;
+            if (i < seg_class1) s0 += v;
         }
+        before = block_sum_u32(s_before, smem);
+        n0 = block_sum_u32(s0, smem);
+        n_all = block_sum_u32(s_all, smem);
+    }
+    const int64_t n = (int64_t)n_all;
+    const uint32_t n1 = n_all - n0;
+    if (b == 0 && threadIdx.x == 0) {
+        a.counts[0] = (int64_t)n0;
+        a.counts[2] = (int64_t)n1;
+    }
+    if ((int64_t)n0 > a.cap || (int64_t)n1 > a.cap) {  // grid-uniform: nothing has been written yet
+        if (b == 0 && threadIdx.x == 0) a.counts[4] = 1;
+        return;
+    }
+    {
+        const int seg_begin = min(sb + warp * spw, a.nseg), seg_end = min(seg_begin + spw, a.nseg);
+        uint32_t mine = 0;
+        for (int i = sb + lane; i < seg_begin; i += 32) mine += a.segcount[i];
+        uint32_t run = before + (uint32_t)warp_sum((int)mine);
+        uint32_t carry = 0u;  // the word before the current one
+        if (seg_begin < seg_end && seg_begin > 0) carry = a.bmp[((int64_t)seg_begin << kSegShift) - 1];
+        for (int64_t i0 = (int64_t)seg_begin << kSegShift; i0 < ((int64_t)seg_end << kSegShift); i0 += 128) {
+            const int64_t widx0 = i0 + 4 * lane;
+            const uint4 wv = *reinterpret_cast<const uint4 *>(a.bmp + widx0);
+            const int c4 = __popc(wv.x) + __popc(wv.y) + __popc(wv.z) + __popc(wv.w);
+            const int excl = warp_excl_scan(c4, lane);
+            uint32_t p = run + (uint32_t)excl;
+            run += (uint32_t)__shfl_sync(kFull, excl + c4, 31);
+            uint32_t prevw = __shfl_up_sync(kFull, wv.w, 1);
+            if (lane == 0) prevw = carry;
+            carry = __shfl_sync(kFull, wv.w, 31);
+            if (c4 == 0) continue;
+            const int k = widx0 >= a.nwords_pad ? 1 : 0;
+            const uint32_t local = (uint32_t)(widx0 - (k ? a.nwords_pad : 0));
+            const uint32_t colrow = local / (uint32_t)a.W;
+            const int w0 = (int)(local - colrow * (uint32_t)a.W);  // W is a multiple of 4: the four words share (column, row)
+            const int64_t out0 = (int64_t)k * a.cap - (k ? (int64_t)n0 : 0);  // output index = out0 + position
+            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t widx = i0 + 32 * q + lane;
-            const uint32_t word = wq[q];
-            const int c0 = __popc(word);
-            const uint32_t p_first = run + (uint32_t)warp_excl_scan(c0, lane);
-            run += (uint32_t)__shfl_sync(kFull, (int)(p_first - run) + c0, 31);
-            uint32_t prev = __shfl_up_sync(kFull, word, 1);
-            if (lane == 0) prev = carry;
-            carry = __shfl_sync(kFull, word, 31);
-            if (widx >= w_end) continue;
-            a.base[widx] = p_first;
-            if (widx == a.nwords_pad) a.counts[0] = (int64_t)p_first;  // everything before plane 1 is class 0
-            if (!word) continue;
-            const int k = widx >= a.nwords_pad ? 1 : 0;
-            const int64_t local = widx - (k ? a.nwords_pad : 0);
-            const int w = (int)(local % a.W);
-            const int64_t colrow = local / a.W;
-            const bool prev_last = (w > 0) && (prev >> 31);
-            // bits that start a run of consecutive sections inside this word (a run entering from the previous word
-            // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
-            const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
-            const uint32_t keybase = (uint32_t)(colrow * a.U2 + (int64_t)w * 32);
-            uint32_t rest = word, p = p_first;
-            while (rest) {
-                const int bit = __ffs(rest) - 1;
-                rest &= rest - 1;
-                // parent = first voxel of the run (path-compressed chaining: finds stay O(1) instead of O(run length))
-                const uint32_t below = starts & ((2u << bit) - 1u);
-                uint32_t par;
-                if (below) {
-                    const int sb = 31 - __clz(below);
-                    par = p_first + (uint32_t)__popc(word & ((1u << sb) - 1u));
-                } else {
-                    par = p_first - 1;  // the run continues from the previous word (prev_last is set)
-                }
-                if (p < pcap) {  // beyond the capacity the overflow flag is raised after the barrier
-                    keyc[p] = keybase + (uint32_t)bit;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t word = words[q];
+                if (!word) continue;
+                const int w = w0 + q;
+                const uint32_t pw = q == 0 ? prevw : words[q > 0 ? q - 1 : 0];
+                const bool prev_last = (w > 0) && (pw >> 31);
+                a.base[widx0 + q] = p;
+                // bits that start a run of consecutive sections inside this word (a run entering from the previous word
+                // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
+                const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
+                const uint32_t keybase = colrow * (uint32_t)a.U2 + (uint32_t)w * 32u;
+                const uint32_t p_first = p;
+                uint32_t rest = word;
+                while (rest) {
+                    const int bit = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    // parent = first voxel of the run (finds stay O(1) instead of O(run length))
+                    const uint32_t below = starts & ((2u << bit) - 1u);
+                    uint32_t par;
+                    if (below) {
+                        const int sbit = 31 - __clz(below);
+                        par = p_first + (uint32_t)__popc(word & ((1u << sbit) - 1u));
+                    } else {
+                        par = p_first - 1;  // the run continues from the previous word (prev_last is set)
+                    }
+                    a.key[out0 + p] = keybase + (uint32_t)bit;
                     a.parent[p] = par;
+                    ++p;
                 }
-                ++p;
             }
         }
     }
     grid.sync();
-    stamp(2);
-    const int64_t n0 = a.counts[0];
-    const int64_t n = (int64_t)n_all;
-    const int64_t n1 = n - n0;
-    const bool overflow = n0 > a.cap || n1 > a.cap;
-    if (b == 0 && threadIdx.x == 0) {
-        a.counts[2] = n1;
-        if (overflow) a.counts[4] = 1;
-    }
-    if (overflow) return;  // grid-uniform
-    stamp(3);
+    stamp(1);
 
-    // ---- S3: hook the 12 predecessor neighbours outside the voxel's own column
-    const int64_t gstride = (int64_t)nb * blockDim.x;
-    const int64_t gtid = (int64_t)b * blockDim.x + threadIdx.x;
+    // ---- P2: hook the 12 predecessor neighbours outside the voxel's own column; zero the per-blob sums
+    const int64_t gstride = (int64_t)nb * kSparseThreads;
+    const int64_t gtid = (int64_t)b * kSparseThreads + threadIdx.x;
+    {
+        const int64_t rows0 = min((int64_t)n0, a.cap_blobs) * 8, rows1 = min((int64_t)n1, a.cap_blobs) * 8;
+        for (int64_t i = gtid; i < rows0; i += gstride) a.stats[i] = 0.0;
+        for (int64_t i = gtid; i < rows1; i += gstride) a.stats[a.cap_blobs * 8 + i] = 0.0;
+    }
     for (int64_t i = gtid; i < n; i += gstride) {
-        const int k = i >= n0 ? 1 : 0;
-        const uint32_t p = (uint32_t)i;
-        const uint32_t kk = a.rank[i];  // the key parked by S2
-        a.key[(int64_t)k * a.cap + (i - (k ? n0 : 0))] = kk;
+        const int k = i >= (int64_t)n0 ? 1 : 0;
+        const int64_t oi = (int64_t)k * a.cap + (i - (k ? (int64_t)n0 : 0));
+        const uint32_t kk = __ldcg(a.key + oi);
         const int s = (int)(kk % (uint32_t)a.U2);
         const uint32_t colrow = kk / (uint32_t)a.U2;
         const int r = (int)(colrow % (uint32_t)a.U1), c = (int)(colrow / (uint32_t)a.U1);
         const int w = s >> 5, bit = s & 31;
         const uint32_t *bmp = a.bmp + (k ? a.nwords_pad : 0);
         const uint32_t *base = a.base + (k ? a.nwords_pad : 0);
-        // the density of the voxel (one independent gather per thread, in flight while the neighbours are looked up)
-        a.value[(int64_t)k * a.cap + (i - (k ? n0 : 0))] = __ldg(a.rho + ((int64_t)s * a.NR + r) * a.NC + c);
-        // the 12 predecessor neighbours outside the voxel's own column: columns (c-1, r-1..r+1) and (c, r-1)
+        // the density of the voxel: one independent gather per thread, in flight while the neighbours are looked up
+        const float dens = __ldg(a.rho + ((int64_t)s * a.NR + r) * a.NC + c);
+        // the four neighbour columns (c-1, r-1), (c-1, r), (c-1, r+1), (c, r-1): their words of this voxel's section
+        // range, all loads in flight together
+        int64_t nw[4];
+        bool ok[4];
+        ok[0] = c > 0 && r > 0;
+        ok[1] = c > 0;
+        ok[2] = c > 0 && r + 1 < a.U1;
+        ok[3] = r > 0;
+        nw[0] = ((int64_t)(c - 1) * a.U1 + r - 1) * a.W + w;
+        nw[1] = nw[0] + a.W;
+        nw[2] = nw[1] + a.W;
+        nw[3] = ((int64_t)c * a.U1 + r - 1) * a.W + w;
+        uint32_t B[4], Bm[4], Bp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            B[j] = ok[j] ? __ldcg(bmp + nw[j]) : 0u;
+            Bm[j] = (ok[j] && bit == 0 && w > 0) ? __ldcg(bmp + nw[j] - 1) : 0u;
+            Bp[j] = (ok[j] && bit == 31 && w + 1 < a.W) ? __ldcg(bmp + nw[j] + 1) : 0u;
+        }
+        // adjacent voxels of a neighbour column: the one at the same section if set (its s-1 / s+1 neighbours are chained
+        // to it already), else those at s-1 and s+1
+        uint32_t bs[4], bsm[4], bsp[4];
+        uint32_t sel[4];  // bit 0: same section, bit 1: s-1 in this word, bit 2: s+1 in this word, bit 3: s-1 in the word before, bit 4: s+1 in the word after
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t m = 0;
+            if ((B[j] >> bit) & 1u) {
+                m = 1u;
+            } else {
+                if (bit > 0 && ((B[j] >> (bit - 1)) & 1u)) m |= 2u;
+                if (bit < 31 && ((B[j] >> (bit + 1)) & 1u)) m |= 4u;
+                if (Bm[j] >> 31) m |= 8u;
+                if (Bp[j] & 1u) m |= 16u;
+            }
+            sel[j] = m;
+            bs[j] = (m & 7u) ? __ldcg(base + nw[j]) : 0u;
+            bsm[j] = (m & 8u) ? __ldcg(base + nw[j] - 1) : 0u;
+            bsp[j] = (m & 16u) ? __ldcg(base + nw[j] + 1) : 0u;
+        }
         uint32_t nbr[8];
         int cnt = 0;
-        if (c > 0) {
-            const int64_t rowbase = (int64_t)(c - 1) * a.U1;
-            if (r > 0) neighbours_in_column(bmp, base, (rowbase + r - 1) * a.W + w, w, bit, a.W, nbr, cnt);
-            neighbours_in_column(bmp, base, (rowbase + r) * a.W + w, w, bit, a.W, nbr, cnt);
-            if (r + 1 < a.U1) neighbours_in_column(bmp, base, (rowbase + r + 1) * a.W + w, w, bit, a.W, nbr, cnt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t m = sel[j];
+            if (m & 1u) nbr[cnt++] = bs[j] + (uint32_t)__popc(B[j] & ((1u << bit) - 1u));
+            if (m & 2u) nbr[cnt++] = bs[j] + (uint32_t)__popc(B[j] & ((1u << (bit - 1)) - 1u));
+            if (m & 8u) nbr[cnt++] = bsm[j] + (uint32_t)__popc(Bm[j] & 0x7fffffffu);
+            if (m & 4u) nbr[cnt++] = bs[j] + (uint32_t)__popc(B[j] & ((1u << (bit + 1)) - 1u));
+            if (m & 16u) nbr[cnt++] = bsp[j];
         }
-        if (r > 0) neighbours_in_column(bmp, base, ((int64_t)c * a.U1 + r - 1) * a.W + w, w, bit, a.W, nbr, cnt);
-        // one union site for all lanes: the finds and hooks of a warp proceed in lock step instead of once per case
+        // one union site for all lanes; the voxel's root is carried from one hook to the next
+        uint32_t cur = (uint32_t)i;
 #pragma unroll 1
-        for (int j = 0; j < cnt; ++j) uf_union(a.parent, p, nbr[j]);
+        for (int j = 0; j < cnt; ++j) cur = uf_union_root(a.parent, cur, nbr[j]);
+        a.value[oi] = dens;
     }
     grid.sync();
-    stamp(4);
+    stamp(2);
 
-    // ---- S4: flatten; S5: rank the roots (blob number = rank of the blob's first voxel)
-    const int64_t vseg = (((n + nwarps - 1) / nwarps) + 31) / 32 * 32;
-    const int64_t v_begin = min(gw * vseg, n), v_end = min(v_begin + vseg, n);
-    uint32_t roots = 0;
-    for (int64_t i = v_begin + lane; i < v_end; i += 32) {
-        const uint32_t root = uf_find(a.parent, (uint32_t)i);
-        a.parent[i] = root;  // still a valid ancestor for concurrent finds
-        roots += root == (uint32_t)i ? 1u : 0u;
-    }
-    const uint32_t warp_roots = (uint32_t)warp_sum((int)roots);
-    __syncthreads();
-    if (lane == 0) warp_cnts[warp] = warp_roots;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int i = 0; i < warps_per_block; ++i) t += warp_cnts[i];
-        a.sums[kSparseMaxBlocks + b] = t;
+    // ---- P3: flatten; root flags per 32 voxels, roots before each word inside its chunk, roots per chunk
+    const int64_t nchunks = (n + kSparseThreads - 1) >> kChunkShift;
+    __shared__ uint32_t wcnt[32];
+    for (int64_t chunk = b; chunk < nchunks; chunk += nb) {
+        const int64_t i = (chunk << kChunkShift) + threadIdx.x;
+        bool isroot = false;
+        if (i < n) {
+            const uint32_t root = uf_find(a.parent, (uint32_t)i);
+            a.parent[i] = root;  // still a valid ancestor for concurrent finds
+            isroot = root == (uint32_t)i;
+        }
+        const uint32_t fw = __ballot_sync(kFull, isroot);
+        if (lane == 0) wcnt[warp] = (uint32_t)__popc(fw);
+        __syncthreads();
+        uint32_t fine = 0, tot = 0;
+        for (int j = 0; j < warps_per_block; ++j) {
+            const uint32_t v = wcnt[j];
+            if (j < warp) fine += v;
+            tot += v;
+        }
+        if (lane == 0) a.flags[(chunk << (kChunkShift - 5)) + warp] = make_uint2(fw, fine);
+        if (threadIdx.x == 0) a.coarse[chunk] = tot;
+        __syncthreads();  // wcnt is rewritten by the next chunk
     }
     grid.sync();
-    stamp(5);
-    uint32_t roots_before, n_roots;
-    grid_prefix(a.sums + kSparseMaxBlocks, nb, b, smem, roots_before, n_roots);
-    uint32_t rrun = roots_before;
-    for (int i = 0; i < warp; ++i) rrun += warp_cnts[i];
-    for (int64_t i0 = v_begin; i0 < v_end; i0 += 32) {
-        const int64_t i = i0 + lane;
-        const int isroot = (i < v_end && a.parent[i] == (uint32_t)i) ? 1 : 0;
-        const uint32_t ex = rrun + (uint32_t)warp_excl_scan(isroot, lane);
-        if (isroot) a.rank[i] = ex;
-        if (i < v_end && i == n0) a.counts[1] = (int64_t)ex;  // roots among the class-0 voxels
-        rrun += (uint32_t)__shfl_sync(kFull, (int)(ex - rrun) + isroot, 31);
+    stamp(3);
+
+    // ---- P4: chunk prefix (per block, in shared memory), blob counts, labels + sums
+    const uint32_t *cpre = cpre_s;
+    uint32_t n_roots;
+    if (nchunks <= kChunkSmem) {
+        // every thread scans kChunkSmem / kSparseThreads consecutive chunk counts, then a block scan of the partials
+        constexpr int kPer = kChunkSmem / kSparseThreads;
+        uint32_t v[kPer], sum = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int64_t ci = (int64_t)threadIdx.x * kPer + j;
+            v[j] = ci < nchunks ? __ldcg(a.coarse + ci) : 0u;
+            sum += v[j];
+        }
+        const uint32_t wex = (uint32_t)warp_excl_scan((int)sum, lane);
+        __syncthreads();
+        if (lane == 31) wcnt[warp] = wex + sum;
+        __syncthreads();
+        uint32_t off = wex;
+        uint32_t all = 0;
+        for (int j = 0; j < warps_per_block; ++j) {
+            const uint32_t t = wcnt[j];
+            if (j < warp) off += t;
+            all += t;
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            cpre_s[threadIdx.x * kPer + j] = off;
+            off += v[j];
+        }
+        n_roots = all;
+        __syncthreads();
+    } else {
+        // very large foreground: block 0 scans the chunk counts into global memory, one more barrier
+        uint32_t *gpre = a.coarse + a.nchunk_cap;
+        if (b == 0) {
+            __shared__ uint32_t carry_s;
+            if (threadIdx.x == 0) carry_s = 0u;
+            __syncthreads();
+            for (int64_t c0 = 0; c0 < nchunks; c0 += kSparseThreads) {
+                const int64_t ci = c0 + threadIdx.x;
+                const uint32_t v = ci < nchunks ? __ldcg(a.coarse + ci) : 0u;
+                const uint32_t wex = (uint32_t)warp_excl_scan((int)v, lane);
+                if (lane == 31) wcnt[warp] = wex + v;
+                __syncthreads();
+                uint32_t off = carry_s + wex, all = 0;
+                for (int j = 0; j < warps_per_block; ++j) {
+                    const uint32_t t = wcnt[j];
+                    if (j < warp) off += t;
+                    all += t;
+                }
+                if (ci < nchunks) gpre[ci] = off;
+                __syncthreads();
+                if (threadIdx.x == 0) carry_s += all;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) gpre[nchunks] = carry_s;
+        }
+        grid.sync();
+        cpre = gpre;
+        n_roots = __ldcg(gpre + nchunks);
     }
-    if (b == 0 && threadIdx.x == 0 && n0 == n) a.counts[1] = (int64_t)n_roots;
-    grid.sync();
-    stamp(6);
-    const int64_t nb0 = a.counts[1];
-    const int64_t nb1 = (int64_t)n_roots - nb0;
-    if (b == 0 && threadIdx.x == 0) a.counts[3] = nb1;
-    const bool blob_overflow = nb0 > a.cap_blobs || nb1 > a.cap_blobs;
-    if (blob_overflow) {
+    const uint32_t nb0 = n0 == n_all ? n_roots : roots_below(a.flags, cpre, n0);  // roots among the class-0 voxels
+    const uint32_t nb1 = n_roots - nb0;
+    if (b == 0 && threadIdx.x == 0) {
+        a.counts[1] = (int64_t)nb0;
+        a.counts[3] = (int64_t)nb1;
+    }
+    if ((int64_t)nb0 > a.cap_blobs || (int64_t)nb1 > a.cap_blobs) {  // grid-uniform
         if (b == 0 && threadIdx.x == 0) a.counts[4] = 1;
-        return;  // grid-uniform
+        return;
     }
-
-    // ---- S6: zero the per-blob sums, then labels + sums (DensityBlob.fromCrsList, pdb_eda/ccp4.py:534-545)
-    for (int64_t i = gtid; i < nb0 * 8; i += gstride) a.stats[i] = 0.0;
-    for (int64_t i = gtid; i < nb1 * 8; i += gstride) a.stats[a.cap_blobs * 8 + i] = 0.0;
-    grid.sync();
-    stamp(7);
     for (int64_t i0 = gtid - lane; i0 < n; i0 += gstride) {  // warp-uniform trip count
         const int64_t i = i0 + lane;
         const bool live = i < n;
         int32_t blob = -1;
-        int k = 0;
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (live) {
-            k = i >= n0 ? 1 : 0;
-            const int64_t oi = (int64_t)k * a.cap + (i - (k ? n0 : 0));
-            const uint32_t gr = a.rank[a.parent[i]];
-            blob = (int32_t)(gr - (k ? (uint32_t)nb0 : 0u));
+            const int k = i >= (int64_t)n0 ? 1 : 0;
+            const int64_t oi = (int64_t)k * a.cap + (i - (k ? (int64_t)n0 : 0));
+            const uint32_t gr = roots_below(a.flags, cpre, __ldcg(a.parent + i));
+            blob = (int32_t)(gr - (k ? nb0 : 0u));
             a.label[oi] = blob;
             blob += k ? (int32_t)a.cap_blobs : 0;  // row of the combined stats table
-            const uint32_t kk = a.key[oi];
+            const uint32_t kk = __ldcg(a.key + oi);
             const int s = (int)(kk % (uint32_t)a.U2);
             const uint32_t colrow = kk / (uint32_t)a.U2;
             const int r = (int)(colrow % (uint32_t)a.U1), c = (int)(colrow / (uint32_t)a.U1);
             double x, y, z;
             crs2xyz(g, c, r, s, x, y, z);
-            const double d = (double)a.value[oi];
+            const double d = (double)__ldcg(a.value + oi);
             v[0] = 1.0;
             v[1] = d;
             v[2] = __dmul_rn(d, x);
@@ -472,7 +578,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
             for (int q = 0; q < 8; ++q) atomicAdd(st + q, v[q]);
         }
     }
-    stamp(8);
+    stamp(4);
 }
 
 }  // namespace pe
@@ -503,6 +609,7 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     PE_CHECK_ARG(cut_pos == cut_pos && cut_neg == cut_neg, "pe_blob_label: NaN cutoff");
     const BlobPlan p = make_plan(g, cap_voxels);
     PE_CHECK_ARG((int64_t)p.U0 * p.U1 * p.U2 < (1ll << 32), "pe_blob_label: unique volume too large for 32-bit keys");
+    PE_CHECK_ARG(p.nwords_pad < (1ll << 31), "pe_blob_label: bit planes too large");
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)d_ws;
     const int NC = g->ncrs[0], NR = g->ncrs[1];
@@ -510,6 +617,8 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     const bool use_pos = cut_pos > 0.f, use_neg = cut_neg < 0.f;
 
     PE_CUDA(cudaMemsetAsync(d_counts, 0, 5 * sizeof(int64_t), st));
+    uint32_t *segcount = (uint32_t *)(ws + p.off_seg);
+    PE_CUDA(cudaMemsetAsync(segcount, 0, (size_t)p.nseg * sizeof(uint32_t), st));
     // K1: the only pass over the map
     {
         const bool vec4 = (NC % 4 == 0) && (((uintptr_t)d_rho & 15u) == 0);
@@ -520,10 +629,10 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         PE_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "pe_blob_label: map too large for the launch grid");
         if (vec4)
             PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<4><<<grid, block, 0, st>>>(
-                d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
+                d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad, p.nwords_pad, segcount));
         else
             PE_LAUNCH("threshold_bitmap_kernel", st, threshold_bitmap_kernel<1><<<grid, block, 0, st>>>(
-                d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad));
+                d_rho, NC, NR, p.U0, p.U1, p.U2, p.W, cut_pos, cut_neg, use_pos, use_neg, bmp, bmp + p.nwords_pad, p.nwords_pad, segcount));
         PE_LAUNCH_CHECK();
     }
     // sparse stage: one cooperative kernel for both signs
@@ -534,29 +643,28 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
     a.U1 = p.U1;
     a.U2 = p.U2;
     a.W = p.W;
-    a.nwords = p.nwords;
     a.nwords_pad = p.nwords_pad;
     a.cap = p.cap;
     a.cap_blobs = cap_blobs;
+    a.nseg = (int)p.nseg;
     a.bmp = bmp;
+    a.segcount = segcount;
     a.base = (uint32_t *)(ws + p.off_base);
     a.parent = (uint32_t *)(ws + p.off_parent);
-    a.rank = (uint32_t *)(ws + p.off_rank);
-    a.sums = (uint32_t *)(ws + p.off_sums);
+    a.flags = (uint2 *)(ws + p.off_flags);
+    a.coarse = (uint32_t *)(ws + p.off_coarse);
+    a.nchunk_cap = p.nchunk_cap;
     a.counts = d_counts;
     a.key = d_key;
     a.value = d_value;
     a.label = d_label;
     a.stats = d_stats;
-    a.use_pos = use_pos;
-    a.use_neg = use_neg;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, blob_sparse_kernel, kSparseThreads, 0));
         PE_CHECK_ARG(blocks_per_sm > 0, "pe_blob_label: the sparse kernel does not fit an SM");
     }
-    int nblocks = sm_count() * (blocks_per_sm < 3 ? blocks_per_sm : 3);
-    if (nblocks > kSparseMaxBlocks) nblocks = kSparseMaxBlocks;
+    const int nblocks = sm_count() * (blocks_per_sm < 3 ? blocks_per_sm : 3);
     pe_geom geom = *g;
     void *args[] = {(void *)&geom, (void *)&a};
     PE_LAUNCH("blob_sparse_kernel", st,

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
 //      (union_gather).  Each voxel of the union is read exactly once however many spheres hold it, and the float64
 //      summation order is fixed, so results are run-to-run deterministic.
 constexpr int kUnionWarps = 4;
-constexpr int kTileC = 64, kTileR = 48, kTileS = 48;
+constexpr int kTileC = 64, kTileR = 40, kTileS = 40;
 
 constexpr int kUnionChunk = 8;       // atoms whose tables are resident at once
 
@@ -488,7 +488,7 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
 __device__ unsigned long long g_union_cycles[4];
 
 template <int MODE>
-__global__ void __launch_bounds__(kUnionWarps * 32, 7)
+__global__ void __launch_bounds__(kUnionWarps * 32, 8)
     sphere_union_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_groups,
                         const int32_t *__restrict__ group_start, const double *__restrict__ xyz,
                         const float *__restrict__ radius, int32_t *box, double *thr, float cp, float cn,
@@ -944,7 +944,8 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     }
     if (n_groups > 0) {
         const int mode = g->map2xyz[2] == 1 ? 0 : (g->map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
-        const int ugrid = min(n_groups, sm_count() * 7);                           // persistent: 7 CTAs fit an SM
+        // persistent CTAs, 8 per SM (64 registers, 23 KB shared memory each); measured 5/6/7/8/9 per SM: 210/189/173/170/175 us on C2
+        const int ugrid = min(n_groups, sm_count() * 8);
         if (mode == 0)
             PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<0><<<ugrid, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, d_radius, box, thr, cut_pos, cut_neg, d_out));

@@ -56,7 +56,7 @@ import ctypes
 t = (ctypes.c_ulonglong * 12)()
 _lib.load().pe_blob_stage_times(t)
 t = list(t)
-print("blob sparse stages (us):", [round((t[i + 1] - t[i]) / 1e3, 1) for i in range(8)])
+print("blob sparse phases P1..P4 (us):", [round((t[i + 1] - t[i]) / 1e3, 1) for i in range(4)])
 u = (ctypes.c_ulonglong * 4)()
 _lib.load().pe_sphere_union_cycles(u)
 tot = float(sum(u)) or 1.0
