@@ -141,6 +141,62 @@ struct SphereAcc {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ exact chords
+// MODE 0: z is carried by the row axis, 1: by the section axis, 2: by the column axis.
+// Squared distance of column k of a box row exactly as the reference adds it: fl(fl(X2 + Y2) + Z2).
+template <int MODE>
+__device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, double B, double T) {
+    // MODE 0/1: A = square of the non-z axis among (row, section), B = square of the z axis;
+    // MODE 2  : A = fl(row square + section square), the column carries z.
+    const double d2 = (MODE == 2) ? __dadd_rn(A, sqc[k]) : __dadd_rn(__dadd_rn(sqc[k], A), B);
+    return d2 <= T;
+}
+
+// In-sphere columns [kl, kh] of one box row, exactly.  Along the columns of a box row the squared distance falls to the
+// column nearest the atom (km) and rises again (every rounding step is monotone), so the in-sphere columns are one
+// interval around that column.  The interval is GUESSED in float32 from the chord of the sphere along the row
+// (half-width sqrt(T - A - B) in columns around the atom's fractional column xc) and then VERIFIED with the exact
+// float64 predicate: inside at kl and kh, outside at kl - 1 and kh + 1 -- four independent tests that, by unimodality,
+// prove the guess.  A guess that fails (an end within ~1e-5 columns of a grid point, or a row that only just misses the
+// sphere) falls back to two binary searches with the same exact predicate.  Rows that miss the sphere leave after one
+// exact test without touching the table: every rounding step is monotone and the column term is >= 0, so
+// d2 >= fl(A + B) for every column of the row.  Returns false when no column of the row is inside.
+template <int MODE>
+__device__ __forceinline__ bool row_chord(const double *sqc, int nC, int km, float xc, float inv_gl, double A, double B, double T,
+                                          int &kl, int &kh) {
+    const double AB = (MODE == 2) ? A : __dadd_rn(A, B);
+    if (!(AB <= T)) return false;  // exact: the row misses the sphere
+    const float rem = (float)__dsub_rn(T, AB);
+    const float h = rem > 0.f ? rem * rsqrtf(rem) * inv_gl : 0.f;
+    kl = min(max((int)ceilf(xc - h), 0), km);
+    kh = max(min((int)floorf(xc + h), nC - 1), km);
+    const bool in_l = row_pred<MODE>(sqc, kl, A, B, T), in_h = row_pred<MODE>(sqc, kh, A, B, T);
+    const bool out_l = kl == 0 || !row_pred<MODE>(sqc, kl - 1, A, B, T);
+    const bool out_h = kh == nC - 1 || !row_pred<MODE>(sqc, kh + 1, A, B, T);
+    if (in_l && in_h && out_l && out_h) return true;
+    if (!row_pred<MODE>(sqc, km, A, B, T)) return false;  // the row misses the sphere
+    int lo = 0, hi = km;  // smallest k in [0, km] inside
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (row_pred<MODE>(sqc, mid, A, B, T))
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    kl = lo;
+    lo = km;
+    hi = nC - 1;  // largest k in [km, nC) inside
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (row_pred<MODE>(sqc, mid, A, B, T))
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    kh = lo;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ sums kernel
 // CASEB: the column axis carries z (the last term of the reference's sum), so fl(X2 + Y2) depends on (row, section).
 template <bool CASEB>
@@ -209,14 +265,11 @@ __device__ __forceinline__ void sums_generic(const pe_geom &g, const float *__re
     }
 }
 
-__global__ void __launch_bounds__(kSphereWarps * 32)
-    sphere_sums_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
-                       const double *__restrict__ xyz, const int32_t *__restrict__ box, const double *__restrict__ thr,
-                       float cp, float cn, double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
-    __shared__ AxisTab tabs[kSphereWarps][2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * kSphereWarps + warp;
-    if (a >= n_atoms) return;
+// One atom by one warp: tabulated separable squares (orthogonal cells) or the generic per-candidate pass.
+template <int MODE>
+__device__ __forceinline__ void sums_one_atom(const pe_geom &g, const float *__restrict__ rho, int a, const double *__restrict__ xyz,
+                                              const int32_t *__restrict__ box, const double *__restrict__ thr, float cp, float cn,
+                                              AxisTab *tab, int lane, double *__restrict__ out) {
     AtomBox b;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -225,16 +278,11 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     }
     const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
     const double T = thr[a];
-    cp = eff_pos(cp);
-    cn = eff_neg(cn);
     SphereAcc acc;
     const bool tabulated = g.orthogonal && b.dim[0] <= kDMax * 32 && b.dim[1] <= kDMax && b.dim[2] <= kDMax;
     if (tabulated) {
-        fill_tables(g, b, ax, ay, az, tabs[warp], lane);
-        if (g.map2xyz[2] == 0)
-            sums_ortho<true>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, acc);
-        else
-            sums_ortho<false>(g, rho, b, ax, ay, az, T, tabs[warp], lane, cp, cn, acc);
+        fill_tables(g, b, ax, ay, az, tab, lane);
+        sums_ortho<MODE == 2>(g, rho, b, ax, ay, az, T, tab, lane, cp, cn, acc);
     } else {
         sums_generic(g, rho, b, ax, ay, az, T, lane, cp, cn, acc);
     }
@@ -252,12 +300,123 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
         o[6] = bad ? 0.0 : 1.0;
         o[7] = (double)b.dim[0] * (double)b.dim[1] * (double)b.dim[2];
     }
+    __syncwarp();  // the tables are refilled for the warp's next atom
+}
+
+// Per-atom sums.  A warp takes kAtomsPerWarp = 4 consecutive atoms.  At the atom-type radii of the cloud pass
+// (0.6 - 1.3 A on a 0.5 A grid) a box is 4^3 or 6^3 candidates for ~15 in-sphere voxels, so when all four boxes are at
+// most 8 wide (orthogonal cell) each atom gets 8 lanes: a lane walks box rows (row, section), finds the row's in-sphere
+// columns exactly (row_chord) and gathers just those -- a fraction of the instructions of one warp per atom (49.7 -> 30.8 us on C2's
+// cloud pass).  Otherwise the warp handles its atoms one after the other with all 32 lanes
+// (sums_one_atom).
+constexpr int kSmallDim = 8;
+constexpr int kAtomsPerWarp = 4;
+struct SmallTab {
+    double sq[3][kSmallDim];  // per crs axis: fl((coord - atom)^2) of the box's indices
+    int off[3][kSmallDim];    // wrapped element offsets, or kInvalidOff
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kSphereWarps * 32)
+    sphere_sums_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
+                       const double *__restrict__ xyz, const int32_t *__restrict__ box, const double *__restrict__ thr,
+                       float cp, float cn, double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    __shared__ SmallTab stab[kSphereWarps][kAtomsPerWarp];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a0 = (blockIdx.x * kSphereWarps + warp) * kAtomsPerWarp;
+    if (a0 >= n_atoms) return;
+    cp = eff_pos(cp);
+    cn = eff_neg(cn);
+    const int sub = lane >> 3, l8 = lane & 7;
+    const int a = a0 + sub;
+    const bool live = a < n_atoms;
+    int lo[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = box[6 * a + k];
+            dim[k] = box[6 * a + 3 + k];
+        }
+    }
+    const bool small = g.orthogonal && dim[0] <= kSmallDim && dim[1] <= kSmallDim && dim[2] <= kSmallDim;
+    if (!__all_sync(kFull, small)) {
+        for (int q = 0; q < kAtomsPerWarp && a0 + q < n_atoms; ++q)
+            sums_one_atom<MODE>(g, rho, a0 + q, xyz, box, thr, cp, cn, tabs[warp], lane, out);
+        return;
+    }
+    SphereAcc acc;
+    if (live && dim[0] > 0 && dim[1] > 0 && dim[2] > 0) {
+        const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+        const double T = thr[a];
+        SmallTab &t = stab[warp][sub];
+#pragma unroll
+        for (int axis = 0; axis < 3; ++axis) {
+            if (l8 < dim[axis]) {
+                t.sq[axis][l8] = axis_sq(g, axis, lo[axis] + l8, ax, ay, az);
+                t.off[axis][l8] = axis_off(g, axis, lo[axis] + l8);
+            }
+        }
+        __syncwarp(0xffu << (8 * sub));  // the 8 lanes of this atom (they take this branch together)
+        const int ic = g.map2crs[0];  // xyz axis carried by the columns
+        const float inv_gl = (float)(1.0 / g.grid_length[ic]);
+        const float xc = (float)(sel3(ax, ay, az, ic) - g.origin[ic]) * inv_gl - (float)lo[0];  // guess only
+        const int nC = dim[0];
+        const double *sqc = t.sq[0];
+        // the column nearest the atom: the box's centre column or, after rounding, one of its neighbours
+        int km = min(max(nC / 2, 0), nC - 1);
+        if (km > 0 && sqc[km - 1] < sqc[km]) --km;
+        else if (km + 1 < nC && sqc[km + 1] < sqc[km]) ++km;
+        const int rows = dim[1] * dim[2];
+        for (int row = l8; row < rows; row += 8) {
+            const int is = row / dim[1], ir = row - is * dim[1];
+            const double sr = t.sq[1][ir], ss = t.sq[2][is];
+            const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
+            const double B = (MODE == 0) ? sr : ss;
+            int kl, kh;
+            if (!row_chord<MODE>(sqc, nC, km, xc, inv_gl, A, B, T, kl, kh)) continue;
+            const int o1 = t.off[1][ir], o2 = t.off[2][is];
+            const int orr = o1 | o2;
+            const unsigned osum = (unsigned)o1 + (unsigned)o2;
+            for (int k = kl; k <= kh; ++k) {
+                const int oc = t.off[0][k];
+                const bool ok = (orr | oc) >= 0;
+                float v = 0.f;
+                if (ok) v = __ldg(rho + (int)(osum + (unsigned)oc));
+                acc.bad |= ok ? 0 : 1;
+                acc.add(true, v, cp, cn);
+            }
+        }
+    }
+    __syncwarp();
+    // sums over the 8 lanes of an atom
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        acc.n_all += __shfl_xor_sync(kFull, acc.n_all, o);
+        acc.n_pos += __shfl_xor_sync(kFull, acc.n_pos, o);
+        acc.n_neg += __shfl_xor_sync(kFull, acc.n_neg, o);
+        acc.bad += __shfl_xor_sync(kFull, acc.bad, o);
+        acc.s_all += __shfl_xor_sync(kFull, acc.s_all, o);
+        acc.s_pos += __shfl_xor_sync(kFull, acc.s_pos, o);
+        acc.s_neg += __shfl_xor_sync(kFull, acc.s_neg, o);
+    }
+    if (live && l8 == 0) {
+        double *o = out + (int64_t)a * PE_SPHERE_NOUT;
+        o[0] = (double)acc.n_all;
+        o[1] = acc.s_all;
+        o[2] = (double)acc.n_pos;
+        o[3] = acc.s_pos;
+        o[4] = (double)acc.n_neg;
+        o[5] = acc.s_neg;
+        o[6] = acc.bad ? 0.0 : 1.0;
+        o[7] = (double)dim[0] * (double)dim[1] * (double)dim[2];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ union kernel
 // Set-union of the spheres of one group of atoms (getSphereCrsFromXyzList, pdb_eda/cutils.pyx:250-271; the region
 // density / discrepancy sums of pdb_eda/densityAnalysis.py:1037-1068, :1160-1211).  One CTA per group, two phases
-// per tile of the group's bounding box (tiles of 64 columns x 48 rows x 48 sections; a residue at the reference's
+// per tile of the group's bounding box (tiles of 64 columns x 40 rows x 40 sections; a residue at the reference's
 // default 3.5 A radius is one tile):
 //   1. membership: every warp walks its share of every atom's box rows and ORs the in-sphere columns of a box row
 //      into a shared-memory bitmap (two 32-bit words per (row, section)) -- one ballot and one or two atomicOr per
@@ -282,25 +441,8 @@ struct UnionShared {
     float xC[kUnionChunk];             // the atom's fractional column, as an index into sqC (interval guess only)
 };
 
-// MODE 0: z is carried by the row axis, 1: by the section axis, 2: by the column axis.
-// Squared distance of column k of a box row exactly as the reference adds it: fl(fl(X2 + Y2) + Z2).
-template <int MODE>
-__device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, double B, double T) {
-    // MODE 0/1: A = square of the non-z axis among (row, section), B = square of the z axis;
-    // MODE 2  : A = fl(row square + section square), the column carries z.
-    const double d2 = (MODE == 2) ? __dadd_rn(A, sqc[k]) : __dadd_rn(__dadd_rn(sqc[k], A), B);
-    return d2 <= T;
-}
-
-// Membership of one chunk of atoms in one tile: a work item is one box row (row, section) of one atom.  Along the
-// columns of a box row the squared distance falls to the column nearest the atom and rises again (every rounding
-// step is monotone), so the in-sphere columns are one interval [kl, kh] around that column.  The interval is
-// GUESSED in float32 from the chord of the sphere along the row (half-width sqrt(T - A - B) in columns around the
-// atom's fractional column xC) and then VERIFIED with the exact float64 predicate: inside at kl and kh, outside at
-// kl - 1 and kh + 1 -- four independent tests that, by unimodality, prove the guess.  A guess that fails (an end
-// within ~1e-5 columns of a grid point, or a row that only just misses the sphere) falls back to two binary searches
-// with the same exact predicate.  Rows that miss the sphere leave after one exact test without touching the tables:
-// every rounding step is monotone and the column term is >= 0, so d2 >= fl(A + B) for every column of the row.
+// Membership of one chunk of atoms in one tile: a work item is one box row (row, section) of one atom; its in-sphere
+// columns (row_chord: ~4 exact float64 tests per box row instead of one per candidate voxel) are OR-ed into the bitmap.
 template <int MODE, bool WIDE>
 __device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int tid, int nthreads, float inv_gl) {
     for (int j = 0; j < nchunk; ++j) {  // block-uniform
@@ -324,37 +466,8 @@ __device__ __forceinline__ void union_mark_rows(UnionShared &sh, int nchunk, int
             const double sr = sh.sqR[j][ir], ss = sh.sqS[j][is];
             const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
             const double B = (MODE == 0) ? sr : ss;
-            const double AB = (MODE == 2) ? A : __dadd_rn(A, B);
-            if (!(AB <= T)) continue;  // exact: the row misses the sphere
-            const float rem = (float)__dsub_rn(T, AB);
-            const float h = rem > 0.f ? rem * rsqrtf(rem) * inv_gl : 0.f;
-            int kl = min(max((int)ceilf(xc - h), 0), km);
-            int kh = max(min((int)floorf(xc + h), nC - 1), km);
-            const bool in_l = row_pred<MODE>(sqc, kl, A, B, T), in_h = row_pred<MODE>(sqc, kh, A, B, T);
-            const bool out_l = kl == 0 || !row_pred<MODE>(sqc, kl - 1, A, B, T);
-            const bool out_h = kh == nC - 1 || !row_pred<MODE>(sqc, kh + 1, A, B, T);
-            if (!(in_l && in_h && out_l && out_h)) {
-                if (!row_pred<MODE>(sqc, km, A, B, T)) continue;  // the row misses the sphere
-                int lo = 0, hi = km;  // smallest k in [0, km] inside
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (row_pred<MODE>(sqc, mid, A, B, T))
-                        hi = mid;
-                    else
-                        lo = mid + 1;
-                }
-                kl = lo;
-                lo = km;
-                hi = nC - 1;  // largest k in [km, nC) inside
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (row_pred<MODE>(sqc, mid, A, B, T))
-                        lo = mid;
-                    else
-                        hi = mid - 1;
-                }
-                kh = lo;
-            }
+            int kl, kh;
+            if (!row_chord<MODE>(sqc, nC, km, xc, inv_gl, A, B, T, kl, kh)) continue;  // the row misses the sphere
             const int count = kh - kl + 1;
             uint32_t *word = rows + 2 * (ir * kTileS + is);
             if (WIDE) {
@@ -933,12 +1046,20 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     ws += align_up((int64_t)n_atoms * 6 * 4, 256);
     double *thr = (double *)ws;
     ws += align_up((int64_t)n_atoms * 8, 256);
-    const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
     if (d_group_start == nullptr) {
         if (n_atoms > 0)
             PE_LAUNCH("sphere_params_kernel", st, sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr));
-        PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
-                                                                                             cut_pos, cut_neg, d_out));
+        const int mode1 = g->map2xyz[2] == 1 ? 0 : (g->map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
+        const int sblocks = (n_atoms + kSphereWarps * kAtomsPerWarp - 1) / (kSphereWarps * kAtomsPerWarp);
+        if (mode1 == 0)
+            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<0><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+                                                                                                  cut_pos, cut_neg, d_out));
+        else if (mode1 == 1)
+            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<1><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+                                                                                                  cut_pos, cut_neg, d_out));
+        else
+            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<2><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+                                                                                                  cut_pos, cut_neg, d_out));
         PE_LAUNCH_CHECK();
         return PE_OK;
     }
