@@ -356,8 +356,9 @@ def main_gpu(args, rank, world, local_rank):
         algo = {"threshold_bitmap_kernel": 4.0 * blob_units,                               # 4 N_vox
                 "sphere_union_kernel": 4.0 * region_union + 52.0 * vp.n_atoms,            # 4 V_in + 52 A (region pass)
                 "sphere_sums_kernel": 4.0 * cloud_units + 52.0 * vp.n_atoms}              # 4 V_in + 52 A (cloud pass)
-        notes = {"sphere_union_kernel": "bound by fp64 membership tests + sector-granular L2 gathers, not by HBM; V_in = union voxels",
-                 "sphere_sums_kernel": "bound by fp64 membership tests (216 candidates per atom at cloud radii), not by HBM"}
+        notes = {"sphere_union_kernel": "bound by instruction issue and dependent shared-memory / L2 latency (exact row chords, bitmap "
+                                        "compaction, sector-granular gathers), not by HBM; V_in = union voxels",
+                 "sphere_sums_kernel": "bound by latency of the per-atom chain (box, tables, exact row chords, 32-byte gathers), not by HBM"}
         kernels = []
         for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             kernels.append({"kernel": name, "launches": count, "ms_total": round(ms, 4), "us_per_launch": round(ms * 1e3 / max(count, 1), 2)})
@@ -378,6 +379,19 @@ def main_gpu(args, rank, world, local_rank):
                 roofs.append(r)
         dominant = roofs[0] if roofs else None      # kernels are sorted by total device time
         others = roofs[1:]
+        # whole paths (north_star quotes its targets per path): every kernel of the path, algorithmic bytes of the path
+        us = {k["kernel"]: k["us_per_launch"] * k["launches"] / args.steps for k in kernels}
+        paths = []
+        for label, names, nbytes in (
+                ("blob_ccl (threshold + sparse labelling, both signs)", ("threshold_bitmap_kernel", "blob_sparse_kernel"),
+                 4.0 * blob_units + 8.0 * n_fg + 64.0 * n_blob),
+                ("atom_spheres (cloud + region passes)", ("sphere_params_kernel", "sphere_sums_kernel", "sphere_union_kernel"),
+                 algo["sphere_union_kernel"] + algo["sphere_sums_kernel"])):
+            t_us = sum(us.get(nm, 0.0) for nm in names)
+            if t_us > 0:
+                ach = nbytes / (t_us * 1e-6) / 1e9
+                paths.append({"path": label, "kernels": list(names), "us_per_step": round(t_us, 2), "algorithmic_bytes_per_step": nbytes,
+                              "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_plain / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -390,7 +404,7 @@ def main_gpu(args, rank, world, local_rank):
                                    "foreground_voxels": n_fg, "blobs": n_blob},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "roofline": dominant, "roofline_other": others,
+                "gpu_launches": int(launches), "roofline": dominant, "roofline_other": others, "roofline_paths": paths,
                 "kernels": kernels[:12], "ms_per_step_profiled": ms_total / args.steps, "clocks": clocks}
         if world == 1 and not args.no_cpu:
             _, cpu, _ = run_cpu_sample(1, 0)

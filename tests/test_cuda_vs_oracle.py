@@ -236,6 +236,36 @@ def test_blob_properties_at_scale():
         assert ncl == nb and torch.equal(lab2.long(), label)
 
 
+def test_blob_dense_foreground_beyond_the_shared_rank_table():
+    """More than 2 M foreground voxels (4,096 ranking chunks): the sparse stage ranks the roots through the global
+    chunk prefix (one more grid barrier) instead of the per-block shared-memory table.  Checked against
+    scipy.ndimage.label (26-connectivity) renumbered by first voxel in createFullCrsList order."""
+    import scipy.ndimage as ndi
+    from pdb_eda_b200 import _device, ccp4, synthetic
+    n = 176
+    import torch
+    vol = np.ascontiguousarray(synthetic.smoothNoiseMap(n, seed=31, sigma=1.0), dtype=np.float32)
+    hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), (88.0,) * 3 + (90, 90, 90), (n, n, n)))
+    dev = _device.DeviceMap(_device.geom_from_header(hdr), torch.from_numpy(vol.reshape(-1)).cuda())
+    m, s = dev.mean_std()
+    cut = float(np.float32(m + 0.3 * s))
+    parts = dev.blob_label(cut, -cut, cap_voxels=3_000_000, cap_blobs=1_000_000)
+    assert sum(p["n_voxels"] for p in parts) > 4096 * 512
+    crs_order = np.ascontiguousarray(vol.transpose(2, 1, 0))  # [c][r][s]: C order = createFullCrsList order
+    for part, mask in zip(parts, (crs_order >= np.float32(cut), crs_order <= np.float32(-cut))):
+        lab, nlab = ndi.label(mask, structure=np.ones((3, 3, 3), dtype=bool))
+        flat = lab[mask]
+        assert part["n_voxels"] == flat.size and part["n_blobs"] == nlab
+        _, first = np.unique(flat, return_index=True)
+        remap = np.empty(nlab + 1, dtype=np.int64)
+        remap[1 + np.argsort(first)] = np.arange(nlab)
+        assert np.array_equal(part["label"].cpu().numpy().astype(np.int64), remap[flat])
+        key = np.flatnonzero(mask.reshape(-1))
+        crs = part["crs"].cpu().numpy().astype(np.int64)
+        assert np.array_equal((crs[:, 0] * n + crs[:, 1]) * n + crs[:, 2], key)
+        assert np.array_equal(np.bincount(remap[flat], minlength=nlab), part["stats"][:, 0].cpu().numpy().astype(np.int64))
+
+
 def test_sphere_properties_at_scale():
     """BASELINE.json config 2 size (384^3, 40,000 atoms / 8,000 residues): size-independent properties of the sphere
     kernels plus an oracle check on a random sample of atoms and residues of the full-size problem."""
