@@ -1,6 +1,6 @@
 // pe_sphere.cu -- per-atom sphere enumeration, density gather-sum and voxel lists.
 //
-// Replaces (batched over atoms, one warp per atom):
+// Replaces (batched over atoms):
 //   getSphereCrsFromXyz / getSphereCrsFromXyzList        pdb_eda/cutils.pyx:220-271
 //   _testXyzWithinDistance                               pdb_eda/cutils.pyx:205-218
 //   testValidXyz / testValidXyzList                      pdb_eda/cutils.pyx:273-313
@@ -14,10 +14,12 @@
 //     is the already-rounded square the reference forms, so the per-axis squares and the wrapped memory offsets
 //     are tabulated once per atom in shared memory and a candidate costs one DADD + one DSETP;
 //   * sqrt is never evaluated:  sqrt_rn(d2) <= r  <=>  d2 <= T(r)  (sphere_threshold);
-//   * per-atom kernel (one warp per atom): lanes run along the column axis (contiguous in memory), small boxes
-//     pack several box rows into one warp, gathers are predicated and the inner loop is unrolled;
-//   * union kernel (one persistent CTA walks the groups): membership by exact interval search per box row into a
-//     shared-memory bitmap, then one coalesced gather per voxel of the union (see sphere_union_kernel);
+//   * along a box row the in-sphere columns are one interval: it is guessed from the sphere's chord in float32 and
+//     proved with four exact float64 tests (row_chord), so a box row costs ~4 tests instead of one per candidate;
+//   * per-atom kernel: four atoms per warp (8 lanes each, lanes walk box rows) while the boxes are at most 8 wide
+//     (atom-type radii); larger boxes take one warp per atom with lanes along the column axis (contiguous in memory);
+//   * union kernel (persistent CTAs walk the groups): row chords OR-ed into a shared-memory bitmap, which is then
+//     compacted into a list of map offsets and gathered densely, once per voxel of the union (see sphere_union_kernel);
 //   * warp-shuffle / fixed-order block reductions make the float64 sums run-to-run deterministic.
 // Skewed cells take generic passes that evaluate the reference's 3x3 mat-vec per candidate in the host BLAS's
 // accumulation order.
