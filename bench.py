@@ -247,6 +247,7 @@ def main_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=device)
     _device.require_cuda()
 
