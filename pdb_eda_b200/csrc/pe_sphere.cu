@@ -308,7 +308,7 @@ __device__ __forceinline__ void sums_one_atom(const pe_geom &g, const float *__r
 // Per-atom sums.  A warp takes kAtomsPerWarp = 4 consecutive atoms.  At the atom-type radii of the cloud pass
 // (0.6 - 1.3 A on a 0.5 A grid) a box is 4^3 or 6^3 candidates for ~15 in-sphere voxels, so when all four boxes are at
 // most 8 wide (orthogonal cell) each atom gets 8 lanes: a lane walks box rows (row, section), finds the row's in-sphere
-// columns exactly (row_chord) and gathers just those -- a fraction of the instructions of one warp per atom (49.7 -> 30.8 us on C2's
+// columns exactly (row_chord) and gathers just those -- a fraction of the instructions of one warp per atom (49.7 -> 29.1 us on C2's
 // cloud pass).  Otherwise the warp handles its atoms one after the other with all 32 lanes
 // (sums_one_atom).
 constexpr int kSmallDim = 8;
@@ -380,14 +380,23 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
             const int o1 = t.off[1][ir], o2 = t.off[2][is];
             const int orr = o1 | o2;
             const unsigned osum = (unsigned)o1 + (unsigned)o2;
-            for (int k = kl; k <= kh; ++k) {
-                const int oc = t.off[0][k];
-                const bool ok = (orr | oc) >= 0;
-                float v = 0.f;
-                if (ok) v = __ldg(rho + (int)(osum + (unsigned)oc));
-                acc.bad |= ok ? 0 : 1;
-                acc.add(true, v, cp, cn);
+            // all loads of the chord first (a chord has at most kSmallDim columns), then the sums.  (Walking the rows of
+            // the four atoms in lock step, reconverged every iteration, is slower -- 31.2 against 29.1 us: left to
+            // themselves the four groups drift apart and hide each other's latency.)
+            float v[kSmallDim];
+#pragma unroll
+            for (int j = 0; j < kSmallDim; ++j) {
+                const int k = kl + j;
+                v[j] = 0.f;
+                if (k <= kh) {
+                    const int oc = t.off[0][k];
+                    const bool ok = (orr | oc) >= 0;
+                    if (ok) v[j] = __ldg(rho + (int)(osum + (unsigned)oc));
+                    acc.bad |= ok ? 0 : 1;
+                }
             }
+#pragma unroll
+            for (int j = 0; j < kSmallDim; ++j) acc.add(kl + j <= kh, v[j], cp, cn);
         }
     }
     __syncwarp();
