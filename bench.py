@@ -386,7 +386,7 @@ def main_gpu(args, rank, world, local_rank):
         for label, names, nbytes in (
                 ("blob_ccl (threshold + sparse labelling, both signs)", ("threshold_bitmap_kernel", "blob_sparse_kernel"),
                  4.0 * blob_units + 8.0 * n_fg + 64.0 * n_blob),
-                ("atom_spheres (cloud + region passes)", ("sphere_params_kernel", "sphere_sums_kernel", "sphere_union_kernel"),
+                ("atom_spheres (cloud + region passes)", ("sphere_sums_kernel", "sphere_union_kernel"),
                  algo["sphere_union_kernel"] + algo["sphere_sums_kernel"])):
             t_us = sum(us.get(nm, 0.0) for nm in names)
             if t_us > 0:

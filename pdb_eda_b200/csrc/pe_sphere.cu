@@ -59,24 +59,6 @@ __device__ __forceinline__ void atom_box(const pe_geom &g, double ax, double ay,
     thr = sphere_threshold(r);
 }
 
-// Boxes and distance thresholds of a batch of atoms, one thread per atom.  Kept as its own (8 us) launch for the
-// per-atom kernel: computing them in that kernel's prologue put a float64 divide / sqrt chain in front of every
-// warp (49 -> 60-72 us); the union kernel, which is persistent, does compute them itself.
-__global__ void sphere_params_kernel(pe_geom g, int n, const double *__restrict__ xyz, const float *__restrict__ radius,
-                                     int32_t *__restrict__ box, double *__restrict__ thr) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
-    AtomBox b;
-    double t;
-    atom_box(g, xyz[3 * a], xyz[3 * a + 1], xyz[3 * a + 2], radius[a], b, t);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        box[6 * a + k] = b.lo[k];
-        box[6 * a + 3 + k] = b.dim[k];
-    }
-    thr[a] = t;
-}
-
 // Axis term of the separable squared distance for crs axis `axis`, index k (orthogonal cells only).
 __device__ __forceinline__ double axis_sq(const pe_geom &g, int axis, int k, double ax, double ay, double az) {
     const int i = g.map2crs[axis];  // xyz axis carried by this crs axis
@@ -270,16 +252,12 @@ __device__ __forceinline__ void sums_generic(const pe_geom &g, const float *__re
 // One atom by one warp: tabulated separable squares (orthogonal cells) or the generic per-candidate pass.
 template <int MODE>
 __device__ __forceinline__ void sums_one_atom(const pe_geom &g, const float *__restrict__ rho, int a, const double *__restrict__ xyz,
-                                              const int32_t *__restrict__ box, const double *__restrict__ thr, float cp, float cn,
-                                              AxisTab *tab, int lane, double *__restrict__ out) {
-    AtomBox b;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        b.lo[k] = box[6 * a + k];
-        b.dim[k] = box[6 * a + 3 + k];
-    }
+                                              const float *__restrict__ radius, float cp, float cn, AxisTab *tab, int lane,
+                                              double *__restrict__ out) {
     const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
-    const double T = thr[a];
+    AtomBox b;
+    double T;
+    atom_box(g, ax, ay, az, radius[a], b, T);
     SphereAcc acc;
     const bool tabulated = g.orthogonal && b.dim[0] <= kDMax * 32 && b.dim[1] <= kDMax && b.dim[2] <= kDMax;
     if (tabulated) {
@@ -321,8 +299,8 @@ struct SmallTab {
 template <int MODE>
 __global__ void __launch_bounds__(kSphereWarps * 32)
     sphere_sums_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_atoms,
-                       const double *__restrict__ xyz, const int32_t *__restrict__ box, const double *__restrict__ thr,
-                       float cp, float cn, double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
+                       const double *__restrict__ xyz, const float *__restrict__ radius, float cp, float cn,
+                       double *__restrict__ out /* n_atoms x PE_SPHERE_NOUT */) {
     __shared__ AxisTab tabs[kSphereWarps][2];
     __shared__ SmallTab stab[kSphereWarps][kAtomsPerWarp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -333,24 +311,30 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     const int sub = lane >> 3, l8 = lane & 7;
     const int a = a0 + sub;
     const bool live = a < n_atoms;
+    // box and distance threshold of this lane's atom (the 8 lanes of an atom compute the same values: SIMT makes that free,
+    // and a separate one-thread-per-atom launch in front of this kernel cost 9 us for C2's 40,000 atoms)
     int lo[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
+    double ax = 0.0, ay = 0.0, az = 0.0, T = -1.0;
     if (live) {
+        ax = xyz[3 * a];
+        ay = xyz[3 * a + 1];
+        az = xyz[3 * a + 2];
+        AtomBox bb;
+        atom_box(g, ax, ay, az, radius[a], bb, T);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            lo[k] = box[6 * a + k];
-            dim[k] = box[6 * a + 3 + k];
+            lo[k] = bb.lo[k];
+            dim[k] = bb.dim[k];
         }
     }
     const bool small = g.orthogonal && dim[0] <= kSmallDim && dim[1] <= kSmallDim && dim[2] <= kSmallDim;
     if (!__all_sync(kFull, small)) {
         for (int q = 0; q < kAtomsPerWarp && a0 + q < n_atoms; ++q)
-            sums_one_atom<MODE>(g, rho, a0 + q, xyz, box, thr, cp, cn, tabs[warp], lane, out);
+            sums_one_atom<MODE>(g, rho, a0 + q, xyz, radius, cp, cn, tabs[warp], lane, out);
         return;
     }
     SphereAcc acc;
     if (live && dim[0] > 0 && dim[1] > 0 && dim[2] > 0) {
-        const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
-        const double T = thr[a];
         SmallTab &t = stab[warp][sub];
 #pragma unroll
         for (int axis = 0; axis < 3; ++axis) {
@@ -1058,18 +1042,16 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     double *thr = (double *)ws;
     ws += align_up((int64_t)n_atoms * 8, 256);
     if (d_group_start == nullptr) {
-        if (n_atoms > 0)
-            PE_LAUNCH("sphere_params_kernel", st, sphere_params_kernel<<<(n_atoms + 127) / 128, 128, 0, st>>>(*g, n_atoms, d_xyz, d_radius, box, thr));
         const int mode1 = g->map2xyz[2] == 1 ? 0 : (g->map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
         const int sblocks = (n_atoms + kSphereWarps * kAtomsPerWarp - 1) / (kSphereWarps * kAtomsPerWarp);
         if (mode1 == 0)
-            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<0><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<0><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius,
                                                                                                   cut_pos, cut_neg, d_out));
         else if (mode1 == 1)
-            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<1><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<1><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius,
                                                                                                   cut_pos, cut_neg, d_out));
         else
-            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<2><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, box, thr,
+            PE_LAUNCH("sphere_sums_kernel", st, sphere_sums_kernel<2><<<sblocks, kSphereWarps * 32, 0, st>>>(*g, d_rho, n_atoms, d_xyz, d_radius,
                                                                                                   cut_pos, cut_neg, d_out));
         PE_LAUNCH_CHECK();
         return PE_OK;
