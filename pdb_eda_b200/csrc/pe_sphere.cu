@@ -145,13 +145,21 @@ __device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, dou
 // sphere) falls back to two binary searches with the same exact predicate.  Rows that miss the sphere leave after one
 // exact test without touching the table: every rounding step is monotone and the column term is >= 0, so
 // d2 >= fl(A + B) for every column of the row.  Returns false when no column of the row is inside.
+// 1 / sqrt(x) for the chord guess only: the bare MUFU.RSQ (rsqrtf() wraps it in denormal scaling, six more instructions
+// per box row; a denormal remainder just yields a guess that the exact tests reject)
+__device__ __forceinline__ float rsqrt_guess(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int MODE>
 __device__ __forceinline__ bool row_chord(const double *sqc, int nC, int km, float xc, float inv_gl, double A, double B, double T,
                                           int &kl, int &kh) {
     const double AB = (MODE == 2) ? A : __dadd_rn(A, B);
     if (!(AB <= T)) return false;  // exact: the row misses the sphere
     const float rem = (float)__dsub_rn(T, AB);
-    const float h = rem > 0.f ? rem * rsqrtf(rem) * inv_gl : 0.f;
+    const float h = rem > 0.f ? rem * rsqrt_guess(rem) * inv_gl : 0.f;
     kl = min(max((int)ceilf(xc - h), 0), km);
     kh = max(min((int)floorf(xc + h), nC - 1), km);
     const bool in_l = row_pred<MODE>(sqc, kl, A, B, T), in_h = row_pred<MODE>(sqc, kh, A, B, T);
@@ -515,7 +523,7 @@ constexpr int kListCap = kUnionChunk * (kTileC + kTileR + kTileS) * 2 / kUnionWa
 
 template <bool WIDE, bool CHECKED, bool HASNEG>
 __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__restrict__ rho, SphereAcc &acc, float cp, float cn,
-                                             int warp, int lane, int tR, int tS, bool contig) {
+                                             int warp, int lane, int tR, int tS) {
     static_assert(offsetof(UnionShared, sqR) == offsetof(UnionShared, sqC) + sizeof(double) * kUnionChunk * kTileC, "table layout");
     static_assert(offsetof(UnionShared, sqS) == offsetof(UnionShared, sqR) + sizeof(double) * kUnionChunk * kTileR, "table layout");
     static_assert(kListCap >= 32, "a word must fit the list");
@@ -549,14 +557,21 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
                 const bool fits = excl + cc <= kListCap;
                 const int total = __reduce_max_sync(kFull, fits ? excl + cc : 0);
                 if (pending && fits) {
-                    int pos = excl;
-                    while (w) {
-                        const int bcol = __ffs((int)w) - 1;
-                        w &= w - 1u;
-                        const int oc = contig ? oc0 + bcol : offc[bcol];  // contig: the tile's columns are adjacent in memory
-                        int e = (int)((unsigned)osum + (unsigned)oc);
-                        if (CHECKED) e = ((orr | oc) < 0) ? -1 : e;
-                        list[pos++] = e;
+                    int *dst = list + excl;
+                    if (CHECKED) {
+                        while (w) {
+                            const int bcol = __ffs((int)w) - 1;
+                            w &= w - 1u;
+                            const int oc = offc[bcol];
+                            *dst++ = ((orr | oc) < 0) ? -1 : (int)((unsigned)osum + (unsigned)oc);
+                        }
+                    } else {  // every index of the tile is stored and its columns are adjacent in memory
+                        const int rowbase = (int)((unsigned)osum + (unsigned)oc0);
+                        while (w) {
+                            const int bcol = __ffs((int)w) - 1;
+                            w &= w - 1u;
+                            *dst++ = rowbase + bcol;
+                        }
                     }
                     pending = false;
                 }
@@ -734,17 +749,17 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 8)
                             if (k > 0 && k < tC) invalid |= (sh.offC[k] != sh.offC[k - 1] + 1) ? 1 : 0;
                         }
                         // tiles that straddle the periodic boundary (columns not adjacent in memory) take the checked path too
-                        const bool checked = __syncthreads_or(invalid) != 0, contig = !checked;
+                        const bool checked = __syncthreads_or(invalid) != 0;
                         const int sel = (wide ? 4 : 0) | (checked ? 2 : 0) | (has_neg ? 1 : 0);
                         switch (sel) {
-                            case 0: union_gather<false, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            case 1: union_gather<false, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            case 2: union_gather<false, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            case 3: union_gather<false, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            case 4: union_gather<true, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            case 5: union_gather<true, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            case 6: union_gather<true, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
-                            default: union_gather<true, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS, contig); break;
+                            case 0: union_gather<false, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 1: union_gather<false, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 2: union_gather<false, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 3: union_gather<false, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 4: union_gather<true, false, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 5: union_gather<true, false, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            case 6: union_gather<true, true, false>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
+                            default: union_gather<true, true, true>(sh, rho, acc, cp, cn, warp, lane, tR, tS); break;
                         }
                     }
                     __syncthreads();
