@@ -196,6 +196,15 @@ def cleanPDBid(pdbid):
     return True
 
 
+def testCCP4URL(pdbid):
+    """Whether the PDBe API has electron density statistics for the entry (pdb_eda/densityAnalysis.py:262-275)."""
+    try:
+        urllib.request.urlopen("https://www.ebi.ac.uk/pdbe/api/pdb/entry/electron_density_statistics/" + pdbid)
+    except urllib.request.HTTPError:
+        return False
+    return True
+
+
 def residueAtomName(atom):
     """RESNAME_ATOMNAME key into the parameter tables (pdb_eda/densityAnalysis.py:1243-1251)."""
     return atom.parent.resname.strip() + "_" + atom.name
