@@ -608,6 +608,11 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
 
 // Diagnostic: SM cycles spent per phase, summed over all CTAs of the launches since the last read
 // (prologue, membership, gather, epilogue); read and reset with pe_sphere_union_cycles().
+// Compiled in with -DPE_UNION_PHASE_CYCLES=1 only: the four 64-bit accumulators and the time mark are live across the whole
+// kernel, and with 64 registers per thread they cost the hot loops registers (163.2 -> 160.9 us without them; pe_sphere_union_cycles() then reads zeros).
+#ifndef PE_UNION_PHASE_CYCLES
+#define PE_UNION_PHASE_CYCLES 0
+#endif
 __device__ unsigned long long g_union_cycles[4];
 
 template <int MODE>
@@ -620,8 +625,10 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 8)
     __shared__ double red_d[kUnionWarps][3];
     __shared__ int red_i[kUnionWarps][4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#if PE_UNION_PHASE_CYCLES
     long long t_mark = clock64();
     long long t_phase[4] = {0, 0, 0, 0};
+#endif
     cp = eff_pos(cp);
     cn = eff_neg(cn);
     const float inv_gl = (float)(1.0 / g.grid_length[g.map2crs[0]]);  // columns per Angstrom (interval guess only)
@@ -667,11 +674,13 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 8)
                     for (int k = tid; k < tR; k += blockDim.x) sh.offR[k] = axis_off(g, 1, tr0 + k);
                     for (int k = tid; k < tS; k += blockDim.x) sh.offS[k] = axis_off(g, 2, ts0 + k);
                     __syncthreads();  // bitmap is clear, offsets are in place
+#if PE_UNION_PHASE_CYCLES
                     {
                         const long long now = clock64();
                         t_phase[0] += now - t_mark;
                         t_mark = now;
                     }
+#endif
                     // phase 1: membership
                     if (g.orthogonal) {
                         for (int c0 = a0; c0 < a1; c0 += kUnionChunk) {
@@ -732,11 +741,13 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 8)
                         }
                     }
                     __syncthreads();
+#if PE_UNION_PHASE_CYCLES
                     {
                         const long long now = clock64();
                         t_phase[1] += now - t_mark;
                         t_mark = now;
                     }
+#endif
                     // phase 2: gather every voxel of the union once (union_gather), specialised on the tile width
                     // (32- or 64-bit bitmap rows), on whether every index of the tile is covered by the stored map
                     // (no validity logic in the loop) and on whether the negative class is in use.
@@ -763,11 +774,13 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 8)
                         }
                     }
                     __syncthreads();
+#if PE_UNION_PHASE_CYCLES
                     {
                         const long long now = clock64();
                         t_phase[2] += now - t_mark;
                         t_mark = now;
                     }
+#endif
                 }
     }
     const int n_all = warp_sum(acc.n_all), n_pos = warp_sum(acc.n_pos), n_neg = warp_sum(acc.n_neg);
@@ -800,16 +813,20 @@ __global__ void __launch_bounds__(kUnionWarps * 32, 8)
         o[6] = ni[3] ? 0.0 : 1.0;
         o[7] = candidates;
     }
+#if PE_UNION_PHASE_CYCLES
     {
         const long long now = clock64();
         t_phase[3] += now - t_mark;
         t_mark = now;
     }
+#endif
     }  // next group
+#if PE_UNION_PHASE_CYCLES
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) atomicAdd(g_union_cycles + k, (unsigned long long)t_phase[k]);
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ list kernels
