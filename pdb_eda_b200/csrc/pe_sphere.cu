@@ -616,7 +616,7 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
 __device__ unsigned long long g_union_cycles[4];
 
 template <int MODE>
-__global__ void __launch_bounds__(kUnionWarps * 32, 8)
+__global__ void __launch_bounds__(kUnionWarps * 32, 7)
     sphere_union_kernel(const __grid_constant__ pe_geom g, const float *__restrict__ rho, int n_groups,
                         const int32_t *__restrict__ group_start, const double *__restrict__ xyz,
                         const float *__restrict__ radius, int32_t *box, double *thr, float cp, float cn,
@@ -1090,8 +1090,9 @@ int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
     }
     if (n_groups > 0) {
         const int mode = g->map2xyz[2] == 1 ? 0 : (g->map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
-        // persistent CTAs, 8 per SM (64 registers, 23 KB shared memory each); measured 5/6/7/8/9 per SM: 210/189/173/170/175 us on C2
-        const int ugrid = min(n_groups, sm_count() * 8);
+        // persistent CTAs, 7 per SM (72 registers, no spills, 23 KB shared memory each).  Measured on C2: 6 / 7 / 8 per SM (78 / 72 /
+        // 64 registers) 174 / 158.6 / 159.8 us; earlier in the round 5 / 6 / 7 / 8 / 9 per SM gave 210 / 189 / 173 / 170 / 175 us
+        const int ugrid = min(n_groups, sm_count() * 7);
         if (mode == 0)
             PE_LAUNCH("sphere_union_kernel", st, sphere_union_kernel<0><<<ugrid, kUnionWarps * 32, 0, st>>>(
                 *g, d_rho, n_groups, d_group_start, d_xyz, d_radius, box, thr, cut_pos, cut_neg, d_out));
