@@ -387,8 +387,15 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
                     acc.bad |= ok ? 0 : 1;
                 }
             }
+            const bool has_neg = cn > __int_as_float(0xff800000);  // warp-uniform: the negative class is in use
 #pragma unroll
-            for (int j = 0; j < kSmallDim; ++j) acc.add(kl + j <= kh, v[j], cp, cn);
+            for (int j = 0; j < kSmallDim; ++j) {
+                if (kl + j > kh) break;  // chords are ~3 columns long: the sums are not worth issuing for empty slots
+                if (has_neg)
+                    acc.add(true, v[j], cp, cn);
+                else
+                    acc.add_pos(true, v[j], cp);
+            }
         }
     }
     __syncwarp();
