@@ -437,7 +437,6 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
         }
         // adjacent voxels of a neighbour column: the one at the same section if set (its s-1 / s+1 neighbours are chained
         // to it already), else those at s-1 and s+1
-        uint32_t bs[4], bsm[4], bsp[4];
         uint32_t sel[4];  // bit 0: same section, bit 1: s-1 in this word, bit 2: s+1 in this word, bit 3: s-1 in the word before, bit 4: s+1 in the word after
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -451,6 +450,25 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
                 if (Bp[j] & 1u) m |= 16u;
             }
             sel[j] = m;
+        }
+        // A neighbour at this voxel's own section is itself 26-adjacent to every other predecessor neighbour within one row
+        // and one column of it, and each of those pairs is hooked by whichever of the two comes later in scan order -- so
+        // hooking that one neighbour is enough (by induction over the scan order the components come out the same), and the
+        // dependent find / atomicMin round trips of the others are saved.  Columns: 0 (c-1, r-1), 1 (c-1, r), 2 (c-1, r+1),
+        // 3 (c, r-1); 0 and 2, and 2 and 3, are two rows apart.
+        if (sel[1] & 1u) {
+            sel[0] = sel[2] = sel[3] = 0u;
+        } else if (sel[3] & 1u) {
+            sel[0] = sel[1] = 0u;
+        } else if (sel[0] & 1u) {
+            sel[1] = sel[3] = 0u;
+        } else if (sel[2] & 1u) {
+            sel[1] = 0u;
+        }
+        uint32_t bs[4], bsm[4], bsp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t m = sel[j];
             bs[j] = (m & 7u) ? __ldcg(base + nw[j]) : 0u;
             bsm[j] = (m & 8u) ? __ldcg(base + nw[j] - 1) : 0u;
             bsp[j] = (m & 16u) ? __ldcg(base + nw[j] + 1) : 0u;
