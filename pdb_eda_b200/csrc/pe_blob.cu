@@ -464,6 +464,20 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
             sel[1] = sel[3] = 0u;
         } else if (sel[2] & 1u) {
             sel[1] = 0u;
+        } else {
+            // no neighbour at this section: the same argument per side (s-1: bits 1 and 3, s+1: bits 2 and 4) -- the
+            // neighbours of one side in columns within one row of each other are adjacent to each other
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t bits = side ? (4u | 16u) : (2u | 8u);
+                if (sel[1] & bits) {
+                    sel[0] &= ~bits;
+                    sel[2] &= ~bits;
+                    sel[3] &= ~bits;
+                } else if (sel[3] & bits) {
+                    sel[0] &= ~bits;
+                }
+            }
         }
         uint32_t bs[4], bsm[4], bsp[4];
 #pragma unroll
