@@ -277,7 +277,10 @@ def main_gpu(args, rank, world, local_rank):
     torch.cuda.synchronize()
     res = vp.results()
     cloud_units = float(res["cloud"][:, 0].sum())
-    region_pairs = float(dens.sphere_sums(vp.xyz, vp.region_radii)[:, 0].sum().item())
+    cloud_candidates = float(res["cloud"][:, 7].sum())          # box voxels examined (SURVEY.md section 8d asks for both)
+    region_per_atom = dens.sphere_sums(vp.xyz, vp.region_radii)
+    region_pairs = float(region_per_atom[:, 0].sum().item())
+    region_candidates = float(region_per_atom[:, 7].sum().item())
     blob_units = float(vp.n_blob_voxels)
     units = cloud_units + region_pairs + blob_units
 
@@ -400,7 +403,8 @@ def main_gpu(args, rank, world, local_rank):
                                        % (vp.n_atoms, vp.n_res),
                            "parallelism": "replicas x%d (single structure does not shard)" % world,
                            "l2": "inputs larger than L2 (2 x 226 MB maps per pass); no explicit flush"},
-                "units_per_step": {"cloud_atom_sphere_voxels": cloud_units, "region_atom_sphere_voxels": region_pairs,
+                "units_per_step": {"cloud_atom_sphere_voxels": cloud_units, "cloud_box_candidates": cloud_candidates,
+                                   "region_atom_sphere_voxels": region_pairs, "region_box_candidates": region_candidates,
                                    "region_union_voxels": region_union, "blob_ccl_voxels": blob_units,
                                    "foreground_voxels": n_fg, "blobs": n_blob},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
