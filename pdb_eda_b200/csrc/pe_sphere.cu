@@ -536,9 +536,12 @@ __device__ __forceinline__ void union_gather(UnionShared &sh, const float *__res
     static_assert(kListCap >= 32, "a word must fit the list");
     int *list = reinterpret_cast<int *>(&sh.sqC[0][0]) + warp * kListCap;
     const int nwords = tR * tS;
+    // wi / tS by multiplication: exact for wi < 2^11 and tS <= 2^6 (wi * tS < 2^20, no 32-bit overflow)
+    const unsigned div_tS = ((1u << 20) + (unsigned)tS - 1u) / (unsigned)tS;
+    static_assert(kTileR * kTileS < (1 << 11) && kTileS <= 64, "magic division by tS");
     for (int w0 = warp * 32; w0 < nwords; w0 += kUnionWarps * 32) {
         const int wi = w0 + lane;
-        const int rl = wi / tS, sl = wi - rl * tS;
+        const int rl = (int)(((unsigned)wi * div_tS) >> 20), sl = wi - rl * tS;
         uint2 mine = make_uint2(0u, 0u);
         uint32_t *wordp = sh.bits + 2 * (rl * kTileS + sl);
         if (wi < nwords) mine = *reinterpret_cast<const uint2 *>(wordp);
