@@ -362,8 +362,10 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
         if (km > 0 && sqc[km - 1] < sqc[km]) --km;
         else if (km + 1 < nC && sqc[km + 1] < sqc[km]) ++km;
         const int rows = dim[1] * dim[2];
+        const unsigned div_d1 = (1024u + (unsigned)dim[1] - 1u) / (unsigned)dim[1];  // exact for row < 64, dim[1] <= 8
+        static_assert(kSmallDim * kSmallDim * kSmallDim <= 1024, "magic division by dim[1]");
         for (int row = l8; row < rows; row += 8) {
-            const int is = row / dim[1], ir = row - is * dim[1];
+            const int is = (int)(((unsigned)row * div_d1) >> 10), ir = row - is * dim[1];  // row / dim[1]
             const double sr = t.sq[1][ir], ss = t.sq[2][is];
             const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
             const double B = (MODE == 0) ? sr : ss;
