@@ -217,6 +217,49 @@ int64_t pe_overlap_workspace_bytes(int64_t n, int64_t cap_pairs);
 int pe_overlap_pairs(int64_t n, const int32_t *d_crs, const int32_t *d_owner, const int32_t *d_group,
                      int64_t cap_pairs, int64_t *d_npairs, int32_t *d_pairs, void *d_ws, void *stream);
 
+/* ---------------------------------------------------------------- batched cloud aggregation ---------------- */
+/* DensityAnalysis.aggregateCloud (pdb_eda/densityAnalysis.py:571-729) for a batch of structures at once: the unit of
+ * work of multiple-structures mode (analyzePDBID, pdb_eda/multipleStructures.py:320-356) and of the optimiser's inner
+ * loop (processFunction, pdb_eda/optimizeParams.py:410-448).
+ *
+ * d_maps (device array, n_maps entries): one 2Fo-Fc map per structure -- geometry, device pointer to its voxels, the
+ * float32-narrowed densityCutoff (pdb_eda/densityAnalysis.py:131) and the range of its atoms in the
+ * batch arrays.  Atoms (the candidates of pdb_eda/densityAnalysis.py:596-603, in traversal order, structure by structure):
+ *   d_atom_map[a]       structure index
+ *   d_xyz[a*3..]        float64 coordinates (Biopython's float32 widened exactly), d_radius[a] float32 atom-type radius
+ *   d_atom_residue[a]   residue id, unique over the batch; d_atom_local[a] index of the atom inside its residue (< 64)
+ *   d_atom_bonded[a]    bit mask of the in-residue indices of its bonded atoms (bonded_atoms table)
+ *   d_atom_electrons[a] electrons * occupancy
+ *
+ * pe_cloud_count:  d_offset (n_atoms + 1 uint32) = exclusive prefix sum of every atom's number of cloud voxels
+ *                  (len(getSphereCrsFromXyz(dm, xyz, r, cutoff))); d_totals[0] = total, d_totals[1] = largest candidate box.
+ *                  d_scan_ws: >= 256 + 4 * (n_atoms / 1024 + 2) bytes.
+ * pe_cloud_aggregate (n_entries = d_totals[0], max_box_voxels = d_totals[1]) writes
+ *   d_atom_out[a*8..]  number of clouds, voxels of the best (nearest-centroid) cloud, its centroid distance, its total
+ *                      density, its centroid x y z, flags (0: does not contribute, 1: contributes, 3: contributes and is
+ *                      completely overlapped, pdb_eda/densityAnalysis.py:623-659)
+ *   d_map_out[m*8..]   numVoxelsAggregated, totalAggregatedDensity, totalAggregatedElectrons, domain clouds, domain clouds
+ *                      with >= min_cloud_electrons, residue clouds, residue clouds with >= min_cloud_electrons,
+ *                      centroidDistanceCutoff (pdb_eda/densityAnalysis.py:609, :681, :712-724)
+ * d_ws: >= pe_cloud_workspace_bytes(n_atoms, n_entries, n_residues).  pe_cloud_status reads the workspace's error flag
+ * (un-wrapped index outside +-8190 or inconsistent counts) and synchronises. */
+typedef struct pe_batch_map {
+    pe_geom geom;
+    const float *d_rho;
+    float cutoff;
+    int32_t atom_begin, atom_end;
+    int32_t reserved;
+} pe_batch_map;
+int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues);
+int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
+                   const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, void *stream);
+int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map,
+                       const double *d_xyz, const float *d_radius, const int32_t *d_atom_residue,
+                       const int32_t *d_atom_local, const uint64_t *d_atom_bonded, const double *d_atom_electrons,
+                       int32_t n_residues, const uint32_t *d_offset, int64_t n_entries, int32_t max_box_voxels,
+                       double min_cloud_electrons, double *d_atom_out, double *d_map_out, void *d_ws, void *stream);
+int pe_cloud_status(const void *d_ws, void *stream, int32_t *bad);
+
 /* ---------------------------------------------------------------- symmetry atoms --------------------------- */
 /* createSymmetryAtoms (pdb_eda/cutils.pyx:73-103).  d_xyz: n_atoms x 3 float64; d_rot: n_ops x 12 float64
  * (REMARK 290 3x4 operators, pdb_eda/pdbParser.py:71-77); d_shift: 27 x 3 float64, the lattice translations

@@ -78,6 +78,11 @@ SIGNATURES = {
     "pe_symmetry_expand": (ctypes.c_int, [_GEOM, _I32, _P, _I32, _P, _P, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_double), _I64, _P, _P, _P, _P, _P, _P]),
     "pe_nearest_atom": (ctypes.c_int, [_I64, _P, _I64, _P, _P, _P, _P]),
+    "pe_cloud_workspace_bytes": (_I64, [_I64, _I64, _I64]),
+    "pe_cloud_count": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "pe_cloud_aggregate": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, ctypes.c_double, _P, _P,
+                                          _P, _P]),
+    "pe_cloud_status": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32)]),
 }
 
 _lib = None

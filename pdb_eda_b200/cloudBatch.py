@@ -1,0 +1,410 @@
+"""Cloud aggregation for a batch of structures -- the unit of work of multiple-structures mode.
+
+The reference analyses one entry per ``multiprocessing.Pool`` task: ``analyzePDBID`` (pdb_eda/multipleStructures.py:320-356)
+and the optimiser's ``processFunction`` (pdb_eda/optimizeParams.py:410-448) both boil down to ``aggregateCloud``
+(pdb_eda/densityAnalysis.py:571-780) plus a handful of per-structure numbers.  Here the atoms of MANY structures are
+laid out as one set of arrays (atoms of a structure contiguous, one ``pe_batch_map`` per structure) and the whole
+aggregation -- per-atom clouds, centroid cutoff, residue / domain merging, completeness counters -- runs as one sequence
+of CUDA launches over the batch (``pe_cloud_count`` + ``pe_cloud_aggregate``, csrc/pe_aggregate.cu); the per-atom-type
+statistics block (pdb_eda/densityAnalysis.py:734-766) is numpy over the batch, one sort per median instead of a Python
+loop per structure and atom type.
+
+What this path does not produce are the order-dependent descriptions of merged clouds (the atom that names a domain
+cloud depends on Python set iteration order, pdb_eda/densityAnalysis.py:717); ``DensityAnalysis.aggregateCloud`` keeps
+the replay that yields those.  Structures this layout cannot express (atoms with identical coordinates, which share one
+``allAtomClouds`` entry at pdb_eda/densityAnalysis.py:606; more than 64 candidate atoms or repeated atom names in one
+residue) are flagged ``supported = False`` and must take ``DensityAnalysis.aggregateCloud``.
+"""
+import collections
+import ctypes
+
+import numpy as np
+import torch
+from scipy import special
+
+from . import _device
+from . import _lib
+from ._device import _ptr, _stream
+from ._lib import PeGeom, check
+
+MEDIAN_COLUMNS = ("num_voxels", "density_electron_ratio", "centroid_distance", "adj_density_electron_ratio", "volume", "bfactor",
+                  "slopes", "domain_fraction", "corrected_fraction", "corrected_density_electron_ratio")
+
+
+class PeBatchMap(ctypes.Structure):
+    """Mirror of ``struct pe_batch_map`` (include/pdbeda_b200.h)."""
+    _fields_ = [("geom", PeGeom), ("d_rho", ctypes.c_void_p), ("cutoff", ctypes.c_float), ("atom_begin", ctypes.c_int32),
+                ("atom_end", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class AtomTable:
+    """The candidate atoms of one structure (pdb_eda/densityAnalysis.py:596-603: residues with id[0] == ' ', atoms with a
+    known RES_ATOM type and non-zero occupancy) as arrays, in the reference's traversal order."""
+
+    def __init__(self, coords32, names, nameIndex, occupancy, bfactor, residue, local, bonded, nResidues, labels=None,
+                 supported=True, reason=""):
+        self.coords32 = np.ascontiguousarray(coords32, dtype=np.float32).reshape(-1, 3)
+        self.names = list(names)                      # distinct RES_ATOM names
+        self.nameIndex = np.asarray(nameIndex, dtype=np.int32)
+        self.occupancy = np.asarray(occupancy, dtype=np.float64)
+        self.bfactor = np.asarray(bfactor, dtype=np.float64)
+        self.residue = np.asarray(residue, dtype=np.int32)
+        self.local = np.asarray(local, dtype=np.int32)
+        self.bonded = np.asarray(bonded, dtype=np.uint64)
+        self.nResidues = int(nResidues)
+        self.labels = labels                          # optional (chain, residue number, residue name, atom name) per atom
+        self.supported = bool(supported)
+        self.reason = reason
+
+    def __len__(self):
+        return len(self.nameIndex)
+
+    @classmethod
+    def fromStructure(cls, biopdbObj, params):
+        """Walks a (duck-typed) Biopython structure once."""
+        types = params["full_atom_name_map_atom_type"]
+        bondedAtoms = params["bonded_atoms"]
+        coords, nameIdx, occ, bf, res, local, labels = [], [], [], [], [], [], []
+        names, nameOf = [], {}
+        residueNames = []                             # per residue: {RES_ATOM: local index}
+        supported, reason = True, ""
+        ridx = -1
+        for residue in biopdbObj.get_residues():
+            if residue.id[0] != ' ':
+                continue
+            ridx += 1
+            present = {}
+            for atom in residue.child_list:
+                resAtom = atom.parent.resname.strip() + "_" + atom.name
+                if resAtom not in types or atom.get_occupancy() == 0:
+                    continue
+                if resAtom in present:
+                    supported, reason = False, "residue with a repeated atom name (%s)" % resAtom
+                k = len(present)
+                present.setdefault(resAtom, k)
+                if resAtom not in nameOf:
+                    nameOf[resAtom] = len(names)
+                    names.append(resAtom)
+                coords.append(atom.coord)
+                nameIdx.append(nameOf[resAtom])
+                occ.append(atom.get_occupancy())
+                bf.append(atom.get_bfactor())
+                res.append(ridx)
+                local.append(k)
+                labels.append((residue.parent.id, residue.id[1], atom.parent.resname, atom.name))
+            residueNames.append(present)
+            if len(present) > 64:
+                supported, reason = False, "residue with more than 64 candidate atoms"
+        n = len(coords)
+        bonded = np.zeros(n, dtype=np.uint64)
+        for k in range(n):
+            present = residueNames[res[k]]
+            mask = 0
+            for other in bondedAtoms.get(names[nameIdx[k]], ()):
+                j = present.get(other)
+                if j is not None and j < 64:
+                    mask |= 1 << j
+            bonded[k] = mask
+        coords32 = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
+        if n and len(np.unique(coords32 + np.float32(0.0), axis=0)) < n:
+            supported, reason = False, "atoms with identical coordinates share one cloud entry"
+        return cls(coords32, names, nameIdx, occ, bf, res, np.minimum(np.asarray(local, dtype=np.int64), 63), bonded, ridx + 1, labels,
+                   supported, reason)
+
+
+def _typeTables(table, params):
+    """Per distinct RES_ATOM name of a table: radius, electrons, atom type."""
+    types = params["full_atom_name_map_atom_type"]
+    radii = params["radii"]
+    electrons = params["full_atom_name_map_electrons"]
+    t = [types[name] for name in table.names]
+    return (np.array([radii[x] for x in t], dtype=np.float64), np.array([electrons[name] for name in table.names], dtype=np.float64), t)
+
+
+# ---------------------------------------------------------------------------------------------------- statistics
+def _segmentedNanMedian(values, group, nGroups, mask=None):
+    """np.nanmedian(values[group == g]) for every g (NaN for an empty selection): one lexsort for all groups."""
+    values = np.asarray(values, dtype=np.float64)
+    if mask is not None:
+        values, group = values[mask], group[mask]
+    out = np.full(nGroups, np.nan)
+    if len(values) == 0:
+        return out
+    order = np.lexsort((values, group))               # NaN sorts last inside its group
+    v, g = values[order], group[order]
+    valid = np.bincount(g[~np.isnan(v)], minlength=nGroups)
+    start = np.concatenate(([0], np.cumsum(np.bincount(g, minlength=nGroups))))[:-1]
+    has = valid > 0
+    lo = start[has] + (valid[has] - 1) // 2
+    hi = start[has] + valid[has] // 2
+    out[has] = (v[lo] + v[hi]) / 2.0
+    odd = has.copy()
+    odd[has] = (valid[has] % 2) == 1
+    out[odd] = v[start[odd] + valid[odd] // 2]        # the middle element itself for odd counts
+    return out
+
+
+def _segmentedNanStd(values, group, nGroups):
+    """np.nanstd(values[group == g]) for every g (population, ddof 0)."""
+    values = np.asarray(values, dtype=np.float64)
+    ok = ~np.isnan(values)
+    n = np.bincount(group[ok], minlength=nGroups).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean = np.bincount(group[ok], weights=values[ok], minlength=nGroups) / n
+        dev = values[ok] - mean[group[ok]]
+        return np.sqrt(np.bincount(group[ok], weights=dev * dev, minlength=nGroups) / n)
+
+
+def batchAtomTypeStatistics(structure, typeIndex, nTypes, densityElectronRatio, numVoxels, centroidDistance, bfactor, ratio,
+                            unitVolume, currentSlopes):
+    """pdb_eda/densityAnalysis.py:734-766 for all structures of a batch at once.
+
+    Rows = contributing atoms (the reference's ``atomList``), ``structure`` / ``typeIndex`` their structure and atom-type
+    indices; ``ratio`` / ``unitVolume`` per structure; ``currentSlopes`` per type.  Returns (keep mask of the rows that
+    survive the centroid filter, {column: (nStructures, nTypes) array of medians, NaN where a type is absent},
+    present (nStructures, nTypes) bool)."""
+    nS = len(ratio)
+    structure = np.asarray(structure, dtype=np.int64)
+    typeIndex = np.asarray(typeIndex, dtype=np.int64)
+    cd = np.asarray(centroidDistance, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        cutoff = _segmentedNanMedian(cd, structure, nS) + _segmentedNanStd(cd, structure, nS) * 2
+        allNan = np.bincount(structure[~np.isnan(cd)], minlength=nS) == 0          # np.isnan(...).all(): no filter then
+        keep = allNan[structure] | (cd < cutoff[structure])
+    s, t = structure[keep], typeIndex[keep]
+    der = np.asarray(densityElectronRatio, dtype=np.float64)[keep]
+    nv = np.asarray(numVoxels, dtype=np.float64)[keep]
+    cd = cd[keep]
+    bf = np.asarray(bfactor, dtype=np.float64)[keep].copy()
+    g = s * nTypes + t
+    nG = nS * nTypes
+    count = np.bincount(g, minlength=nG)
+    present = (count > 0).reshape(nS, nTypes)
+    med = {}
+    with np.errstate(all="ignore"):
+        med["num_voxels"] = _segmentedNanMedian(nv, g, nG)
+        adj = der / nv * med["num_voxels"][g]
+        volume = nv * np.asarray(unitVolume, dtype=np.float64)[s]
+        med["density_electron_ratio"] = _segmentedNanMedian(der, g, nG)
+        med["centroid_distance"] = _segmentedNanMedian(cd, g, nG)
+        med["adj_density_electron_ratio"] = _segmentedNanMedian(adj, g, nG)
+        med["volume"] = _segmentedNanMedian(volume, g, nG)
+        med["bfactor"] = _segmentedNanMedian(bf, g, nG, mask=bf > 0)
+        low = bf <= 0
+        bf[low] = med["bfactor"][g][low]
+        # slopes: linregress(log(bfactor), (adj - ratio) / ratio) per (structure, type) group
+        r_s = np.asarray(ratio, dtype=np.float64)[s]
+        x = np.log(bf)
+        y = (adj - r_s) / r_s
+        n = count.astype(np.float64)
+        xm = np.bincount(g, weights=x, minlength=nG) / n
+        ym = np.bincount(g, weights=y, minlength=nG) / n
+        dx, dy = x - xm[g], y - ym[g]
+        ssxm = np.bincount(g, weights=dx * dx, minlength=nG) / n
+        ssym = np.bincount(g, weights=dy * dy, minlength=nG) / n
+        ssxym = np.bincount(g, weights=dx * dy, minlength=nG) / n
+        degenerate = (ssxm == 0.0) | (ssym == 0.0)
+        rr = np.where(degenerate, np.where(ssxym == 0, np.nan, 0.0), np.clip(ssxym / np.sqrt(ssxm * ssym), -1.0, 1.0))
+        fitSlope = ssxym / ssxm
+        df = n - 2
+        tt = rr * np.sqrt(df / ((1.0 - rr + 1.0e-20) * (1.0 + rr + 1.0e-20)))
+        prob = 2 * special.stdtr(df, -np.abs(tt))
+        # distinct b-factors per group (NaN counts as one value, like np.unique)
+        order = np.lexsort((bf, g))
+        bs, gs = bf[order], g[order]
+        newValue = np.ones(len(bs), dtype=bool)
+        if len(bs) > 1:
+            same = (gs[1:] == gs[:-1]) & ((bs[1:] == bs[:-1]) | (np.isnan(bs[1:]) & np.isnan(bs[:-1])))
+            newValue[1:] = ~same
+        nUnique = np.bincount(gs[newValue], minlength=nG)
+        current = np.tile(np.asarray(currentSlopes, dtype=np.float64), nS)
+        useCurrent = (count <= 2) | (nUnique == 1) | (prob > 0.05)
+        med["slopes"] = np.where(useCurrent, current, fitSlope)
+        med["slopes"][count == 0] = np.nan
+        domain = (adj - r_s) / r_s
+        corrected = domain - (np.log(bf) - np.log(med["bfactor"][g])) * med["slopes"][g]
+        correctedRatio = corrected * r_s + r_s
+        med["domain_fraction"] = _segmentedNanMedian(domain, g, nG)
+        med["corrected_fraction"] = _segmentedNanMedian(corrected, g, nG)
+        med["corrected_density_electron_ratio"] = _segmentedNanMedian(correctedRatio, g, nG)
+    return keep, {k: v.reshape(nS, nTypes) for k, v in med.items()}, present
+
+
+# ---------------------------------------------------------------------------------------------------- results
+class CloudResult:
+    """What ``analyzePDBID`` / ``processFunction`` read from a DensityAnalysis after ``aggregateCloud``."""
+
+    def __init__(self, pdbid=None):
+        self.pdbid = pdbid
+        self.densityElectronRatio = None
+        self.numVoxelsAggregated = None
+        self.totalAggregatedElectrons = None
+        self.totalAggregatedDensity = None
+        self.numAtomsAnalyzed = 0
+        self.numResidueClouds = 0
+        self.numDomainClouds = 0
+        self.medians = None
+        self.atomTypeOverlapCompleteness = None
+        self.atomTypeOverlapIncompleteness = None
+        self.centroidDistanceCutoff = None
+        self.unitVolume = None
+
+
+class CloudBatch:
+    """A batch of (2Fo-Fc DensityMatrix, AtomTable) pairs laid out for ``pe_cloud_aggregate``; the maps stay where they are
+    in HBM (only pointers are gathered), the atom arrays are uploaded once."""
+
+    def __init__(self, items, params, device=None, pdbids=None):
+        self.items = list(items)
+        self.params = params
+        self.lib = _lib.load()
+        _device.require_cuda()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self.pdbids = list(pdbids) if pdbids is not None else [getattr(dm, "pdbid", None) for dm, _ in self.items]
+        self.atomTypes = sorted(params["radii"])
+        typeOf = {t: k for k, t in enumerate(self.atomTypes)}
+        nS = len(self.items)
+        counts = np.array([len(t) for _, t in self.items], dtype=np.int64)
+        self.atomStart = np.concatenate(([0], np.cumsum(counts)))
+        nA = int(self.atomStart[-1])
+        self.nAtoms, self.nStructures = nA, nS
+        resStart = np.concatenate(([0], np.cumsum([t.nResidues for _, t in self.items])))
+        self.nResidues = int(resStart[-1])
+        xyz = np.empty((nA, 3), dtype=np.float64)
+        radius = np.empty(nA, dtype=np.float32)
+        self.atomMap = np.empty(nA, dtype=np.int32)
+        residue = np.empty(nA, dtype=np.int32)
+        local = np.empty(nA, dtype=np.int32)
+        bonded = np.empty(nA, dtype=np.uint64)
+        self.electrons = np.empty(nA, dtype=np.float64)          # electrons of the atom's RES_ATOM name
+        self.occupancy = np.empty(nA, dtype=np.float64)
+        self.bfactor = np.empty(nA, dtype=np.float64)
+        self.typeIndex = np.empty(nA, dtype=np.int32)
+        maps = (PeBatchMap * max(nS, 1))()
+        self.unitVolume = np.empty(nS, dtype=np.float64)
+        self._keepAlive = []
+        for k, (dm, table) in enumerate(self.items):
+            if not table.supported:
+                raise ValueError("structure %d cannot take the batched path: %s" % (k, table.reason))
+            a0, a1 = int(self.atomStart[k]), int(self.atomStart[k + 1])
+            r, e, tnames = _typeTables(table, params)
+            xyz[a0:a1] = table.coords32                           # float32 widened exactly
+            radius[a0:a1] = r[table.nameIndex].astype(np.float32)
+            self.atomMap[a0:a1] = k
+            residue[a0:a1] = table.residue + resStart[k]
+            local[a0:a1] = table.local
+            bonded[a0:a1] = table.bonded
+            self.electrons[a0:a1] = e[table.nameIndex]
+            self.occupancy[a0:a1] = table.occupancy
+            self.bfactor[a0:a1] = table.bfactor
+            self.typeIndex[a0:a1] = np.array([typeOf[x] for x in tnames], dtype=np.int32)[table.nameIndex] if len(table) else 0
+            dmap = dm.deviceMap
+            self._keepAlive.append(dmap)
+            maps[k].geom = dmap.geom
+            maps[k].d_rho = dmap.rho.data_ptr()
+            maps[k].cutoff = float(np.float32(dm.densityCutoff))
+            maps[k].atom_begin, maps[k].atom_end = a0, a1
+            self.unitVolume[k] = dm.header.unitVolume
+        up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        self.d_maps = torch.frombuffer(bytearray(bytes(maps)), dtype=torch.uint8).to(device)
+        self.d_xyz, self.d_radius, self.d_atomMap = up(xyz), up(radius), up(self.atomMap)
+        self.d_residue, self.d_local = up(residue), up(local)
+        self.d_bonded = up(bonded.view(np.int64))
+        self.d_electrons = up(self.electrons * self.occupancy)
+        self.d_offset = torch.empty(nA + 1, dtype=torch.int32, device=device)
+        self.d_totals = torch.zeros(2, dtype=torch.int64, device=device)
+        self.d_scan = torch.empty(256 + 4 * (nA // 1024 + 4), dtype=torch.uint8, device=device)
+        self.d_atomOut = torch.empty((nA, 8), dtype=torch.float64, device=device)
+        self.d_mapOut = torch.empty((max(nS, 1), 8), dtype=torch.float64, device=device)
+        self.ws = None
+
+    def setRadii(self, params):
+        """New radii / slopes (one optimiser iteration, pdb_eda/optimizeParams.py:417-421); the atoms stay on the device."""
+        self.params = params
+        radius = np.empty(self.nAtoms, dtype=np.float32)
+        for k, (_, table) in enumerate(self.items):
+            a0, a1 = int(self.atomStart[k]), int(self.atomStart[k + 1])
+            radius[a0:a1] = _typeTables(table, params)[0][table.nameIndex].astype(np.float32)
+        self.d_radius.copy_(torch.from_numpy(radius))
+
+    # ---- device part: enqueue, then read back -------------------------------------------------------------------
+    def launch(self, minCloudElectrons=25.0):
+        """Enqueues the whole aggregation; one host synchronisation (the number of cloud voxels sizes the workspace)."""
+        nS, nA = self.nStructures, self.nAtoms
+        if nS == 0:
+            return
+        check(self.lib.pe_cloud_count(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomMap), _ptr(self.d_xyz), _ptr(self.d_radius),
+                                      _ptr(self.d_offset), _ptr(self.d_totals), _ptr(self.d_scan), _stream()), "pe_cloud_count")
+        nEntries, maxBox = self.d_totals.tolist()
+        self.nEntries = int(nEntries)
+        need = int(self.lib.pe_cloud_workspace_bytes(nA, nEntries, self.nResidues))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        check(self.lib.pe_cloud_aggregate(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomMap), _ptr(self.d_xyz), _ptr(self.d_radius),
+                                          _ptr(self.d_residue), _ptr(self.d_local), _ptr(self.d_bonded), _ptr(self.d_electrons),
+                                          self.nResidues, _ptr(self.d_offset), nEntries, max(int(maxBox), 1),
+                                          ctypes.c_double(minCloudElectrons), _ptr(self.d_atomOut), _ptr(self.d_mapOut),
+                                          _ptr(self.ws), _stream()), "pe_cloud_aggregate")
+
+    def collect(self, minTotalElectrons=400.0):
+        """Reads the per-atom / per-structure results back and finishes the statistics on the host -> [CloudResult]."""
+        nS = self.nStructures
+        if nS == 0:
+            return []
+        atomOut = self.d_atomOut.cpu().numpy()
+        mapOut = self.d_mapOut.cpu().numpy()
+        bad = ctypes.c_int32(0)
+        check(self.lib.pe_cloud_status(_ptr(self.ws), _stream(), ctypes.byref(bad)), "pe_cloud_status")
+        if bad.value:
+            raise _lib.PdbEdaLibError("pe_cloud_aggregate: voxel index outside the supported key range or inconsistent counts")
+        return self._finish(atomOut, mapOut, minTotalElectrons)
+
+    def run(self, minCloudElectrons=25.0, minTotalElectrons=400.0):
+        self.launch(minCloudElectrons)
+        return self.collect(minTotalElectrons)
+
+    # ---- host part ------------------------------------------------------------------------------------------------
+    def _finish(self, atomOut, mapOut, minTotalElectrons):
+        nS, nT = self.nStructures, len(self.atomTypes)
+        flags = atomOut[:, 7].astype(np.int64)
+        rows = np.flatnonzero(flags & 1)
+        s = self.atomMap[rows].astype(np.int64)
+        t = self.typeIndex[rows].astype(np.int64)
+        totalElectrons = mapOut[:nS, 2]
+        totalDensity = mapOut[:nS, 1]
+        ok = totalElectrons >= minTotalElectrons                   # :726 -- otherwise aggregateCloud returns nothing
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = totalDensity / totalElectrons
+        slopes = self.params["slopes"]
+        currentSlopes = np.array([slopes.get(x, np.nan) for x in self.atomTypes], dtype=np.float64)
+        der = atomOut[rows, 3] / self.electrons[rows] / self.occupancy[rows]
+        keep, med, present = batchAtomTypeStatistics(s, t, nT, der, atomOut[rows, 1], atomOut[rows, 2], self.bfactor[rows], ratio,
+                                                     self.unitVolume, currentSlopes)
+        analysed = np.bincount(s[keep], minlength=nS)
+        complete = (flags[rows] & 2) != 0
+        nG = nS * nT
+        completeCount = np.bincount((s * nT + t)[complete], minlength=nG).reshape(nS, nT)
+        incompleteCount = np.bincount((s * nT + t)[~complete], minlength=nG).reshape(nS, nT)
+        results = []
+        for k in range(nS):
+            res = CloudResult(self.pdbids[k])
+            res.centroidDistanceCutoff = mapOut[k, 7]
+            res.unitVolume = self.unitVolume[k]
+            if ok[k]:
+                res.densityElectronRatio = float(ratio[k])
+                res.numVoxelsAggregated = int(mapOut[k, 0])
+                res.totalAggregatedElectrons = float(totalElectrons[k])
+                res.totalAggregatedDensity = float(totalDensity[k])
+                res.numAtomsAnalyzed = int(analysed[k])
+                res.numResidueClouds = int(mapOut[k, 6])
+                res.numDomainClouds = int(mapOut[k, 4])
+                cols = np.flatnonzero(present[k])
+                res.medians = {c: {self.atomTypes[j]: med[c][k, j] for j in cols} for c in MEDIAN_COLUMNS}
+                res.atomTypeOverlapCompleteness = collections.defaultdict(
+                    int, {self.atomTypes[j]: int(completeCount[k, j]) for j in np.flatnonzero(completeCount[k])})
+                res.atomTypeOverlapIncompleteness = collections.defaultdict(
+                    int, {self.atomTypes[j]: int(incompleteCount[k, j]) for j in np.flatnonzero(incompleteCount[k])})
+            results.append(res)
+        return results

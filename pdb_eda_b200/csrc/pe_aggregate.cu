@@ -1,0 +1,746 @@
+// pe_aggregate.cu -- cloud aggregation (DensityAnalysis.aggregateCloud, pdb_eda/densityAnalysis.py:571-729) for a BATCH of
+// structures in one sequence of launches: the unit of multiple-structures mode (analyzePDBID,
+// pdb_eda/multipleStructures.py:320-356) and of the optimiser's inner loop (processFunction,
+// pdb_eda/optimizeParams.py:410-448).
+//
+// What the reference does per structure, and what runs here for all structures of the batch at once:
+//   pass 1  every candidate atom's clouds = findAberrantBlobs(atom.coord, radius[type], densityCutoff) (:605):
+//           sphere voxels with rho > cutoff, 26-connected clusters, per cloud sum rho / centroid / size; the atom's
+//           smallest centroid distance (:608)                                   -> cloud_count_kernel, cloud_fill_kernel
+//           centroidDistanceCutoff = nanmedian + 2.5 nanstd per structure (:609) -> cutoff_kernel (radix select)
+//   pass 2  an atom contributes unless it has several clouds and even the nearest centroid is beyond the cutoff
+//           (:623-634); all clouds of a contributing atom join its residue's pool (:638-639)   -> accept_kernel
+//           residue level: clouds of one residue that touch (testOverlap, pdb_eda/cutils.pyx:8-25) are merged; an atom
+//           is "completely overlapped" when it touches every bonded atom of its residue that contributes (:646-659)
+//           domain level: residue clouds that touch are merged (:689-708); a merged cloud is a voxel SET, so the
+//           totals run over each distinct voxel once and over the distinct atoms of the merged cloud (:712-724)
+//                                                      -> one hash table of all pool voxels of the batch (key = structure +
+//                                                         un-wrapped crs), cloud_merge_kernel (two union-finds over cloud
+//                                                         ids + per-atom adjacency bits), cloud_roots_kernel,
+//                                                         cloud_first_kernel, map_summary_kernel
+// The host keeps the per-atom-type statistics (numpy / scipy, pdb_eda/densityAnalysis.py:734-766), vectorised over the
+// batch.  Order-dependent descriptions (which atom names a merged cloud, :717) are not produced here; the single
+// structure API (DensityAnalysis.aggregateCloud) replays those with Python sets.
+//
+// Batch layout: atoms of one structure are contiguous (pe_batch_map::atom_begin/end); every atom carries its structure
+// index, a residue id that is unique over the batch, its index inside the residue (< 64) and the bit mask of its bonded
+// atoms' indices inside the residue.
+#include <math.h>
+#include "pe_sphere_dev.cuh"
+
+namespace pe {
+
+constexpr int kAggThreads = 256;
+constexpr uint64_t kAggEmpty = ~0ull;
+constexpr uint32_t kAggNil = 0xffffffffu;
+constexpr int kKeyBits = 14;                 // per crs axis, offset 2^13: |index| < 8192
+constexpr int kKeyOff = 1 << (kKeyBits - 1);
+
+struct AggTable {
+    unsigned long long *key;
+    uint32_t *head;
+    uint32_t *next;  // per entry
+    int log2cap;
+};
+
+__device__ __forceinline__ uint64_t agg_hash(uint64_t key, int log2cap) { return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2cap); }
+
+__device__ __forceinline__ uint32_t agg_lookup(const AggTable &t, uint64_t key) {
+    const uint64_t mask = (1ull << t.log2cap) - 1;
+    uint64_t h = agg_hash(key, t.log2cap);
+    for (;;) {
+        const unsigned long long k = t.key[h];
+        if (k == key) return t.head[h];
+        if (k == kAggEmpty) return kAggNil;
+        h = (h + 1) & mask;
+    }
+}
+
+// per-warp copy of a structure's geometry in shared memory (the device helpers take it by reference)
+__device__ __forceinline__ void load_geom(pe_geom *dst, const pe_batch_map *m, int lane) {
+    static_assert(sizeof(pe_geom) % 8 == 0 && offsetof(pe_batch_map, geom) == 0, "geometry is copied as 64-bit words");
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&m->geom);
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(dst);
+    for (int k = lane; k < (int)(sizeof(pe_geom) / 8); k += 32) d[k] = src[k];
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ pass 1: counts
+__global__ void __launch_bounds__(kSphereWarps * 32)
+    cloud_count_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
+                       const double *__restrict__ xyz, const float *__restrict__ radius, uint32_t *__restrict__ count,
+                       unsigned long long *__restrict__ d_maxbox) {
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    __shared__ pe_geom geoms[kSphereWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * kSphereWarps + warp;
+    if (a >= n_atoms) return;
+    const pe_batch_map *m = maps + atom_map[a];
+    load_geom(&geoms[warp], m, lane);
+    const pe_geom &g = geoms[warp];
+    const float *rho = m->d_rho;
+    const float cutoff = m->cutoff;
+    const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+    AtomBox b;
+    double T;
+    atom_box(g, ax, ay, az, radius[a], b, T);
+    int n = 0;
+    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane,
+                    [&](int, int, int, bool, float v) { n += passes(v, cutoff) ? 1 : 0; });
+    n = warp_sum(n);
+    if (lane == 0) {
+        count[a] = (uint32_t)n;
+        atomicMax(d_maxbox, (unsigned long long)b.dim[0] * (unsigned long long)b.dim[1] * (unsigned long long)b.dim[2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 1: clouds
+// One warp per atom: membership bitmap in the reference's product order, ordered emission of the voxels (packed key,
+// density, cluster number), in-warp 26-connected clustering (numbered in createCrsLists order) and the per-cloud sums of
+// DensityBlob.fromCrsList (pdb_eda/ccp4.py:522-545).  Per-atom record (8 doubles): number of clouds, voxels of the best
+// cloud, smallest centroid distance, total density of the best cloud, its centroid xyz, [7] is written by later kernels.
+// Dynamic shared memory per warp: bits[nw] | pref[nw] | pidx[maxbox] lab[maxbox] rnk[maxbox] (u16).
+__global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
+                                  const double *__restrict__ xyz, const float *__restrict__ radius,
+                                  const uint32_t *__restrict__ offset, int max_box, unsigned long long *__restrict__ e_key,
+                                  float *__restrict__ e_val, uint32_t *__restrict__ e_atom, uint16_t *__restrict__ e_lab,
+                                  uint32_t *__restrict__ n_clouds, double *__restrict__ atom_out, int *__restrict__ d_bad) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    __shared__ pe_geom geoms[kSphereWarps];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * warps + warp;
+    if (a >= n_atoms) return;
+    const int nw_max = (max_box + 31) / 32;
+    const int box_pad = (max_box + 1) / 2 * 2;
+    const size_t per_warp = (size_t)nw_max * 8 + (size_t)box_pad * 6;
+    unsigned char *base = dyn_smem + per_warp * warp;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(base);
+    uint32_t *pref = bits + nw_max;
+    uint16_t *pidx = reinterpret_cast<uint16_t *>(pref + nw_max);
+    uint16_t *lab = pidx + box_pad;
+    uint16_t *rnk = lab + box_pad;
+
+    const int map_id = atom_map[a];
+    const pe_batch_map *m = maps + map_id;
+    load_geom(&geoms[warp], m, lane);
+    const pe_geom &g = geoms[warp];
+    const float *rho = m->d_rho;
+    const float cutoff = m->cutoff;
+    const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+    AtomBox b;
+    double T;
+    atom_box(g, ax, ay, az, radius[a], b, T);
+    const int D1 = b.dim[1], D2 = b.dim[2];
+    const int vol = b.dim[0] * D1 * D2;
+    double *rec = atom_out + (int64_t)a * 8;
+    if (vol > max_box || vol > 65535) {  // cannot happen: max_box comes from the count pass over the same atoms
+        if (lane == 0) {
+            *d_bad = 1;
+            n_clouds[a] = 0;
+            for (int k = 0; k < 8; ++k) rec[k] = 0.0;
+        }
+        return;
+    }
+    const int nw = (vol + 31) / 32;
+    for (int w = lane; w < nw; w += 32) bits[w] = 0u;
+    __syncwarp();
+    // 1. membership bits in the reference's order: p = (ic*D1 + ir)*D2 + is
+    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
+        if (passes(v, cutoff)) {
+            const int p = (ic * D1 + ir) * D2 + is;
+            atomicOr(bits + (p >> 5), 1u << (p & 31));
+        }
+    });
+    // 2. per-word prefix counts
+    int running = 0;
+    for (int w0 = 0; w0 < nw; w0 += 32) {
+        const int w = w0 + lane;
+        const int cnt = w < nw ? __popc(bits[w]) : 0;
+        const int ex = warp_excl_scan(cnt, lane);
+        if (w < nw) pref[w] = (uint32_t)(running + ex);
+        running += __shfl_sync(kFull, ex + cnt, 31);
+    }
+    __syncwarp();
+    const int n = running;
+    const uint32_t obase = offset[a];
+    if ((uint32_t)n != offset[a + 1] - obase) {  // the two passes must agree
+        if (lane == 0) *d_bad = 1;
+        return;
+    }
+    // 3. ordered list of box positions
+    for (int w = lane; w < nw; w += 32) {
+        uint32_t word = bits[w];
+        int j = (int)pref[w];
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            pidx[j++] = (uint16_t)(w * 32 + bit);
+        }
+    }
+    __syncwarp();
+    // 4. 26-connected clusters of the listed voxels: min-label propagation with pointer jumping
+    for (int j = lane; j < n; j += 32) lab[j] = (uint16_t)j;
+    __syncwarp();
+    for (;;) {
+        bool changed = false;
+        for (int j = lane; j < n; j += 32) {
+            const int p = pidx[j];
+            const int is = p % D2, t = p / D2, ir = t % D1, ic = t / D1;
+            int mn = lab[j];
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int c2 = ic + dc;
+                if (c2 < 0 || c2 >= b.dim[0]) continue;
+                for (int dr = -1; dr <= 1; ++dr) {
+                    const int r2 = ir + dr;
+                    if (r2 < 0 || r2 >= D1) continue;
+                    for (int ds = -1; ds <= 1; ++ds) {
+                        const int s2 = is + ds;
+                        if (s2 < 0 || s2 >= D2) continue;
+                        const int q = (c2 * D1 + r2) * D2 + s2;
+                        const uint32_t word = bits[q >> 5];
+                        if (!((word >> (q & 31)) & 1u)) continue;
+                        const int jn = (int)pref[q >> 5] + __popc(word & ((1u << (q & 31)) - 1u));
+                        mn = min(mn, (int)lab[jn]);
+                    }
+                }
+            }
+            mn = min(mn, (int)lab[mn]);
+            if (mn < (int)lab[j]) {
+                lab[j] = (uint16_t)mn;
+                changed = true;
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(kFull, changed)) break;
+    }
+    // 5. number the clusters by their first member (the order createCrsLists creates them in)
+    int nroots = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const int isroot = (j < n && lab[j] == j) ? 1 : 0;
+        const int ex = warp_excl_scan(isroot, lane);
+        if (isroot) rnk[j] = (uint16_t)(nroots + ex);
+        nroots += __shfl_sync(kFull, ex + isroot, 31);
+    }
+    __syncwarp();
+    // 6. entries: packed key (structure, un-wrapped crs), density, owning atom, cloud number inside the atom
+    bool bad = false;
+    for (int j = lane; j < n; j += 32) {
+        const int p = pidx[j];
+        const int is = p % D2, t = p / D2, ir = t % D1, ic = t / D1;
+        const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+        const unsigned uc = (unsigned)(c + kKeyOff), ur = (unsigned)(r + kKeyOff), us = (unsigned)(s + kKeyOff);
+        // neighbours (+-1) must stay inside the field: 1 <= u < 2^14 - 1
+        if (uc - 1u >= (1u << kKeyBits) - 2u || ur - 1u >= (1u << kKeyBits) - 2u || us - 1u >= (1u << kKeyBits) - 2u) bad = true;
+        const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
+        e_key[obase + j] = ((unsigned long long)(unsigned)map_id << (3 * kKeyBits)) | ((unsigned long long)uc << (2 * kKeyBits)) |
+                           ((unsigned long long)ur << kKeyBits) | (unsigned long long)us;
+        e_val[obase + j] = ((oc | orr | os) >= 0) ? __ldg(rho + (oc + orr + os)) : 0.f;
+        e_atom[obase + j] = (uint32_t)a;
+        e_lab[obase + j] = rnk[lab[j]];
+    }
+    if (__any_sync(kFull, bad) && lane == 0) *d_bad = 1;
+    // 7. per-cloud sums (fromCrsList) -> centroid distance; the nearest cloud (first minimum, :630-634)
+    double best_dist = 0.0, best_sum = 0.0, bcx = 0.0, bcy = 0.0, bcz = 0.0;
+    int best_n = 0;
+    for (int k = 0; k < nroots; ++k) {
+        double sd = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+        int cn = 0;
+        for (int j = lane; j < n; j += 32) {
+            if ((int)rnk[lab[j]] != k) continue;
+            const int p = pidx[j];
+            const int is = p % D2, t = p / D2, ir = t % D1, ic = t / D1;
+            const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+            const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
+            const double d = ((oc | orr | os) >= 0) ? (double)__ldg(rho + (oc + orr + os)) : 0.0;
+            double x, y, z;
+            crs2xyz(g, c, r, s, x, y, z);
+            sd += d;
+            sx += __dmul_rn(d, x);
+            sy += __dmul_rn(d, y);
+            sz += __dmul_rn(d, z);
+            ++cn;
+        }
+        sd = warp_sum(sd);
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        sz = warp_sum(sz);
+        cn = warp_sum(cn);
+        const double cx = sx / sd, cy = sy / sd, cz = sz / sd;
+        const double dx = ax - cx, dy = ay - cy, dz = az - cz;
+        const double dist = sqrt(dx * dx + dy * dy + dz * dz);  // np.linalg.norm(atom.coord - cloud.centroid)
+        if (k == 0 || dist < best_dist) {  // Python's min(): a later value replaces only when strictly smaller
+            best_dist = dist;
+            best_sum = sd;
+            best_n = cn;
+            bcx = cx;
+            bcy = cy;
+            bcz = cz;
+        }
+    }
+    if (lane == 0) {
+        n_clouds[a] = (uint32_t)nroots;
+        rec[0] = (double)nroots;
+        rec[1] = (double)best_n;
+        rec[2] = best_dist;
+        rec[3] = best_sum;
+        rec[4] = bcx;
+        rec[5] = bcy;
+        rec[6] = bcz;
+        rec[7] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ centroid cutoff
+// np.nanmedian(d) + 2.5 * np.nanstd(d) over the smallest centroid distances of a structure's atoms that have clouds
+// (pdb_eda/densityAnalysis.py:608-609).  One CTA per structure; exact order statistics by radix select on the bit
+// patterns (distances are >= 0, so IEEE order is integer order); fixed-order reductions: deterministic.
+__device__ __forceinline__ double block_sum_fixed(double v, double *scratch /* >= blockDim.x / 32 */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += scratch[k];
+    return tot;
+}
+
+__global__ void __launch_bounds__(kAggThreads)
+    cutoff_kernel(const pe_batch_map *__restrict__ maps, const double *__restrict__ atom_out, double *__restrict__ map_out) {
+    __shared__ unsigned int hist[256];
+    __shared__ double scratch[kAggThreads / 32];
+    __shared__ unsigned long long sel_prefix;
+    __shared__ unsigned int sel_rank;
+    const pe_batch_map *m = maps + blockIdx.x;
+    const int a0 = m->atom_begin, a1 = m->atom_end;
+    double *mo = map_out + (int64_t)blockIdx.x * 8;
+    // count and mean of the valid distances
+    double cnt_d = 0.0, sum = 0.0;
+    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+        const double *rec = atom_out + (int64_t)a * 8;
+        if (rec[0] > 0.0 && !isnan(rec[2])) {
+            cnt_d += 1.0;
+            sum += rec[2];
+        }
+    }
+    const double cnt = block_sum_fixed(cnt_d, scratch);
+    sum = block_sum_fixed(sum, scratch);
+    if (cnt == 0.0) {
+        if (threadIdx.x == 0) mo[7] = nan("");
+        return;
+    }
+    const double mean = sum / cnt;
+    double sq = 0.0;
+    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+        const double *rec = atom_out + (int64_t)a * 8;
+        if (rec[0] > 0.0 && !isnan(rec[2])) {
+            const double d = rec[2] - mean;
+            sq += d * d;
+        }
+    }
+    sq = block_sum_fixed(sq, scratch);
+    const double sd = sqrt(sq / cnt);
+    // the two middle order statistics
+    const unsigned int n = (unsigned int)cnt;
+    double mid[2];
+    for (int which = 0; which < 2; ++which) {
+        unsigned int want = which == 0 ? (n - 1) / 2 : n / 2;  // 0-based rank
+        unsigned long long prefix = 0ull;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[k] = 0u;
+            __syncthreads();
+            const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+            for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+                const double *rec = atom_out + (int64_t)a * 8;
+                if (rec[0] > 0.0 && !isnan(rec[2])) {
+                    const unsigned long long bitsv = (unsigned long long)__double_as_longlong(rec[2] + 0.0);  // -0.0 -> 0.0
+                    if ((bitsv & himask) == prefix) atomicAdd(&hist[(bitsv >> shift) & 0xffu], 1u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int acc = 0;
+                int k = 0;
+                for (; k < 256; ++k) {
+                    if (acc + hist[k] > want) break;
+                    acc += hist[k];
+                }
+                sel_prefix = prefix | ((unsigned long long)k << shift);
+                sel_rank = want - acc;
+            }
+            __syncthreads();
+            prefix = sel_prefix;
+            want = sel_rank;
+            __syncthreads();
+        }
+        mid[which] = __longlong_as_double((long long)prefix);
+    }
+    if (threadIdx.x == 0) {
+        const double median = (n & 1u) ? mid[0] : (mid[0] + mid[1]) / 2.0;
+        mo[7] = median + 2.5 * sd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 2: which atoms contribute
+__global__ void __launch_bounds__(kAggThreads)
+    accept_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
+                  const int32_t *__restrict__ atom_residue, const int32_t *__restrict__ atom_local, double *__restrict__ atom_out,
+                  const double *__restrict__ map_out, uint32_t *__restrict__ cloud_count, unsigned long long *__restrict__ res_mask) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > n_atoms) return;
+    if (a == n_atoms) {
+        cloud_count[a] = 0u;  // the scan wants n_atoms + 1 entries
+        return;
+    }
+    double *rec = atom_out + (int64_t)a * 8;
+    const double cutoff = map_out[(int64_t)atom_map[a] * 8 + 7];
+    const int nc = (int)rec[0];
+    const bool ok = nc > 0 && (nc == 1 || !(rec[2] > cutoff));
+    rec[7] = ok ? 1.0 : 0.0;
+    cloud_count[a] = ok ? (uint32_t)nc : 0u;
+    if (ok) atomicOr(res_mask + atom_residue[a], 1ull << atom_local[a]);
+}
+
+// ------------------------------------------------------------------------------------------------ pool voxel table
+__global__ void __launch_bounds__(kAggThreads)
+    pool_insert_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
+                       const double *__restrict__ atom_out, AggTable t) {
+    const uint64_t mask = (1ull << t.log2cap) - 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        t.next[i] = kAggNil;
+        if (atom_out[(int64_t)e_atom[i] * 8 + 7] == 0.0) continue;  // the atom does not contribute
+        const unsigned long long key = e_key[i];
+        uint64_t h = agg_hash(key, t.log2cap);
+        for (;;) {
+            unsigned long long old = t.key[h];
+            if (old == kAggEmpty) old = atomicCAS(t.key + h, (unsigned long long)kAggEmpty, key);
+            if (old == kAggEmpty || old == key) {
+                t.next[i] = atomicExch(t.head + h, (uint32_t)i);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+// Every pool voxel looks at its own position and at 13 of its 26 neighbours (adjacency is symmetric): clouds that share or
+// touch a voxel are united in the domain union-find; clouds of one residue also in the residue union-find, and their atoms
+// mark each other in the per-atom adjacency masks (the overlap matrix of pdb_eda/densityAnalysis.py:646-649 reduced to
+// what the completeness test of :653-659 reads).
+__global__ void __launch_bounds__(kAggThreads)
+    cloud_merge_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
+                       const uint16_t *__restrict__ e_lab, const double *__restrict__ atom_out,
+                       const uint32_t *__restrict__ cloud_start, const int32_t *__restrict__ atom_residue,
+                       const int32_t *__restrict__ atom_local, AggTable t, uint32_t *parent_dom, uint32_t *parent_res,
+                       unsigned long long *adj) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t ai = e_atom[i];
+        if (atom_out[(int64_t)ai * 8 + 7] == 0.0) continue;
+        const unsigned long long key = e_key[i];
+        const uint32_t ci = cloud_start[ai] + e_lab[i];
+        const int ri = atom_residue[ai];
+#pragma unroll 1
+        for (int q = 0; q < 14; ++q) {
+            // q = 0: the voxel itself; q = 1..13: the neighbours that precede it in (c, r, s) order
+            const int p = q - 1;
+            const int dc = q == 0 ? 0 : (p < 9 ? -1 : 0);
+            const int dr = q == 0 ? 0 : (p < 9 ? (p / 3) - 1 : (p < 12 ? -1 : 0));
+            const int ds = q == 0 ? 0 : (p < 9 ? (p % 3) - 1 : (p < 12 ? (p - 9) - 1 : -1));
+            const unsigned long long nk = key + (long long)dc * (1ll << (2 * kKeyBits)) + (long long)dr * (1ll << kKeyBits) + (long long)ds;
+            for (uint32_t j = agg_lookup(t, nk); j != kAggNil; j = t.next[j]) {
+                if (j == (uint32_t)i) continue;
+                const uint32_t aj = e_atom[j];
+                if (aj == ai) continue;  // clouds of one atom are disjoint components: never adjacent
+                const uint32_t cj = cloud_start[aj] + e_lab[j];
+                uf_union(parent_dom, ci, cj);
+                if (atom_residue[aj] == ri) {
+                    uf_union(parent_res, ci, cj);
+                    const unsigned long long bi = 1ull << atom_local[ai], bj = 1ull << atom_local[aj];
+                    if (!(adj[ai] & bj)) atomicOr(adj + ai, bj);
+                    if (!(adj[aj] & bi)) atomicOr(adj + aj, bi);
+                }
+            }
+        }
+    }
+}
+
+// first[i] = 1 iff entry i is the first pool entry of its voxel: the SET semantics of DensityBlob.merge (pdb_eda/ccp4.py:575-586)
+__global__ void __launch_bounds__(kAggThreads)
+    cloud_first_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
+                       const double *__restrict__ atom_out, AggTable t, uint8_t *__restrict__ first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint8_t f = 0;
+        if (atom_out[(int64_t)e_atom[i] * 8 + 7] != 0.0) {
+            uint32_t mn = kAggNil;
+            for (uint32_t j = agg_lookup(t, e_key[i]); j != kAggNil; j = t.next[j]) mn = min(mn, j);
+            f = mn == (uint32_t)i ? 1 : 0;
+        }
+        first[i] = f;
+    }
+}
+
+// Electrons of every merged cloud: the sum over the DISTINCT atoms that have a cloud in it (blob.atoms after merge,
+// pdb_eda/ccp4.py:582).  One thread per contributing atom; the atom's clouds are consecutive ids.
+__global__ void __launch_bounds__(kAggThreads)
+    cloud_roots_kernel(int n_atoms, const double *__restrict__ atom_out, const uint32_t *__restrict__ cloud_start,
+                       const double *__restrict__ atom_electrons, uint32_t *parent_dom, uint32_t *parent_res,
+                       double *elec_dom, double *elec_res) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_atoms) return;
+    if (atom_out[(int64_t)a * 8 + 7] == 0.0) return;
+    const uint32_t c0 = cloud_start[a], c1 = cloud_start[a + 1];
+    const double e = atom_electrons[a];
+    for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t rd = uf_find(parent_dom, c), rr = uf_find(parent_res, c);
+        bool seen_d = false, seen_r = false;
+        for (uint32_t p = c0; p < c; ++p) {  // an earlier cloud of this atom already brought the atom into that merged cloud
+            seen_d |= uf_find(parent_dom, p) == rd;
+            seen_r |= uf_find(parent_res, p) == rr;
+        }
+        if (!seen_d) atomicAdd(elec_dom + rd, e);
+        if (!seen_r) atomicAdd(elec_res + rr, e);
+    }
+}
+
+// Per structure (one CTA each, fixed-order reductions): distinct pool voxels and their density sum (numVoxelsAggregated,
+// totalAggregatedDensity), merged clouds and their electrons (totalAggregatedElectrons; residue / domain clouds with at
+// least min_cloud_electrons, pdb_eda/densityAnalysis.py:681, :722), and the completeness flag of every contributing atom.
+__global__ void __launch_bounds__(kAggThreads)
+    map_summary_kernel(const pe_batch_map *__restrict__ maps, const uint32_t *__restrict__ offset, const float *__restrict__ e_val,
+                       const uint8_t *__restrict__ first, double *__restrict__ atom_out, const uint32_t *__restrict__ cloud_start,
+                       const uint32_t *__restrict__ parent_dom, const uint32_t *__restrict__ parent_res,
+                       const double *__restrict__ elec_dom, const double *__restrict__ elec_res,
+                       const int32_t *__restrict__ atom_residue, const unsigned long long *__restrict__ atom_bonded,
+                       const unsigned long long *__restrict__ adj, const unsigned long long *__restrict__ res_mask,
+                       double min_cloud_electrons, double *__restrict__ map_out) {
+    __shared__ double scratch[kAggThreads / 32];
+    const pe_batch_map *m = maps + blockIdx.x;
+    const int a0 = m->atom_begin, a1 = m->atom_end;
+    double *mo = map_out + (int64_t)blockIdx.x * 8;
+    // voxels
+    double nvox = 0.0, dens = 0.0;
+    for (uint32_t i = offset[a0] + threadIdx.x; i < offset[a1]; i += blockDim.x) {
+        if (first[i]) {
+            nvox += 1.0;
+            dens += (double)e_val[i];
+        }
+    }
+    nvox = block_sum_fixed(nvox, scratch);
+    dens = block_sum_fixed(dens, scratch);
+    // merged clouds
+    double n_dom = 0.0, n_dom_min = 0.0, n_res = 0.0, n_res_min = 0.0, elec = 0.0;
+    for (uint32_t c = cloud_start[a0] + threadIdx.x; c < cloud_start[a1]; c += blockDim.x) {
+        if (parent_dom[c] == c) {  // a root points at itself whether or not the tree below it is flat
+            n_dom += 1.0;
+            elec += elec_dom[c];
+            if (elec_dom[c] >= min_cloud_electrons) n_dom_min += 1.0;
+        }
+        if (parent_res[c] == c) {
+            n_res += 1.0;
+            if (elec_res[c] >= min_cloud_electrons) n_res_min += 1.0;
+        }
+    }
+    n_dom = block_sum_fixed(n_dom, scratch);
+    n_dom_min = block_sum_fixed(n_dom_min, scratch);
+    n_res = block_sum_fixed(n_res, scratch);
+    n_res_min = block_sum_fixed(n_res_min, scratch);
+    elec = block_sum_fixed(elec, scratch);
+    // completeness (:653-659): every bonded atom of the residue that contributes must touch this atom
+    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+        double *rec = atom_out + (int64_t)a * 8;
+        if (rec[7] == 0.0) continue;
+        const unsigned long long need = atom_bonded[a] & res_mask[atom_residue[a]];
+        rec[7] = (need & ~adj[a]) == 0ull ? 3.0 : 1.0;  // bit 0: contributes, bit 1: completely overlapped
+    }
+    if (threadIdx.x == 0) {
+        mo[0] = nvox;
+        mo[1] = dens;
+        mo[2] = elec;
+        mo[3] = n_dom;
+        mo[4] = n_dom_min;
+        mo[5] = n_res;
+        mo[6] = n_res_min;
+    }
+}
+
+__global__ void __launch_bounds__(kAggThreads) iota_kernel(int64_t n, uint32_t *a, uint32_t *b) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        a[i] = (uint32_t)i;
+        b[i] = (uint32_t)i;
+    }
+}
+
+static int agg_log2cap(int64_t n) {
+    int l = 6;
+    while ((1ll << l) < 2 * n + 16) ++l;
+    return l;
+}
+
+static int agg_grid(int64_t n) {
+    int64_t blocks = (n + kAggThreads - 1) / kAggThreads;
+    const int64_t max_blocks = (int64_t)sm_count() * 16;
+    if (blocks < 1) blocks = 1;
+    return (int)(blocks < max_blocks ? blocks : max_blocks);
+}
+
+struct AggLayout {
+    int64_t cloud_count, cloud_start, scan, key, val, atom, lab, next, first, tkey, thead, parent_dom, parent_res, elec_dom,
+        elec_res, adj, res_mask, flags, total;
+};
+
+static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residues) {
+    AggLayout L;
+    int64_t p = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t at = p;
+        p += align_up(bytes > 0 ? bytes : 1, 256);
+        return at;
+    };
+    const int64_t cap = 1ll << agg_log2cap(n_entries);
+    L.flags = take(256);
+    L.cloud_count = take((n_atoms + 1) * 4);
+    L.cloud_start = take((n_atoms + 1) * 4);
+    L.scan = take(scan_ws_bytes(n_atoms + 1));
+    L.key = take(n_entries * 8);
+    L.val = take(n_entries * 4);
+    L.atom = take(n_entries * 4);
+    L.lab = take(n_entries * 2);
+    L.next = take(n_entries * 4);
+    L.first = take(n_entries);
+    L.tkey = take(cap * 8);
+    L.thead = take(cap * 4);
+    L.parent_dom = take(n_entries * 4);
+    L.parent_res = take(n_entries * 4);
+    L.elec_dom = take(n_entries * 8);
+    L.elec_res = take(n_entries * 8);
+    L.adj = take(n_atoms * 8);
+    L.res_mask = take(n_residues * 8);
+    L.total = p;
+    return L;
+}
+
+}  // namespace pe
+
+using namespace pe;
+
+extern "C" {
+
+int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues) {
+    if (n_atoms < 0 || n_entries < 0 || n_residues < 0) return -1;
+    return agg_layout(n_atoms, n_entries, n_residues).total;
+}
+
+int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
+                   const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, void *stream) {
+    PE_CHECK_ARG(n_maps >= 0 && n_atoms >= 0 && d_totals, "pe_cloud_count: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PE_CUDA(cudaMemsetAsync(d_totals, 0, 2 * sizeof(int64_t), st));
+    if (n_atoms == 0) return PE_OK;
+    PE_CHECK_ARG(d_maps && d_atom_map && d_xyz && d_radius && d_offset && d_scan_ws, "pe_cloud_count: null pointer");
+    PE_CHECK_ARG(n_maps < (1 << 20), "pe_cloud_count: at most 2^20 structures per batch");
+    // counts are written into d_offset and scanned in place (n_atoms + 1 entries, the last one zero)
+    PE_CUDA(cudaMemsetAsync(d_offset + n_atoms, 0, sizeof(uint32_t), st));
+    const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
+    PE_LAUNCH("cloud_count_kernel", st, cloud_count_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(
+        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, (unsigned long long *)(d_totals + 1)));
+    PE_LAUNCH_CHECK();
+    return exclusive_scan_u32(d_offset, d_offset, (int64_t)n_atoms + 1, nullptr, d_totals, d_scan_ws, st, false);
+}
+
+int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
+                       const float *d_radius, const int32_t *d_atom_residue, const int32_t *d_atom_local,
+                       const uint64_t *d_atom_bonded, const double *d_atom_electrons, int32_t n_residues, const uint32_t *d_offset,
+                       int64_t n_entries, int32_t max_box_voxels, double min_cloud_electrons, double *d_atom_out, double *d_map_out,
+                       void *d_ws, void *stream) {
+    PE_CHECK_ARG(n_maps >= 0 && n_atoms >= 0 && n_residues >= 0 && n_entries >= 0, "pe_cloud_aggregate: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_maps == 0) return PE_OK;
+    PE_CHECK_ARG(d_maps && d_map_out && d_ws, "pe_cloud_aggregate: null pointer");
+    PE_CUDA(cudaMemsetAsync(d_map_out, 0, (size_t)n_maps * 8 * sizeof(double), st));
+    if (n_atoms == 0) return PE_OK;
+    PE_CHECK_ARG(d_atom_map && d_xyz && d_radius && d_atom_residue && d_atom_local && d_atom_bonded && d_atom_electrons && d_offset &&
+                     d_atom_out,
+                 "pe_cloud_aggregate: null pointer");
+    PE_CHECK_ARG(n_entries < (1ll << 31), "pe_cloud_aggregate: too many cloud voxels in one batch");
+    PE_CHECK_ARG(max_box_voxels > 0 && max_box_voxels <= 16384, "pe_cloud_aggregate: atom boxes of %d voxels are not supported (1..16384)",
+                 max_box_voxels);
+    const AggLayout L = agg_layout(n_atoms, n_entries, n_residues);
+    char *ws = (char *)d_ws;
+    int *d_bad = (int *)(ws + L.flags);
+    uint32_t *cloud_count = (uint32_t *)(ws + L.cloud_count);
+    uint32_t *cloud_start = (uint32_t *)(ws + L.cloud_start);
+    unsigned long long *e_key = (unsigned long long *)(ws + L.key);
+    float *e_val = (float *)(ws + L.val);
+    uint32_t *e_atom = (uint32_t *)(ws + L.atom);
+    uint16_t *e_lab = (uint16_t *)(ws + L.lab);
+    uint8_t *first = (uint8_t *)(ws + L.first);
+    AggTable t;
+    t.log2cap = agg_log2cap(n_entries);
+    t.key = (unsigned long long *)(ws + L.tkey);
+    t.head = (uint32_t *)(ws + L.thead);
+    t.next = (uint32_t *)(ws + L.next);
+    uint32_t *parent_dom = (uint32_t *)(ws + L.parent_dom), *parent_res = (uint32_t *)(ws + L.parent_res);
+    double *elec_dom = (double *)(ws + L.elec_dom), *elec_res = (double *)(ws + L.elec_res);
+    unsigned long long *adj = (unsigned long long *)(ws + L.adj), *res_mask = (unsigned long long *)(ws + L.res_mask);
+    const int64_t cap = 1ll << t.log2cap;
+
+    PE_CUDA(cudaMemsetAsync(d_bad, 0, 256, st));
+    PE_CUDA(cudaMemsetAsync(t.key, 0xff, (size_t)cap * 8, st));
+    PE_CUDA(cudaMemsetAsync(t.head, 0xff, (size_t)cap * 4, st));
+    PE_CUDA(cudaMemsetAsync(elec_dom, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
+    PE_CUDA(cudaMemsetAsync(elec_res, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
+    PE_CUDA(cudaMemsetAsync(adj, 0, (size_t)n_atoms * 8, st));
+    PE_CUDA(cudaMemsetAsync(res_mask, 0, (size_t)(n_residues > 0 ? n_residues : 1) * 8, st));
+
+    // pass 1: clouds of every atom
+    const int nw_max = (max_box_voxels + 31) / 32;
+    const size_t per_warp = (size_t)nw_max * 8 + (size_t)((max_box_voxels + 1) / 2 * 2) * 6;
+    int warps = (int)((size_t)(160 * 1024) / per_warp);
+    if (warps > kSphereWarps) warps = kSphereWarps;
+    PE_CHECK_ARG(warps >= 1, "pe_cloud_aggregate: a box of %d voxels needs %zu bytes of shared memory", max_box_voxels, per_warp);
+    const size_t smem = per_warp * warps;
+    PE_CUDA(cudaFuncSetAttribute(cloud_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PE_LAUNCH("cloud_fill_kernel", st, cloud_fill_kernel<<<(n_atoms + warps - 1) / warps, warps * 32, smem, st>>>(
+        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, max_box_voxels, e_key, e_val, e_atom, e_lab, cloud_count, d_atom_out, d_bad));
+    PE_LAUNCH("cutoff_kernel", st, cutoff_kernel<<<n_maps, kAggThreads, 0, st>>>(d_maps, d_atom_out, d_map_out));
+    // pass 2: contributing atoms, cloud ids
+    PE_LAUNCH("accept_kernel", st, accept_kernel<<<(n_atoms + 1 + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
+        d_maps, n_atoms, d_atom_map, d_atom_residue, d_atom_local, d_atom_out, d_map_out, cloud_count, res_mask));
+    PE_LAUNCH_CHECK();
+    if (int rc = exclusive_scan_u32(cloud_count, cloud_start, (int64_t)n_atoms + 1, nullptr, nullptr, ws + L.scan, st, false)) return rc;
+    if (n_entries > 0) {
+        const int grid = agg_grid(n_entries);
+        PE_LAUNCH("iota_kernel", st, iota_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, parent_dom, parent_res));
+        PE_LAUNCH("pool_insert_kernel", st, pool_insert_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t));
+        PE_LAUNCH("cloud_merge_kernel", st, cloud_merge_kernel<<<grid, kAggThreads, 0, st>>>(
+            n_entries, e_key, e_atom, e_lab, d_atom_out, cloud_start, d_atom_residue, d_atom_local, t, parent_dom, parent_res, adj));
+        PE_LAUNCH("cloud_first_kernel", st, cloud_first_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t, first));
+    }
+    PE_LAUNCH("cloud_roots_kernel", st, cloud_roots_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
+        n_atoms, d_atom_out, cloud_start, d_atom_electrons, parent_dom, parent_res, elec_dom, elec_res));
+    PE_LAUNCH("map_summary_kernel", st, map_summary_kernel<<<n_maps, kAggThreads, 0, st>>>(
+        d_maps, d_offset, e_val, first, d_atom_out, cloud_start, parent_dom, parent_res, elec_dom, elec_res, d_atom_residue,
+        (const unsigned long long *)d_atom_bonded, adj, res_mask, min_cloud_electrons, d_map_out));
+    PE_LAUNCH_CHECK();
+    return PE_OK;
+}
+
+/* Non-zero when the last pe_cloud_aggregate on this workspace met an index outside the key range or an inconsistent
+ * count (synchronises the stream). */
+int pe_cloud_status(const void *d_ws, void *stream, int32_t *bad) {
+    PE_CHECK_ARG(d_ws && bad, "pe_cloud_status: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const AggLayout L = agg_layout(0, 0, 0);
+    PE_CUDA(cudaMemcpyAsync(bad, (const char *)d_ws + L.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PE_CUDA(cudaStreamSynchronize(st));
+    return PE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+"""Batched cloud aggregation (pdb_eda_b200/cloudBatch.py, csrc/pe_aggregate.cu).
+
+CPU tier: the batch-wide statistics block against the per-structure restatement of pdb_eda/densityAnalysis.py:734-766
+(``DensityAnalysis._atomTypeStatistics``, itself checked against the live reference in test_analysis_vs_reference.py).
+GPU tier: ``CloudBatch`` over several structures in ONE batch against the REAL reference's ``aggregateCloud`` run on each
+structure (oracle/_ref on the host CPU): every number ``analyzePDBID`` (pdb_eda/multipleStructures.py:320-356) reads.
+"""
+import io
+
+import numpy as np
+import pytest
+
+import golden_checks as gc
+from pdb_eda_b200 import synthetic
+
+
+def _fake_atoms(rng, n, types):
+    rows = []
+    for k in range(n):
+        t = types[int(rng.integers(len(types)))]
+        bf = float(rng.uniform(5, 60))
+        if rng.random() < 0.08:
+            bf = 0.0 if rng.random() < 0.5 else -1.0
+        cd = float(abs(rng.normal(0.1, 0.05)))
+        if rng.random() < 0.02:
+            cd = float(rng.uniform(1, 2))          # outliers for the centroid filter
+        rows.append(["A", k, "ALA", "X", t, float(rng.uniform(0.3, 0.8)), int(rng.integers(5, 40)), 7, bf, cd, [0.0, 0.0, 0.0]])
+    return rows
+
+
+def test_batch_statistics_match_per_structure():
+    from pdb_eda_b200 import cloudBatch, densityAnalysis
+    params = synthetic.defaultParams()
+    types = sorted(params["radii"])
+    params["slopes"] = {t: 0.01 * (k + 1) for k, t in enumerate(types)}
+    saved = densityAnalysis.paramsGlobal
+    densityAnalysis.setGlobals(params)
+    try:
+        rng = np.random.default_rng(5)
+        sizes = [400, 37, 3, 150, 9, 0, 60]
+        structures = [_fake_atoms(rng, n, types if k != 3 else types[:2]) for k, n in enumerate(sizes)]
+        for row in structures[4]:
+            row[8] = 20.0                              # all b-factors equal: slopes fall back to the current ones
+        structures[4][0][9] = float("nan")
+        ratios = [0.5, 0.45, 0.6, 0.52, 0.4, 0.5, 0.48]
+        vols = [0.125, 0.1, 0.2, 0.125, 0.15, 0.1, 0.11]
+        typeOf = {t: k for k, t in enumerate(types)}
+        s = np.array([k for k, rows in enumerate(structures) for _ in rows])
+        flat = [row for rows in structures for row in rows]
+        keep, med, present = cloudBatch.batchAtomTypeStatistics(
+            s, [typeOf[r[4]] for r in flat], len(types), [r[5] for r in flat], [r[6] for r in flat], [r[9] for r in flat],
+            [r[8] for r in flat], ratios, vols, [params["slopes"][t] for t in types])
+        for k, rows in enumerate(structures):
+            with np.errstate(all="ignore"):
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    atoms, medians = densityAnalysis.DensityAnalysis._atomTypeStatistics([list(r) for r in rows], ratios[k], vols[k])
+            assert len(atoms) == int(keep[s == k].sum())
+            have = {types[j] for j in np.flatnonzero(present[k])}
+            assert have == set(str(t) for t in medians["num_voxels"])
+            for column in cloudBatch.MEDIAN_COLUMNS:
+                for t in medians[column]:
+                    gc.close(med[column][k, typeOf[str(t)]], medians[column][t], rtol=1e-11, atol=1e-12)
+    finally:
+        densityAnalysis.setGlobals(saved)
+
+
+def test_segmented_median_and_std():
+    from pdb_eda_b200 import cloudBatch
+    rng = np.random.default_rng(3)
+    group = rng.integers(0, 7, 500)
+    values = rng.normal(size=500)
+    values[rng.random(500) < 0.1] = np.nan
+    group[group == 5] = 4                              # group 5 is empty
+    med = cloudBatch._segmentedNanMedian(values, group, 8)
+    std = cloudBatch._segmentedNanStd(values, group, 8)
+    for g in range(8):
+        sel = values[group == g]
+        if np.isnan(sel).all():
+            assert np.isnan(med[g])
+            continue
+        assert med[g] == np.nanmedian(sel)
+        gc.close(std[g], np.nanstd(sel), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cloud_batch_matches_the_reference(ref):
+    import test_analysis_vs_reference as tar
+    from pdb_eda_b200 import cloudBatch, densityAnalysis, pdbParser
+    ref_ccp4, ref_da, ref_cutils, ref_pp = ref
+    densityAnalysis.setGlobals(ref_da.paramsGlobal)
+    params = ref_da.paramsGlobal
+    refs, items = [], []
+    for name in tar.CASES:
+        st, d1, d2, pdb_text = tar._build(name)
+        r_dens = ref_ccp4.parse(io.BytesIO(d1), "t")
+        r_dens.densityCutoff = r_dens.meanDensity + 1.5 * r_dens.stdDensity
+        r = ref_da.DensityAnalysis("t", r_dens, None, st, ref_pp.readPDBfile(io.StringIO(pdb_text)))
+        r.aggregateCloud()
+        assert r.densityElectronRatio is not None
+        refs.append(r)
+        m = densityAnalysis.fromFile(io.StringIO(pdb_text), io.BytesIO(d1), io.BytesIO(d2))
+        m.densityObj.densityCutoff = r_dens.densityCutoff
+        table = cloudBatch.AtomTable.fromStructure(m.biopdbObj, params)
+        assert table.supported
+        items.append((m.densityObj, table))
+    # one structure with too few electrons: no result, the others are unaffected (pdb_eda/densityAnalysis.py:726)
+    st, d1, d2, pdb_text = tar._build("p212121")
+    tiny = synthetic.polyAlaStructure(3, (0, 0, 0), (32.0, 32.0, 32.0), seed=5)
+    m = densityAnalysis.fromFile(io.StringIO(__import__("pdb_eda_b200").structure.formatPDB(tiny, cell=tar.CASES["p212121"]["cell"], spaceGroup="P 1")),
+                                 io.BytesIO(d1), io.BytesIO(d2))
+    items.append((m.densityObj, cloudBatch.AtomTable.fromStructure(m.biopdbObj, params)))
+    results = cloudBatch.CloudBatch(items, params).run()
+    assert results[-1].densityElectronRatio is None
+    for r, res in zip(refs, results):
+        assert res.numVoxelsAggregated == r.numVoxelsAggregated
+        gc.close([res.densityElectronRatio, res.totalAggregatedDensity, res.totalAggregatedElectrons],
+                 [r.densityElectronRatio, r.totalAggregatedDensity, r.totalAggregatedElectrons], rtol=1e-9)
+        assert dict(res.atomTypeOverlapCompleteness) == dict(r.atomTypeOverlapCompleteness)
+        assert dict(res.atomTypeOverlapIncompleteness) == dict(r.atomTypeOverlapIncompleteness)
+        assert res.numAtomsAnalyzed == len(r.atomCloudDescriptions)
+        assert res.numResidueClouds == len(r.residueCloudDescriptions)
+        assert res.numDomainClouds == len(r.domainCloudDescriptions)
+        assert set(res.medians) == set(r.medians)
+        for column in r.medians:
+            assert set(res.medians[column]) == set(str(t) for t in r.medians[column])
+            for t in r.medians[column]:
+                gc.close(res.medians[column][str(t)], r.medians[column][t], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_cloud_batch_is_deterministic_and_order_independent(ref):
+    """The same structures in another batch order / alone give identical numbers (no cross-structure leakage)."""
+    import test_analysis_vs_reference as tar
+    from pdb_eda_b200 import cloudBatch, densityAnalysis
+    ref_da = ref[1]
+    densityAnalysis.setGlobals(ref_da.paramsGlobal)
+    params = ref_da.paramsGlobal
+    items = []
+    for name in ("p212121", "perm"):
+        st, d1, d2, pdb_text = tar._build(name)
+        m = densityAnalysis.fromFile(io.StringIO(pdb_text), io.BytesIO(d1), io.BytesIO(d2))
+        items.append((m.densityObj, cloudBatch.AtomTable.fromStructure(m.biopdbObj, params)))
+    both = cloudBatch.CloudBatch(items, params).run()
+    again = cloudBatch.CloudBatch(items, params).run()
+    swapped = cloudBatch.CloudBatch(items[::-1], params).run()[::-1]
+    alone = [cloudBatch.CloudBatch([it], params).run()[0] for it in items]
+    for a, others in zip(both, zip(again, swapped, alone)):
+        for b in others:
+            assert (a.numVoxelsAggregated, a.totalAggregatedDensity, a.totalAggregatedElectrons, a.numAtomsAnalyzed, a.numDomainClouds) == \
+                   (b.numVoxelsAggregated, b.totalAggregatedDensity, b.totalAggregatedElectrons, b.numAtomsAnalyzed, b.numDomainClouds)
