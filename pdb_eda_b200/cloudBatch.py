@@ -5,9 +5,11 @@ and the optimiser's ``processFunction`` (pdb_eda/optimizeParams.py:410-448) both
 (pdb_eda/densityAnalysis.py:571-780) plus a handful of per-structure numbers.  Here the atoms of MANY structures are
 laid out as one set of arrays (atoms of a structure contiguous, one ``pe_batch_map`` per structure) and the whole
 aggregation -- per-atom clouds, centroid cutoff, residue / domain merging, completeness counters -- runs as one sequence
-of CUDA launches over the batch (``pe_cloud_count`` + ``pe_cloud_aggregate``, csrc/pe_aggregate.cu); the per-atom-type
-statistics block (pdb_eda/densityAnalysis.py:734-766) is numpy over the batch, one sort per median instead of a Python
-loop per structure and atom type.
+of CUDA launches over the batch (``pe_cloud_count`` + ``pe_cloud_aggregate``, csrc/pe_aggregate.cu), followed by the
+per-atom-type statistics block (pdb_eda/densityAnalysis.py:734-766) as one more kernel (``pe_cloud_statistics``,
+csrc/pe_cloudstats.cu: exact medians by radix select, the b-factor regression with its p-value test).  The host reads back
+a few numbers per structure and per (structure, atom type).  ``batchAtomTypeStatistics`` is the numpy statement of the
+same block over a batch; the tests hold the kernel against it and it against the per-structure code.
 
 What this path does not produce are the order-dependent descriptions of merged clouds (the atom that names a domain
 cloud depends on Python set iteration order, pdb_eda/densityAnalysis.py:717); ``DensityAnalysis.aggregateCloud`` keeps
@@ -250,6 +252,16 @@ class CloudResult:
         self.unitVolume = None
 
 
+class MapRef:
+    """The part of a 2Fo-Fc ``DensityMatrix`` the batch needs, for maps that only exist on the device (synthetic pools)."""
+
+    def __init__(self, deviceMap, densityCutoff, unitVolume, pdbid=None):
+        self.deviceMap = deviceMap
+        self.densityCutoff = densityCutoff
+        self.unitVolume = unitVolume
+        self.pdbid = pdbid
+
+
 class CloudBatch:
     """A batch of (2Fo-Fc DensityMatrix, AtomTable) pairs laid out for ``pe_cloud_aggregate``; the maps stay where they are
     in HBM (only pointers are gathered), the atom arrays are uploaded once."""
@@ -306,19 +318,44 @@ class CloudBatch:
             maps[k].d_rho = dmap.rho.data_ptr()
             maps[k].cutoff = float(np.float32(dm.densityCutoff))
             maps[k].atom_begin, maps[k].atom_end = a0, a1
-            self.unitVolume[k] = dm.header.unitVolume
+            self.unitVolume[k] = dm.unitVolume if isinstance(dm, MapRef) else dm.header.unitVolume
+        # atoms type by type inside every structure: the (structure, type) groups of the statistics block are segments
+        perm = np.lexsort((self.typeIndex, self.atomMap)).astype(np.int32)
+        gkey = self.atomMap[perm].astype(np.int64) * len(self.atomTypes) + self.typeIndex[perm]
+        edge = np.flatnonzero(np.concatenate(([True], gkey[1:] != gkey[:-1]))) if nA else np.zeros(0, dtype=np.int64)
+        self.segBegin = edge.astype(np.int32)
+        self.segEnd = np.concatenate((edge[1:], [nA])).astype(np.int32) if nA else np.zeros(0, dtype=np.int32)
+        self.segMap = (gkey[edge] // len(self.atomTypes)).astype(np.int32) if nA else np.zeros(0, dtype=np.int32)
+        self.segType = (gkey[edge] % len(self.atomTypes)).astype(np.int32) if nA else np.zeros(0, dtype=np.int32)
+        self.nSegments = len(self.segBegin)
+        self.mapSegPtr = np.searchsorted(self.segMap, np.arange(nS + 1)).astype(np.int32)
         up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(device)
         self.d_maps = torch.frombuffer(bytearray(bytes(maps)), dtype=torch.uint8).to(device)
         self.d_xyz, self.d_radius, self.d_atomMap = up(xyz), up(radius), up(self.atomMap)
         self.d_residue, self.d_local = up(residue), up(local)
         self.d_bonded = up(bonded.view(np.int64))
         self.d_electrons = up(self.electrons * self.occupancy)
+        self.d_static = up(np.stack((self.electrons, self.occupancy, self.bfactor), axis=1))
+        self.d_perm, self.d_mapSegPtr = up(perm), up(self.mapSegPtr)
+        self.d_segType, self.d_segBegin, self.d_segEnd = up(self.segType), up(self.segBegin), up(self.segEnd)
+        self.d_unitVolume = up(self.unitVolume)
+        self.d_slopes = up(self._currentSlopes(params))
         self.d_offset = torch.empty(nA + 1, dtype=torch.int32, device=device)
         self.d_totals = torch.zeros(2, dtype=torch.int64, device=device)
         self.d_scan = torch.empty(256 + 4 * (nA // 1024 + 4), dtype=torch.uint8, device=device)
         self.d_atomOut = torch.empty((nA, 8), dtype=torch.float64, device=device)
         self.d_mapOut = torch.empty((max(nS, 1), 8), dtype=torch.float64, device=device)
+        self.d_scratch = torch.empty((max(nA, 1), 6), dtype=torch.float64, device=device)
+        self.d_segOut = torch.empty((max(self.nSegments, 1), 14), dtype=torch.float64, device=device)
+        self.d_mapStats = torch.empty((max(nS, 1), 4), dtype=torch.float64, device=device)
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        self.h_mapOut, self.h_segOut, self.h_mapStats = pin(self.d_mapOut), pin(self.d_segOut), pin(self.d_mapStats)
         self.ws = None
+        self.nEntries = 0
+
+    def _currentSlopes(self, params):
+        slopes = params["slopes"]
+        return np.array([slopes.get(x, np.nan) for x in self.atomTypes], dtype=np.float64)
 
     def setRadii(self, params):
         """New radii / slopes (one optimiser iteration, pdb_eda/optimizeParams.py:417-421); the atoms stay on the device."""
@@ -328,10 +365,12 @@ class CloudBatch:
             a0, a1 = int(self.atomStart[k]), int(self.atomStart[k + 1])
             radius[a0:a1] = _typeTables(table, params)[0][table.nameIndex].astype(np.float32)
         self.d_radius.copy_(torch.from_numpy(radius))
+        self.d_slopes.copy_(torch.from_numpy(self._currentSlopes(params)))
 
     # ---- device part: enqueue, then read back -------------------------------------------------------------------
-    def launch(self, minCloudElectrons=25.0):
-        """Enqueues the whole aggregation; one host synchronisation (the number of cloud voxels sizes the workspace)."""
+    def launch(self, minCloudElectrons=25.0, minTotalElectrons=400.0):
+        """Enqueues the whole aggregation and the statistics; one host synchronisation in between (the number of cloud
+        voxels of the batch sizes the workspace), then asynchronous copies of the small result tables to pinned memory."""
         nS, nA = self.nStructures, self.nAtoms
         if nS == 0:
             return
@@ -347,64 +386,79 @@ class CloudBatch:
                                           self.nResidues, _ptr(self.d_offset), nEntries, max(int(maxBox), 1),
                                           ctypes.c_double(minCloudElectrons), _ptr(self.d_atomOut), _ptr(self.d_mapOut),
                                           _ptr(self.ws), _stream()), "pe_cloud_aggregate")
+        check(self.lib.pe_cloud_statistics(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomOut), _ptr(self.d_mapOut), _ptr(self.d_static),
+                                           _ptr(self.d_perm), _ptr(self.d_mapSegPtr), self.nSegments, _ptr(self.d_segType),
+                                           _ptr(self.d_segBegin), _ptr(self.d_segEnd), _ptr(self.d_unitVolume), _ptr(self.d_slopes),
+                                           ctypes.c_double(minTotalElectrons), _ptr(self.d_scratch), _ptr(self.d_segOut),
+                                           _ptr(self.d_mapStats), _stream()), "pe_cloud_statistics")
+        self.h_mapOut.copy_(self.d_mapOut, non_blocking=True)
+        self.h_segOut.copy_(self.d_segOut, non_blocking=True)
+        self.h_mapStats.copy_(self.d_mapStats, non_blocking=True)
 
-    def collect(self, minTotalElectrons=400.0):
-        """Reads the per-atom / per-structure results back and finishes the statistics on the host -> [CloudResult]."""
-        nS = self.nStructures
-        if nS == 0:
-            return []
-        atomOut = self.d_atomOut.cpu().numpy()
-        mapOut = self.d_mapOut.cpu().numpy()
+    def collectArrays(self):
+        """Synchronises and returns the batch's results as arrays: per structure ``ok`` (enough electrons, :726), ``ratio``,
+        ``numVoxels``, ``totalElectrons``, ``totalDensity``, ``analysed`` (len(atomCloudDescriptions)), ``residueClouds`` /
+        ``domainClouds`` (those with >= minCloudElectrons); per (structure, atom type) ``present``, ``medians[column]``,
+        ``complete`` / ``incomplete`` (the overlap completeness counters, :653-659)."""
+        nS, nT = self.nStructures, len(self.atomTypes)
         bad = ctypes.c_int32(0)
-        check(self.lib.pe_cloud_status(_ptr(self.ws), _stream(), ctypes.byref(bad)), "pe_cloud_status")
+        if nS and self.nAtoms:
+            check(self.lib.pe_cloud_status(_ptr(self.ws), _stream(), ctypes.byref(bad)), "pe_cloud_status")
+        else:
+            torch.cuda.current_stream().synchronize()
         if bad.value:
             raise _lib.PdbEdaLibError("pe_cloud_aggregate: voxel index outside the supported key range or inconsistent counts")
-        return self._finish(atomOut, mapOut, minTotalElectrons)
+        mapOut = self.h_mapOut.numpy()[:nS]
+        mapStats = self.h_mapStats.numpy()[:nS]
+        seg = self.h_segOut.numpy()[:self.nSegments]
+        ok = mapStats[:, 3] != 0
+        out = {"ok": ok, "ratio": mapStats[:, 1].copy(), "numVoxels": mapOut[:, 0].copy(), "totalDensity": mapOut[:, 1].copy(),
+               "totalElectrons": mapOut[:, 2].copy(), "analysed": mapStats[:, 0].copy(), "domainClouds": mapOut[:, 4].copy(),
+               "residueClouds": mapOut[:, 6].copy(), "centroidCutoff": mapOut[:, 7].copy(), "unitVolume": self.unitVolume}
+        sm, stp = self.segMap, self.segType
+        present = np.zeros((nS, nT), dtype=bool)
+        present[sm, stp] = (seg[:, 0] > 0) & ok[sm]
+        medians = {}
+        for j, column in enumerate(MEDIAN_COLUMNS):
+            table = np.full((nS, nT), np.nan)
+            table[sm, stp] = seg[:, 1 + j]
+            medians[column] = table
+        complete = np.zeros((nS, nT), dtype=np.int64)
+        incomplete = np.zeros((nS, nT), dtype=np.int64)
+        complete[sm, stp] = seg[:, 12].astype(np.int64)
+        incomplete[sm, stp] = (seg[:, 11] - seg[:, 12]).astype(np.int64)
+        out.update(present=present, medians=medians, complete=complete, incomplete=incomplete)
+        return out
 
-    def run(self, minCloudElectrons=25.0, minTotalElectrons=400.0):
-        self.launch(minCloudElectrons)
-        return self.collect(minTotalElectrons)
-
-    # ---- host part ------------------------------------------------------------------------------------------------
-    def _finish(self, atomOut, mapOut, minTotalElectrons):
-        nS, nT = self.nStructures, len(self.atomTypes)
-        flags = atomOut[:, 7].astype(np.int64)
-        rows = np.flatnonzero(flags & 1)
-        s = self.atomMap[rows].astype(np.int64)
-        t = self.typeIndex[rows].astype(np.int64)
-        totalElectrons = mapOut[:nS, 2]
-        totalDensity = mapOut[:nS, 1]
-        ok = totalElectrons >= minTotalElectrons                   # :726 -- otherwise aggregateCloud returns nothing
-        with np.errstate(divide="ignore", invalid="ignore"):
-            ratio = totalDensity / totalElectrons
-        slopes = self.params["slopes"]
-        currentSlopes = np.array([slopes.get(x, np.nan) for x in self.atomTypes], dtype=np.float64)
-        der = atomOut[rows, 3] / self.electrons[rows] / self.occupancy[rows]
-        keep, med, present = batchAtomTypeStatistics(s, t, nT, der, atomOut[rows, 1], atomOut[rows, 2], self.bfactor[rows], ratio,
-                                                     self.unitVolume, currentSlopes)
-        analysed = np.bincount(s[keep], minlength=nS)
-        complete = (flags[rows] & 2) != 0
-        nG = nS * nT
-        completeCount = np.bincount((s * nT + t)[complete], minlength=nG).reshape(nS, nT)
-        incompleteCount = np.bincount((s * nT + t)[~complete], minlength=nG).reshape(nS, nT)
+    def collect(self):
+        """The same as objects, one ``CloudResult`` per structure (all fields None-like below minTotalElectrons)."""
+        arr = self.collectArrays()
         results = []
-        for k in range(nS):
+        for k in range(self.nStructures):
             res = CloudResult(self.pdbids[k])
-            res.centroidDistanceCutoff = mapOut[k, 7]
+            res.centroidDistanceCutoff = arr["centroidCutoff"][k]
             res.unitVolume = self.unitVolume[k]
-            if ok[k]:
-                res.densityElectronRatio = float(ratio[k])
-                res.numVoxelsAggregated = int(mapOut[k, 0])
-                res.totalAggregatedElectrons = float(totalElectrons[k])
-                res.totalAggregatedDensity = float(totalDensity[k])
-                res.numAtomsAnalyzed = int(analysed[k])
-                res.numResidueClouds = int(mapOut[k, 6])
-                res.numDomainClouds = int(mapOut[k, 4])
-                cols = np.flatnonzero(present[k])
-                res.medians = {c: {self.atomTypes[j]: med[c][k, j] for j in cols} for c in MEDIAN_COLUMNS}
+            if arr["ok"][k]:
+                res.densityElectronRatio = float(arr["ratio"][k])
+                res.numVoxelsAggregated = int(arr["numVoxels"][k])
+                res.totalAggregatedElectrons = float(arr["totalElectrons"][k])
+                res.totalAggregatedDensity = float(arr["totalDensity"][k])
+                res.numAtomsAnalyzed = int(arr["analysed"][k])
+                res.numResidueClouds = int(arr["residueClouds"][k])
+                res.numDomainClouds = int(arr["domainClouds"][k])
+                cols = np.flatnonzero(arr["present"][k])
+                res.medians = {c: {self.atomTypes[j]: arr["medians"][c][k, j] for j in cols} for c in MEDIAN_COLUMNS}
                 res.atomTypeOverlapCompleteness = collections.defaultdict(
-                    int, {self.atomTypes[j]: int(completeCount[k, j]) for j in np.flatnonzero(completeCount[k])})
+                    int, {self.atomTypes[j]: int(arr["complete"][k, j]) for j in np.flatnonzero(arr["complete"][k])})
                 res.atomTypeOverlapIncompleteness = collections.defaultdict(
-                    int, {self.atomTypes[j]: int(incompleteCount[k, j]) for j in np.flatnonzero(incompleteCount[k])})
+                    int, {self.atomTypes[j]: int(arr["incomplete"][k, j]) for j in np.flatnonzero(arr["incomplete"][k])})
             results.append(res)
         return results
+
+    def run(self, minCloudElectrons=25.0, minTotalElectrons=400.0):
+        self.launch(minCloudElectrons, minTotalElectrons)
+        return self.collect()
+
+    def atomRows(self):
+        """Device -> host read of the per-atom records (n_atoms x 8, see ``pe_cloud_aggregate``)."""
+        return self.d_atomOut.cpu().numpy()

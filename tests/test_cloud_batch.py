@@ -150,3 +150,81 @@ def test_cloud_batch_is_deterministic_and_order_independent(ref):
         for b in others:
             assert (a.numVoxelsAggregated, a.totalAggregatedDensity, a.totalAggregatedElectrons, a.numAtomsAnalyzed, a.numDomainClouds) == \
                    (b.numVoxelsAggregated, b.totalAggregatedDensity, b.totalAggregatedElectrons, b.numAtomsAnalyzed, b.numDomainClouds)
+
+
+@pytest.mark.gpu
+def test_statistics_kernel_matches_the_numpy_statement():
+    """pe_cloud_statistics on hand-made per-atom records (b-factors <= 0, types with one or two atoms, equal b-factors, NaN
+    and outlying centroid distances, a structure below minTotalElectrons) against batchAtomTypeStatistics."""
+    import ctypes
+    import torch
+    from pdb_eda_b200 import cloudBatch, _lib
+    from pdb_eda_b200._device import _ptr, _stream
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    nT = 6
+    sizes = [700, 41, 3, 2500, 12, 0, 90, 260]
+    slopes = np.array([0.01 * (k + 1) for k in range(nT)])
+    atomMap, typeIndex, recs, static = [], [], [], []
+    for k, n in enumerate(sizes):
+        for _ in range(n):
+            t = int(rng.integers(nT if k != 3 else 2))
+            bf = float(rng.uniform(5, 60)) if k != 4 else 20.0
+            if rng.random() < 0.08 and k != 4:
+                bf = 0.0 if rng.random() < 0.5 else -1.0
+            cd = float(abs(rng.normal(0.1, 0.05)))
+            if rng.random() < 0.02:
+                cd = float(rng.uniform(1, 2)) if rng.random() < 0.7 else float("nan")
+            acc = rng.random() < 0.9
+            recs.append([1.0, float(rng.integers(5, 40)), cd, float(rng.uniform(2, 7)), 0, 0, 0, (3.0 if rng.random() < 0.6 else 1.0) if acc else 0.0])
+            static.append([float(rng.integers(6, 9)), float(rng.choice([1.0, 0.5, 0.37])), bf])
+            atomMap.append(k)
+            typeIndex.append(t)
+    atomMap, typeIndex = np.array(atomMap, dtype=np.int32), np.array(typeIndex, dtype=np.int32)
+    recs, static = np.array(recs), np.array(static)
+    nS, nA = len(sizes), len(atomMap)
+    start = np.concatenate(([0], np.cumsum(sizes)))
+    maps = (cloudBatch.PeBatchMap * nS)()
+    for k in range(nS):
+        maps[k].atom_begin, maps[k].atom_end = int(start[k]), int(start[k + 1])
+    mapOut = np.zeros((nS, 8))
+    mapOut[:, 1] = rng.uniform(400, 600, nS)
+    mapOut[:, 2] = rng.uniform(900, 1100, nS)
+    mapOut[6, 2] = 100.0                                   # below minTotalElectrons
+    unitVolume = rng.uniform(0.1, 0.2, nS)
+    perm = np.lexsort((typeIndex, atomMap)).astype(np.int32)
+    gkey = atomMap[perm].astype(np.int64) * nT + typeIndex[perm]
+    edge = np.flatnonzero(np.concatenate(([True], gkey[1:] != gkey[:-1])))
+    segBegin, segEnd = edge.astype(np.int32), np.concatenate((edge[1:], [nA])).astype(np.int32)
+    segMap, segType = (gkey[edge] // nT).astype(np.int32), (gkey[edge] % nT).astype(np.int32)
+    mapSegPtr = np.searchsorted(segMap, np.arange(nS + 1)).astype(np.int32)
+    dev = "cuda"
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = dict(maps=torch.frombuffer(bytearray(bytes(maps)), dtype=torch.uint8).to(dev), recs=up(recs), mapOut=up(mapOut), static=up(static),
+             perm=up(perm), ptr=up(mapSegPtr), st=up(segType), sb=up(segBegin), se=up(segEnd), uv=up(unitVolume), sl=up(slopes))
+    scratch = torch.empty((nA, 6), dtype=torch.float64, device=dev)
+    segOut = torch.empty((len(segBegin), 14), dtype=torch.float64, device=dev)
+    mapStats = torch.empty((nS, 4), dtype=torch.float64, device=dev)
+    _lib.check(lib.pe_cloud_statistics(nS, _ptr(d["maps"]), nA, _ptr(d["recs"]), _ptr(d["mapOut"]), _ptr(d["static"]), _ptr(d["perm"]),
+                                       _ptr(d["ptr"]), len(segBegin), _ptr(d["st"]), _ptr(d["sb"]), _ptr(d["se"]), _ptr(d["uv"]), _ptr(d["sl"]),
+                                       ctypes.c_double(400.0), _ptr(scratch), _ptr(segOut), _ptr(mapStats), _stream()), "pe_cloud_statistics")
+    segOut, mapStats = segOut.cpu().numpy(), mapStats.cpu().numpy()
+    rows = np.flatnonzero(recs[:, 7].astype(int) & 1)
+    ratio = mapOut[:, 1] / mapOut[:, 2]
+    der = recs[rows, 3] / static[rows, 0] / static[rows, 1]
+    keep, med, present = cloudBatch.batchAtomTypeStatistics(atomMap[rows], typeIndex[rows], nT, der, recs[rows, 1], recs[rows, 2],
+                                                            static[rows, 2], ratio, unitVolume, slopes)
+    ok = mapOut[:, 2] >= 400.0
+    analysed = np.bincount(atomMap[rows][keep], minlength=nS)
+    assert np.array_equal(mapStats[:, 0], np.where(ok, analysed, 0))
+    gc.close(mapStats[ok, 1], ratio[ok], rtol=1e-15)
+    for s_ in range(len(segBegin)):
+        k, t = int(segMap[s_]), int(segType[s_])
+        sel = (atomMap == k) & (typeIndex == t)
+        assert segOut[s_, 11] == (recs[sel, 7].astype(int) & 1).sum() and segOut[s_, 12] == ((recs[sel, 7].astype(int) >> 1) & 1).sum()
+        if not ok[k] or not present[k, t]:
+            assert segOut[s_, 0] == 0
+            continue
+        assert segOut[s_, 0] == (keep & (atomMap[rows] == k) & (typeIndex[rows] == t)).sum()
+        for j, column in enumerate(cloudBatch.MEDIAN_COLUMNS):
+            gc.close(segOut[s_, 1 + j], med[column][k, t], rtol=1e-10, atol=1e-12)
