@@ -264,16 +264,15 @@ int pe_cloud_status(const void *d_ws, void *stream, int32_t *bad);
  * num_voxels, density_electron_ratio, centroid_distance, adj_density_electron_ratio, volume, bfactor (> 0), the b-factor slope
  * (scipy.stats.linregress with its p-value test, :729-733), domain_fraction, corrected_fraction and
  * corrected_density_electron_ratio.  d_perm lists the batch's atoms structure by structure and, inside a structure, atom type
- * by atom type; segment s (d_seg_begin[s] .. d_seg_end[s] into d_perm) holds the atoms of type d_seg_type[s] of one structure,
- * d_map_seg_ptr (n_maps + 1) the segments of each structure.  d_atom_static: n_atoms x 3 (electrons, occupancy, bfactor).
+ * by atom type; segment s (d_seg_begin[s] .. d_seg_end[s] into d_perm, at most max_segment long) holds the atoms of type
+ * d_seg_type[s] of structure d_seg_map[s].  d_atom_static: n_atoms x 3 (electrons, occupancy, bfactor).
  * Outputs: d_seg_out[s*14..] = kept rows, the ten values above in that order, contributing atoms of the type, those completely
- * overlapped (pdb_eda/densityAnalysis.py:653-659), spare; d_map_stats[m*4..] = atoms analysed
- * (len(atomCloudDescriptions)), densityElectronRatio (NaN below min_total_electrons, :726), the centroid cutoff, ok flag.
- * d_scratch: n_atoms x 6 float64. */
+ * overlapped (pdb_eda/densityAnalysis.py:653-659), spare; d_map_stats[m*4..] = atoms analysed (len(atomCloudDescriptions)),
+ * densityElectronRatio (NaN below min_total_electrons, :726), the centroid cutoff, ok flag.  d_scratch: 9 x n_atoms float64. */
 int pe_cloud_statistics(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const double *d_atom_out,
-                        const double *d_map_out, const double *d_atom_static, const int32_t *d_perm,
-                        const int32_t *d_map_seg_ptr, int32_t n_segments, const int32_t *d_seg_type,
-                        const int32_t *d_seg_begin, const int32_t *d_seg_end, const double *d_unit_volume,
+                        const double *d_map_out, const double *d_atom_static, const int32_t *d_perm, int32_t n_segments,
+                        const int32_t *d_seg_map, const int32_t *d_seg_type, const int32_t *d_seg_begin,
+                        const int32_t *d_seg_end, int32_t max_segment, const double *d_unit_volume,
                         const double *d_current_slopes, double min_total_electrons, double *d_scratch, double *d_seg_out,
                         double *d_map_stats, void *stream);
 

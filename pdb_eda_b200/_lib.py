@@ -83,7 +83,8 @@ SIGNATURES = {
     "pe_cloud_aggregate": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, ctypes.c_double, _P, _P,
                                           _P, _P]),
     "pe_cloud_status": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32)]),
-    "pe_cloud_statistics": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, ctypes.c_double, _P, _P, _P, _P]),
+    "pe_cloud_statistics": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, ctypes.c_double, _P, _P,
+                                           _P, _P]),
 }
 
 _lib = None

@@ -108,10 +108,16 @@ class AtomTable:
                     mask |= 1 << j
             bonded[k] = mask
         coords32 = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
-        if n and len(np.unique(coords32 + np.float32(0.0), axis=0)) < n:
+        if n and _distinctRows(coords32) < n:
             supported, reason = False, "atoms with identical coordinates share one cloud entry"
         return cls(coords32, names, nameIdx, occ, bf, res, np.minimum(np.asarray(local, dtype=np.int64), 63), bonded, ridx + 1, labels,
                    supported, reason)
+
+
+def _distinctRows(coords32):
+    """Number of distinct coordinate triples (-0.0 and 0.0 are one key, like the tuple keys of pdb_eda/densityAnalysis.py:606)."""
+    rows = np.ascontiguousarray(np.asarray(coords32, dtype=np.float32) + np.float32(0.0))
+    return len(np.unique(rows.view(np.dtype((np.void, 12))).ravel()))
 
 
 def _typeTables(table, params):
@@ -328,7 +334,7 @@ class CloudBatch:
         self.segMap = (gkey[edge] // len(self.atomTypes)).astype(np.int32) if nA else np.zeros(0, dtype=np.int32)
         self.segType = (gkey[edge] % len(self.atomTypes)).astype(np.int32) if nA else np.zeros(0, dtype=np.int32)
         self.nSegments = len(self.segBegin)
-        self.mapSegPtr = np.searchsorted(self.segMap, np.arange(nS + 1)).astype(np.int32)
+        self.maxSegment = int((self.segEnd - self.segBegin).max()) if self.nSegments else 0
         up = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(device)
         self.d_maps = torch.frombuffer(bytearray(bytes(maps)), dtype=torch.uint8).to(device)
         self.d_xyz, self.d_radius, self.d_atomMap = up(xyz), up(radius), up(self.atomMap)
@@ -336,7 +342,7 @@ class CloudBatch:
         self.d_bonded = up(bonded.view(np.int64))
         self.d_electrons = up(self.electrons * self.occupancy)
         self.d_static = up(np.stack((self.electrons, self.occupancy, self.bfactor), axis=1))
-        self.d_perm, self.d_mapSegPtr = up(perm), up(self.mapSegPtr)
+        self.d_perm, self.d_segMap = up(perm), up(self.segMap)
         self.d_segType, self.d_segBegin, self.d_segEnd = up(self.segType), up(self.segBegin), up(self.segEnd)
         self.d_unitVolume = up(self.unitVolume)
         self.d_slopes = up(self._currentSlopes(params))
@@ -345,7 +351,7 @@ class CloudBatch:
         self.d_scan = torch.empty(256 + 4 * (nA // 1024 + 4), dtype=torch.uint8, device=device)
         self.d_atomOut = torch.empty((nA, 8), dtype=torch.float64, device=device)
         self.d_mapOut = torch.empty((max(nS, 1), 8), dtype=torch.float64, device=device)
-        self.d_scratch = torch.empty((max(nA, 1), 6), dtype=torch.float64, device=device)
+        self.d_scratch = torch.empty((9, max(nA, 1)), dtype=torch.float64, device=device)
         self.d_segOut = torch.empty((max(self.nSegments, 1), 14), dtype=torch.float64, device=device)
         self.d_mapStats = torch.empty((max(nS, 1), 4), dtype=torch.float64, device=device)
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
@@ -387,8 +393,8 @@ class CloudBatch:
                                           ctypes.c_double(minCloudElectrons), _ptr(self.d_atomOut), _ptr(self.d_mapOut),
                                           _ptr(self.ws), _stream()), "pe_cloud_aggregate")
         check(self.lib.pe_cloud_statistics(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomOut), _ptr(self.d_mapOut), _ptr(self.d_static),
-                                           _ptr(self.d_perm), _ptr(self.d_mapSegPtr), self.nSegments, _ptr(self.d_segType),
-                                           _ptr(self.d_segBegin), _ptr(self.d_segEnd), _ptr(self.d_unitVolume), _ptr(self.d_slopes),
+                                           _ptr(self.d_perm), self.nSegments, _ptr(self.d_segMap), _ptr(self.d_segType),
+                                           _ptr(self.d_segBegin), _ptr(self.d_segEnd), self.maxSegment, _ptr(self.d_unitVolume), _ptr(self.d_slopes),
                                            ctypes.c_double(minTotalElectrons), _ptr(self.d_scratch), _ptr(self.d_segOut),
                                            _ptr(self.d_mapStats), _stream()), "pe_cloud_statistics")
         self.h_mapOut.copy_(self.d_mapOut, non_blocking=True)

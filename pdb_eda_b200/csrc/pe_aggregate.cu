@@ -26,6 +26,7 @@
 // index, a residue id that is unique over the batch, its index inside the residue (< 64) and the bit mask of its bonded
 // atoms' indices inside the residue.
 #include <math.h>
+#include "pe_select.cuh"
 #include "pe_sphere_dev.cuh"
 
 namespace pe {
@@ -297,91 +298,32 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
 // np.nanmedian(d) + 2.5 * np.nanstd(d) over the smallest centroid distances of a structure's atoms that have clouds
 // (pdb_eda/densityAnalysis.py:608-609).  One CTA per structure; exact order statistics by radix select on the bit
 // patterns (distances are >= 0, so IEEE order is integer order); fixed-order reductions: deterministic.
-__device__ __forceinline__ double block_sum_fixed(double v, double *scratch /* >= blockDim.x / 32 */) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) scratch[w] = v;
-    __syncthreads();
-    double tot = 0.0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += scratch[k];
-    return tot;
-}
-
 __global__ void __launch_bounds__(kAggThreads)
     cutoff_kernel(const pe_batch_map *__restrict__ maps, const double *__restrict__ atom_out, double *__restrict__ map_out) {
-    __shared__ unsigned int hist[256];
+    __shared__ SelectShared sel;
     __shared__ double scratch[kAggThreads / 32];
-    __shared__ unsigned long long sel_prefix;
-    __shared__ unsigned int sel_rank;
     const pe_batch_map *m = maps + blockIdx.x;
     const int a0 = m->atom_begin, a1 = m->atom_end;
     double *mo = map_out + (int64_t)blockIdx.x * 8;
-    // count and mean of the valid distances
-    double cnt_d = 0.0, sum = 0.0;
-    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
-        const double *rec = atom_out + (int64_t)a * 8;
-        if (rec[0] > 0.0 && !isnan(rec[2])) {
-            cnt_d += 1.0;
-            sum += rec[2];
+    auto valid = [&](int a) { return atom_out[(int64_t)a * 8] > 0.0 && !isnan(atom_out[(int64_t)a * 8 + 2]); };
+    double cnt = 0.0, sum = 0.0;
+    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x)
+        if (valid(a)) {
+            cnt += 1.0;
+            sum += atom_out[(int64_t)a * 8 + 2];
         }
-    }
-    const double cnt = block_sum_fixed(cnt_d, scratch);
+    cnt = block_sum_fixed(cnt, scratch);
     sum = block_sum_fixed(sum, scratch);
-    if (cnt == 0.0) {
-        if (threadIdx.x == 0) mo[7] = nan("");
-        return;
-    }
     const double mean = sum / cnt;
     double sq = 0.0;
-    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
-        const double *rec = atom_out + (int64_t)a * 8;
-        if (rec[0] > 0.0 && !isnan(rec[2])) {
-            const double d = rec[2] - mean;
+    for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x)
+        if (valid(a)) {
+            const double d = atom_out[(int64_t)a * 8 + 2] - mean;
             sq += d * d;
         }
-    }
     sq = block_sum_fixed(sq, scratch);
-    const double sd = sqrt(sq / cnt);
-    // the two middle order statistics
-    const unsigned int n = (unsigned int)cnt;
-    double mid[2];
-    for (int which = 0; which < 2; ++which) {
-        unsigned int want = which == 0 ? (n - 1) / 2 : n / 2;  // 0-based rank
-        unsigned long long prefix = 0ull;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[k] = 0u;
-            __syncthreads();
-            const unsigned long long himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-            for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
-                const double *rec = atom_out + (int64_t)a * 8;
-                if (rec[0] > 0.0 && !isnan(rec[2])) {
-                    const unsigned long long bitsv = (unsigned long long)__double_as_longlong(rec[2] + 0.0);  // -0.0 -> 0.0
-                    if ((bitsv & himask) == prefix) atomicAdd(&hist[(bitsv >> shift) & 0xffu], 1u);
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned int acc = 0;
-                int k = 0;
-                for (; k < 256; ++k) {
-                    if (acc + hist[k] > want) break;
-                    acc += hist[k];
-                }
-                sel_prefix = prefix | ((unsigned long long)k << shift);
-                sel_rank = want - acc;
-            }
-            __syncthreads();
-            prefix = sel_prefix;
-            want = sel_rank;
-            __syncthreads();
-        }
-        mid[which] = __longlong_as_double((long long)prefix);
-    }
-    if (threadIdx.x == 0) {
-        const double median = (n & 1u) ? mid[0] : (mid[0] + mid[1]) / 2.0;
-        mo[7] = median + 2.5 * sd;
-    }
+    const double median = block_nanmedian(a1 - a0, [&](int i) { return valid(a0 + i) ? order_key(atom_out[(int64_t)(a0 + i) * 8 + 2]) : kNoKey; }, sel);
+    if (threadIdx.x == 0) mo[7] = median + 2.5 * sqrt(sq / cnt);  // NaN when no atom has a cloud
 }
 
 // ------------------------------------------------------------------------------------------------ pass 2: which atoms contribute

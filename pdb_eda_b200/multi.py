@@ -39,15 +39,18 @@ def shardStructures(costs, worldSize):
     return shards
 
 
-def analyzeStructure(analyzer, atomTypes):
-    """The per-structure result of ``analyzePDBID`` (pdb_eda/multipleStructures.py:320-356) /
-    ``processFunction`` (pdb_eda/optimizeParams.py:410-448), or 0 when the structure cannot be analysed."""
+def analyzeStructure(analyzer, atomTypes, optimizer=False):
+    """The per-structure result of ``analyzePDBID`` (pdb_eda/multipleStructures.py:320-356), or 0 when the structure cannot
+    be analysed.  ``optimizer=True`` gives the flavour of the optimiser's ``processFunction`` (pdb_eda/optimizeParams.py:410-448):
+    an atom type the structure lacks (or whose median is NaN) is OMITTED there (:434-436) -- NaN here, which the medians over
+    structures skip -- whereas analyzePDBID reports 0 for it (:335-336)."""
     start = time.process_time()
     if not analyzer or not analyzer.densityElectronRatio:
         return 0
     ratio = analyzer.densityElectronRatio
     corrected = analyzer.medians['corrected_density_electron_ratio']
-    diffs = {t: ((corrected[t] - ratio) / ratio) if t in corrected else 0 for t in atomTypes}
+    missing = np.nan if optimizer else 0
+    diffs = {t: ((corrected[t] - ratio) / ratio) if t in corrected else missing for t in atomTypes}
     slopes = {t: analyzer.medians['slopes'][t] if t in analyzer.medians['slopes'] else np.nan for t in atomTypes}
     complete = sum(analyzer.atomTypeOverlapCompleteness.values())
     incomplete = sum(analyzer.atomTypeOverlapIncompleteness.values())
@@ -86,15 +89,54 @@ def _pack(results, indices, atomTypes):
     return cumulative, np.asarray(rows, dtype=np.float64).reshape(-1, width)
 
 
+def packBatch(arr, indices, atomTypes, optimizer=False, executionTime=0.0):
+    """``_pack`` for the arrays of ``CloudBatch.collectArrays`` (one entry per structure of the batch; ``indices`` their pool
+    indices): no Python loop over structures.  Same row layout and the same two flavours as ``analyzeStructure``."""
+    T = len(atomTypes)
+    ok = np.asarray(arr["ok"], dtype=bool)
+    idx = np.asarray(indices, dtype=np.float64)[ok]
+    ratio = arr["ratio"][ok]
+    complete, incomplete = arr["complete"][ok], arr["incomplete"][ok]
+    cumulative = np.zeros(4 + 2 * T, dtype=np.float64)
+    cumulative[0] = ok.sum()
+    cumulative[1] = arr["numVoxels"][ok].sum()
+    cumulative[2] = arr["totalElectrons"][ok].sum()
+    cumulative[3] = arr["totalDensity"][ok].sum()
+    cumulative[4:4 + T] = complete.sum(axis=0)
+    cumulative[4 + T:] = incomplete.sum(axis=0)
+    csum, isum = complete.sum(axis=1).astype(np.float64), incomplete.sum(axis=1).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        completeness = np.where((csum > 0) | (isum > 0), csum / (csum + isum), csum)
+        corrected = arr["medians"]["corrected_density_electron_ratio"][ok]
+        present = arr["present"][ok]
+        diffs = (corrected - ratio[:, None]) / ratio[:, None]
+    if optimizer:
+        diffs = np.where(present, diffs, np.nan)                 # processFunction omits absent / NaN types (:434-436)
+    else:
+        diffs = np.where(present, diffs, 0.0)                    # analyzePDBID: 0 for a type the structure lacks (:335-336)
+    slopes = np.where(present, arr["medians"]["slopes"][ok], np.nan)
+    stats = np.stack((ratio, np.asarray(arr["unitVolume"], dtype=np.float64)[ok], arr["numVoxels"][ok], arr["totalElectrons"][ok],
+                      arr["totalDensity"][ok], arr["analysed"][ok], arr["residueClouds"][ok], arr["domainClouds"][ok], completeness,
+                      np.full(len(idx), float(executionTime))), axis=1)
+    rows = np.concatenate((idx[:, None], stats, diffs, slopes), axis=1) if len(idx) else np.zeros((0, 1 + len(STAT_COLUMNS) + 2 * T))
+    return cumulative, rows
+
+
 def gatherResults(results, indices, nStructures, atomTypes, device="cpu", group=None):
     """Collective step of multiple-structures mode.  ``results``: {structure index: result dict or 0} of THIS rank's
-    shard ``indices``.  Returns the same summary on every rank:
+    shard ``indices``.  Returns the same summary on every rank (see ``gatherPacked``)."""
+    atomTypes = list(atomTypes)
+    cumulative, rows = _pack(results, indices, atomTypes)
+    return gatherPacked(cumulative, rows, atomTypes, device, group)
+
+
+def gatherPacked(cumulative, rows, atomTypes, device="cpu", group=None):
+    """The two collectives on a rank's packed results (``_pack`` / ``packBatch``).  Returns the same summary on every rank:
     ``cumulative`` (dict), ``rows`` (n_ok x width float64, ordered by structure index), ``medianDiffs``, ``meanDiffs``,
     ``overallStdDevDiffs``, ``medianSlopes``, ``sizeDiffs``, ``atomTypeOverlapCompleteness`` --
     the quantities of ``calculateMedianDiffsSlopes`` (pdb_eda/optimizeParams.py:400-408)."""
     atomTypes = list(atomTypes)
     T = len(atomTypes)
-    cumulative, rows = _pack(results, indices, atomTypes)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     width = 1 + len(STAT_COLUMNS) + 2 * T
     if world > 1:
@@ -116,18 +158,26 @@ def gatherResults(results, indices, nStructures, atomTypes, device="cpu", group=
         allrows = rows
     allrows = allrows[np.argsort(allrows[:, 0], kind="stable")] if len(allrows) else allrows
     ns = 1 + len(STAT_COLUMNS)
-    diffs = {t: allrows[:, ns + k].tolist() for k, t in enumerate(atomTypes)}
-    slopes = {t: allrows[:, ns + T + k].tolist() for k, t in enumerate(atomTypes)}
+    D = np.asarray(allrows[:, ns:ns + T], dtype=np.float64).reshape(-1, T)           # per-structure diffs, one column per type
+    S = np.asarray(allrows[:, ns + T:ns + 2 * T], dtype=np.float64).reshape(-1, T)   # slopes
     complete = {t: cumulative[4 + k] for k, t in enumerate(atomTypes)}
     incomplete = {t: cumulative[4 + T + k] for k, t in enumerate(atomTypes)}
     completeness = {t: (complete[t] / (complete[t] + incomplete[t]) if (complete[t] > 0 or incomplete[t] > 0) else 1) for t in atomTypes}
     with np.errstate(all="ignore"):
-        medianDiffs = {t: (np.nanmedian(v) if (v and not np.isnan(v).all()) else 0) for t, v in diffs.items()}
-        meanDiffs = {t: (np.nanmean(v) if (v and not np.isnan(v).all()) else 0) for t, v in diffs.items()}
-        sizeDiffs = {t: int(np.sum(~np.isnan(v))) if v else 0 for t, v in diffs.items()}
-        squared = [x ** 2 for v in diffs.values() for x in v if not np.isnan(x)]
-        overallStd = float(np.sqrt(sum(squared) / (len(squared) - 1))) if len(squared) > 1 else float("nan")
-        medianSlopes = {t: np.nanmedian(v) for t, v in slopes.items() if v and not np.isnan(v).all()}
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            haveD = (~np.isnan(D)).any(axis=0) if len(D) else np.zeros(T, dtype=bool)
+            medD = np.nanmedian(D, axis=0) if len(D) else np.zeros(T)
+            meanD = np.nanmean(D, axis=0) if len(D) else np.zeros(T)
+            haveS = (~np.isnan(S)).any(axis=0) if len(S) else np.zeros(T, dtype=bool)
+            medS = np.nanmedian(S, axis=0) if len(S) else np.zeros(T)
+        medianDiffs = {t: (medD[k] if haveD[k] else 0) for k, t in enumerate(atomTypes)}
+        meanDiffs = {t: (meanD[k] if haveD[k] else 0) for k, t in enumerate(atomTypes)}
+        sizeDiffs = {t: int(np.sum(~np.isnan(D[:, k]))) for k, t in enumerate(atomTypes)}
+        valid = D[~np.isnan(D)]
+        overallStd = float(np.sqrt(np.sum(valid ** 2) / (len(valid) - 1))) if len(valid) > 1 else float("nan")
+        medianSlopes = {t: medS[k] for k, t in enumerate(atomTypes) if haveS[k]}
     return {"cumulative": {"structures": int(cumulative[0]), "num_voxels_aggregated": cumulative[1],
                            "total_aggregated_electrons": cumulative[2], "total_aggregated_density": cumulative[3],
                            "density_electron_ratio": cumulative[3] / cumulative[2] if cumulative[2] else None,
@@ -227,3 +277,60 @@ class OptimizeService:
                 results[idx] = 0
         s = gatherResults(results, self.mine, self.n, types, self.device, self.group)
         return (s["medianDiffs"], s["meanDiffs"], s["overallStdDevDiffs"], s["medianSlopes"], s["sizeDiffs"], s["atomTypeOverlapCompleteness"])
+
+
+class PoolShard:
+    """One rank's share of a pool of structures, resident on its GPU and analysed in batches (``cloudBatch.CloudBatch``):
+    the device-side form of the reference's Pool of ``analyzePDBID`` / ``processFunction`` tasks
+    (pdb_eda/multipleStructures.py:164-180, pdb_eda/optimizeParams.py:355-358).  ``entries``: (pool index, 2Fo-Fc map
+    (DensityMatrix or cloudBatch.MapRef), cloudBatch.AtomTable) of the structures this rank owns, e.g. the shard
+    ``shardStructures`` assigns to it.  A batch holds at most ``maxAtoms`` atoms (its cloud voxels size one workspace)."""
+
+    def __init__(self, entries, params, maxAtoms=1 << 21, device=None):
+        from .cloudBatch import CloudBatch
+        self.params = params
+        self.atomTypes = sorted(params["radii"])
+        self.batches, self.indices = [], []
+        cur, curIdx, atoms = [], [], 0
+        for idx, dm, table in entries:
+            if cur and atoms + len(table) > maxAtoms:
+                self.batches.append(CloudBatch(cur, params, device))
+                self.indices.append(curIdx)
+                cur, curIdx, atoms = [], [], 0
+            cur.append((dm, table))
+            curIdx.append(idx)
+            atoms += len(table)
+        if cur:
+            self.batches.append(CloudBatch(cur, params, device))
+            self.indices.append(curIdx)
+        self.nStructures = sum(len(i) for i in self.indices)
+        self.nAtoms = sum(b.nAtoms for b in self.batches)
+
+    def setRadii(self, params):
+        self.params = params
+        for b in self.batches:
+            b.setRadii(params)
+
+    def launch(self, minCloudElectrons=25.0, minTotalElectrons=400.0):
+        for b in self.batches:
+            b.launch(minCloudElectrons, minTotalElectrons)
+
+    def pack(self, optimizer=False):
+        """(cumulative vector, rows) of this shard: the payload of the two collectives."""
+        T = len(self.atomTypes)
+        cumulative = np.zeros(4 + 2 * T, dtype=np.float64)
+        rows = []
+        for b, idx in zip(self.batches, self.indices):
+            c, r = packBatch(b.collectArrays(), idx, self.atomTypes, optimizer)
+            cumulative += c
+            rows.append(r)
+        width = 1 + len(STAT_COLUMNS) + 2 * T
+        return cumulative, (np.concatenate(rows) if rows else np.zeros((0, width)))
+
+    def analyze(self, device=None, group=None, optimizer=False, minCloudElectrons=25.0, minTotalElectrons=400.0):
+        """One pass over the shard + the fused all-reduce and the all-gather; the same summary on every rank."""
+        self.launch(minCloudElectrons, minTotalElectrons)
+        cumulative, rows = self.pack(optimizer)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        return gatherPacked(cumulative, rows, self.atomTypes, device, group)

@@ -215,3 +215,99 @@ def smoothNoiseMapDevice(n, seed=4, passes=2, device="cuda"):
             vol = (vol + torch.roll(vol, 1, axis) + torch.roll(vol, -1, axis)) / 3.0
     vol = vol / vol.std()
     return vol.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------- structure pools
+# BASELINE.json config 3: many synthetic structures of mixed size and space group.  Everything below is input synthesis
+# (numpy + torch on the device), none of it is on the measured path.
+POOL_SIZES = (64, 96, 128, 192, 256)
+POOL_SPACE_GROUPS = ("P 1", "P 1 21 1", "P 21 21 21", "P 43 21 2", "P 65 2 2")
+
+
+def poolSpec(nStructures, seed=3, sizes=POOL_SIZES, spaceGroups=POOL_SPACE_GROUPS, atomsPerVoxel=1.0 / 350.0):
+    """The pool as a list of dicts (index, n, cell, spaceGroup, residues, seed): grid sizes and space groups drawn with
+    ``seed``, 0.5 A grid, atoms ~ n^3 / 350.  P 65 2 2 gets a hexagonal cell (gamma = 120)."""
+    rng = np.random.default_rng(seed)
+    spec = []
+    for k in range(nStructures):
+        n = int(sizes[int(rng.integers(len(sizes)))])
+        sg = spaceGroups[int(rng.integers(len(spaceGroups)))]
+        edge = 0.5 * n
+        cell = (edge, edge, edge, 90.0, 90.0, 120.0 if sg == "P 65 2 2" else 90.0)
+        volumeFraction = np.sin(np.radians(cell[5]))
+        residues = max(int(round(n ** 3 * atomsPerVoxel * volumeFraction / 5.0)), 4)
+        spec.append({"index": k, "n": n, "cell": cell, "spaceGroup": sg, "residues": residues, "seed": 1000 + seed * 100003 + k})
+    return spec
+
+
+def fastPolyAla(nResidues, cell, seed):
+    """Vectorised poly-ALA generator: CA random walk (3.8 A steps, reflected into a box inscribed in the cell), a random
+    rotation of the residue frame per residue, coordinates rounded to 3 decimals as float32.
+    Returns (coords32 (5 n, 3), bfactor (5 n))."""
+    rng = np.random.default_rng(seed)
+    omat = orthoMatrix(cell)
+    if cell[5] != 90:
+        corners = np.array([omat @ np.array([0.28, 0.3, 0.08]), omat @ np.array([0.55, 0.7, 0.92])])
+        lo, hi = corners.min(axis=0) + 2.5, corners.max(axis=0) - 2.5
+        lo[0], hi[0] = omat[0, 0] * 0.3, omat[0, 0] * 0.55      # stay inside the sheared x range for every y of the box
+    else:
+        lo, hi = np.full(3, 3.0), np.asarray(cell[:3], dtype=np.float64) - 3.0
+    steps = rng.normal(size=(nResidues, 3))
+    steps *= 3.8 / np.linalg.norm(steps, axis=1, keepdims=True)
+    span = hi - lo
+    walk = (span * rng.uniform(0.3, 0.7, 3)) + np.cumsum(steps, axis=0)
+    folded = np.mod(walk, 2 * span)
+    ca = lo + np.where(folded > span, 2 * span - folded, folded)           # triangle wave: reflection at the box faces
+    q = rng.normal(size=(nResidues, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    rot = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], axis=1),
+                    np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], axis=1),
+                    np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=1)], axis=1)
+    offs = np.array([o for _, o, _ in _ALA_ATOMS], dtype=np.float64)           # (5, 3)
+    coords = ca[:, None, :] + np.einsum("nij,aj->nai", rot, offs)
+    coords32 = np.round(coords.reshape(-1, 3), 3).astype(np.float32)
+    bfactor = np.round(rng.uniform(10, 40, 5 * nResidues), 2)
+    return coords32, bfactor
+
+
+def polyAlaTable(coords32, bfactor, params):
+    """``cloudBatch.AtomTable`` of a poly-ALA chain given as arrays (the same rows AtomTable.fromStructure would yield)."""
+    from .cloudBatch import AtomTable, _distinctRows
+    names = ["ALA_" + a for a, _, _ in _ALA_ATOMS]
+    n = len(coords32)
+    nres = n // 5
+    local = np.tile(np.arange(5, dtype=np.int32), nres)
+    bondedOf = np.zeros(5, dtype=np.uint64)
+    for k, name in enumerate(names):
+        for other in params["bonded_atoms"].get(name, ()):
+            if other in names:
+                bondedOf[k] |= np.uint64(1 << names.index(other))
+    supported = _distinctRows(coords32) == n
+    return AtomTable(coords32, names, local.copy(), np.ones(n), bfactor, np.repeat(np.arange(nres, dtype=np.int32), 5), local,
+                     np.tile(bondedOf, nres), nres, None, supported, "" if supported else "atoms with identical coordinates")
+
+
+def densityMapDevice(coords32, electronsPerAtom, n, cell, seed, sigma=1.2, device="cuda"):
+    """2Fo-Fc-like volume generated in HBM: electrons deposited at each atom's nearest grid point, periodic Gaussian smoothing
+    (sigma voxels), 2 % noise -- the recipe of ``mapPair`` for column/row/section = x/y/z.  float32 CUDA tensor [n][n][n]."""
+    import torch
+    inv = np.linalg.inv(orthoMatrix(cell))
+    frac = coords32.astype(np.float64) @ inv.T
+    g = np.rint(frac * n).astype(np.int64) % n
+    flat = torch.from_numpy((g[:, 2] * n + g[:, 1]) * n + g[:, 0]).to(device)
+    vol = torch.zeros(n * n * n, dtype=torch.float32, device=device)
+    vol.index_add_(0, flat, torch.from_numpy(np.asarray(electronsPerAtom, dtype=np.float32)).to(device))
+    vol = vol.view(n, n, n)
+    radius = int(np.ceil(4 * sigma))
+    ks = np.exp(-0.5 * (np.arange(-radius, radius + 1) / sigma) ** 2)
+    ks /= ks.sum()
+    for axis in range(3):
+        acc = torch.zeros_like(vol)
+        for k, wgt in zip(range(-radius, radius + 1), ks):
+            acc.add_(torch.roll(vol, k, axis), alpha=float(wgt))
+        vol = acc
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    vol = vol + 0.02 * vol.std() * torch.randn(vol.shape, generator=gen, device=device, dtype=torch.float32)
+    return vol.contiguous()

@@ -197,16 +197,16 @@ def test_statistics_kernel_matches_the_numpy_statement():
     edge = np.flatnonzero(np.concatenate(([True], gkey[1:] != gkey[:-1])))
     segBegin, segEnd = edge.astype(np.int32), np.concatenate((edge[1:], [nA])).astype(np.int32)
     segMap, segType = (gkey[edge] // nT).astype(np.int32), (gkey[edge] % nT).astype(np.int32)
-    mapSegPtr = np.searchsorted(segMap, np.arange(nS + 1)).astype(np.int32)
     dev = "cuda"
     up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d = dict(maps=torch.frombuffer(bytearray(bytes(maps)), dtype=torch.uint8).to(dev), recs=up(recs), mapOut=up(mapOut), static=up(static),
-             perm=up(perm), ptr=up(mapSegPtr), st=up(segType), sb=up(segBegin), se=up(segEnd), uv=up(unitVolume), sl=up(slopes))
-    scratch = torch.empty((nA, 6), dtype=torch.float64, device=dev)
+             perm=up(perm), sm=up(segMap), st=up(segType), sb=up(segBegin), se=up(segEnd), uv=up(unitVolume), sl=up(slopes))
+    scratch = torch.empty((9, nA), dtype=torch.float64, device=dev)
     segOut = torch.empty((len(segBegin), 14), dtype=torch.float64, device=dev)
     mapStats = torch.empty((nS, 4), dtype=torch.float64, device=dev)
     _lib.check(lib.pe_cloud_statistics(nS, _ptr(d["maps"]), nA, _ptr(d["recs"]), _ptr(d["mapOut"]), _ptr(d["static"]), _ptr(d["perm"]),
-                                       _ptr(d["ptr"]), len(segBegin), _ptr(d["st"]), _ptr(d["sb"]), _ptr(d["se"]), _ptr(d["uv"]), _ptr(d["sl"]),
+                                       len(segBegin), _ptr(d["sm"]), _ptr(d["st"]), _ptr(d["sb"]), _ptr(d["se"]),
+                                       int((segEnd - segBegin).max()), _ptr(d["uv"]), _ptr(d["sl"]),
                                        ctypes.c_double(400.0), _ptr(scratch), _ptr(segOut), _ptr(mapStats), _stream()), "pe_cloud_statistics")
     segOut, mapStats = segOut.cpu().numpy(), mapStats.cpu().numpy()
     rows = np.flatnonzero(recs[:, 7].astype(int) & 1)
