@@ -1,21 +1,29 @@
 #!/usr/bin/env python3
-"""bench.py -- the voxel hot path on BASELINE.json's config 2 (one line of JSON on stdout).
+"""bench.py -- the voxel hot path on BASELINE.json's configurations (one line of JSON on stdout).
 
-Workload ("config.workload": "C2"): a ~40k-atom synthetic poly-ALA structure (8,000 residues) on a 384^3 P1 map pair
+N = 1  ("config.workload": "C2"): a ~40k-atom synthetic poly-ALA structure (8,000 residues) on a 384^3 P1 map pair
 (cell 192 A, 0.5 A grid).  One step = one pass of the hot path over that structure:
   cloud   per-atom sphere gather-sums at the atom-type radii (2Fo-Fc, cutoff mean + 1.5 sigma)
   region  per-residue set-union sphere sums at 3.5 A (2Fo-Fc)
   blobs   green + red blob lists of the Fo-Fc map at +-(mean + 3 sigma): threshold, 26-connected labelling in the
           reference's blob order, per-blob sums
 Units: atom-sphere voxels ((atom, voxel) pairs passing the distance test; cloud + region) + blob-CCL voxels (voxels
-of the scanned unique volume).  `value` = units of all ranks / device time of the slowest rank, inputs resident in
-HBM.  `e2e` = the same through the public API with HOST buffers (maps + atoms copied in, results copied out, every
-step).  N > 1: replicas only -- a single structure does not shard; every rank runs its own
-structure, no data-path collective.
+of the scanned unique volume).  `value` = units / device time, inputs resident in HBM.  `e2e` = the same through the
+public API with HOST buffers (maps + atoms copied in, results copied out, every step).  The line also carries `c3`
+(the multiple-structures pool of the N > 1 runs on this one GPU) and `e2e_api` (the DensityAnalysis calls a user makes).
 
---impl reference: the UNMODIFIED reference (oracle/_ref: pdb_eda 2.7.1 + its compiled Cython cutils) on the host
-CPU, one core (its single-structure path is single threaded), on a bounded sample of the same workload (64^3 map,
-same atom density, same three sub-workloads through the reference's public methods).
+N > 1  ("config.workload": "C3", BASELINE.json configs[2]): multiple-structures mode.  A fixed pool of synthetic
+structures (mixed space groups, 64^3 - 256^3 maps, atoms ~ n^3 / 350; --pool, default 1,024 of the 4,096 so that the
+whole pool also fits ONE GPU for the strong-scaling reference) is sharded over the ranks longest-first
+(multi.shardStructures); one step = every rank analyses its share (cloud aggregation = analyzePDBID,
+pdb_eda/multipleStructures.py:320-356, batched: cloudBatch / pe_cloud_*) + the fused all-reduce of the cumulative
+statistics + the all-gather of the per-structure rows (multi.gatherPacked), all inside the timed region.  STRONG
+scaling: the same pool at every N.  Units: atom-sphere voxels of the pool (multiple-structures mode computes no blobs).
+`pool_on_one_gpu` = the same pool on rank 0 alone, timed in the same run (the denominator for scaling at fixed work);
+`c4` = BASELINE.json configs[3]: one 1024^3 Fo-Fc map slab-partitioned over the ranks vs the whole map on one GPU.
+
+--impl reference: the UNMODIFIED reference (oracle/_ref: pdb_eda 2.7.1 + its compiled Cython cutils) on the host CPU,
+one core (its single-structure path is single threaded), on a bounded sample of the C2 workload.
 """
 import argparse
 import json
@@ -415,9 +423,253 @@ def main_gpu(args, rank, world, local_rank):
             _, cpu, _ = run_cpu_sample(1, 0)
             line["cpu_baseline"] = cpu
             line["api_c2"] = api_timing(work)
+        if world == 1 and not args.no_c3:
+            # BASELINE.json configs[2] on this one GPU: the pool the N > 1 runs shard (their strong-scaling reference point)
+            del vp, dens, diff, d_dens, d_diff
+            torch.cuda.empty_cache()
+            line["c3"] = run_c3_one_gpu(args.pool, 3, device, synthetic.defaultParams())[0]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ config 3: structure pool
+def _pool_units(entries, params):
+    """Atom-sphere voxels ((atom, voxel) pairs passing the distance test) of a list of pool entries."""
+    from pdb_eda_b200 import cloudBatch
+    units = 0.0
+    for _, mref, table in entries:
+        radii = cloudBatch._typeTables(table, params)[0][table.nameIndex].astype(np.float32)
+        out = mref.deviceMap.sphere_sums(table.coords32.astype(np.float64), radii)
+        units += float(out[:, 0].sum().item())
+    return units
+
+
+def _time_passes(shard, steps, warmup, barrier, **kw):
+    """(ms per pass by CUDA events, ms per pass by the host clock, last summary)."""
+    import torch
+    summary = None
+    for _ in range(warmup):
+        summary = shard.analyze(**kw)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        summary = shard.analyze(**kw)
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3 / steps
+    return e0.elapsed_time(e1) / steps, wall, summary
+
+
+def _summary_digest(summary):
+    c = summary["cumulative"]
+    return {"structures": c["structures"], "num_voxels_aggregated": c["num_voxels_aggregated"],
+            "total_aggregated_electrons": c["total_aggregated_electrons"], "total_aggregated_density": c["total_aggregated_density"],
+            "density_electron_ratio": c["density_electron_ratio"],
+            "median_diffs": {k.split("#")[0]: float(v) for k, v in summary["medianDiffs"].items()}}
+
+
+def run_c3_one_gpu(pool, steps, device, params):
+    """The whole pool on this GPU alone (no collectives): {ms_per_pass, structures_per_s, value, summary digest}."""
+    import torch
+    from pdb_eda_b200 import multi
+    spec = synthetic.poolSpec(pool)
+    t0 = time.perf_counter()
+    entries = synthetic.buildPoolEntries(spec, params, device)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    units = _pool_units(entries, params)
+    shard = multi.PoolShard(entries, params, device=device)
+    ms, wall, summary = _time_passes(shard, steps, 2, torch.cuda.synchronize, device=device, local=True)
+    return {"structures": pool, "atoms": shard.nAtoms, "batches": len(shard.batches), "atom_sphere_voxels": units,
+            "cloud_voxels": int(sum(b.nEntries for b in shard.batches)), "ms_per_pass": ms, "ms_per_pass_host_clock": wall,
+            "structures_per_s": pool / (ms * 1e-3), "value": units / (ms * 1e-3), "unit": UNIT, "setup_s": round(setup_s, 1),
+            "summary": _summary_digest(summary)}, summary
+
+
+def main_c3(args, rank, world, local_rank):
+    """N > 1: BASELINE.json configs[2], strong scaling over a fixed pool (see the module docstring)."""
+    import torch
+    import torch.distributed as dist
+    from pdb_eda_b200 import _device, _lib, multi
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
+    dist.init_process_group("nccl", device_id=device)
+    _device.require_cuda()
+    params = synthetic.defaultParams()
+    spec = synthetic.poolSpec(args.pool)
+    costs = synthetic.poolCosts(spec)
+    mine = multi.shardStructures(costs, world)[rank]
+    t0 = time.perf_counter()
+    entries = synthetic.buildPoolEntries([spec[i] for i in mine], params, device)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    units = _pool_units(entries, params)
+    shard = multi.PoolShard(entries, params, device=device)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib = _lib.load()
+    # ---- device-resident timing: K passes over the pool, collectives inside
+    ms, wall, summary = _time_passes(shard, args.steps, warmup, barrier, device=device)
+    # ---- instrumented repeat: per-kernel device times + launch count
+    launches0 = lib.pe_launch_count()
+    _lib.profile(True, reset=True)
+    ms_prof, _, _ = _time_passes(shard, args.steps, 0, barrier, device=device)
+    launches = lib.pe_launch_count() - launches0
+    prof = _lib.profile()
+    _lib.profile(False)
+    # ---- end to end: every step uploads the shard's maps from pinned host memory first
+    host_maps = []
+    for _, mref, _ in entries:
+        h = torch.empty(mref.deviceMap.rho.shape, dtype=torch.float32).pin_memory()
+        h.copy_(mref.deviceMap.rho)
+        host_maps.append(h)
+    torch.cuda.synchronize()
+
+    class _E2E:
+        def analyze(self, **kw):
+            for (_, mref, _), h in zip(entries, host_maps):
+                mref.deviceMap.rho.copy_(h, non_blocking=True)
+            return shard.analyze(**kw)
+
+    e2e_steps = max(args.steps // 4, 2)
+    ms_e2e, _, _ = _time_passes(_E2E(), e2e_steps, 1, barrier, device=device)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(h.numel() * 4 for h in host_maps)
+    d2h = sum(b.h_mapOut.numel() + b.h_segOut.numel() + b.h_mapStats.numel() for b in shard.batches) * 8
+
+    stats = torch.tensor([ms, ms_e2e, ms_prof, wall], dtype=torch.float64, device=device)
+    sums = torch.tensor([units, float(shard.nAtoms), float(sum(b.nEntries for b in shard.batches)), float(h2d), float(d2h),
+                         float(len(shard.batches))], dtype=torch.float64, device=device)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms, ms_e2e, ms_prof, wall = stats.tolist()
+    all_units, all_atoms, all_entries, all_h2d, all_d2h, all_batches = sums.tolist()
+    del host_maps
+
+    one = None
+    if rank == 0 and not args.no_single:
+        # strong-scaling denominator measured in the same run: the same pool on this GPU alone
+        del shard, entries
+        torch.cuda.empty_cache()
+        one, one_summary = run_c3_one_gpu(args.pool, max(args.steps // 4, 2), device, params)
+        a, b = _summary_digest(summary), one["summary"]
+        close = lambda x, y: abs(x - y) <= 1e-9 * max(abs(x), abs(y), 1e-300)
+        one["same_results_as_%d_gpus" % world] = bool(
+            a["structures"] == b["structures"] and a["num_voxels_aggregated"] == b["num_voxels_aggregated"] and
+            close(a["total_aggregated_density"], b["total_aggregated_density"]) and
+            close(a["total_aggregated_electrons"], b["total_aggregated_electrons"]) and
+            all(close(a["median_diffs"][k], b["median_diffs"][k]) for k in a["median_diffs"]) and
+            np.array_equal(np.asarray(summary["rows"])[:, 0], np.asarray(one_summary["rows"])[:, 0]))
+    c4 = run_c4(args, rank, world, device) if not args.no_c4 else None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        kernels = []
+        for name, (count, kms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            kernels.append({"kernel": name, "launches": count, "ms_total": round(kms, 4), "us_per_launch": round(kms * 1e3 / max(count, 1), 2)})
+        # rank 0's share of the pool for the per-kernel lines (kernel times are rank 0's)
+        dominant = kernels[0] if kernels else None
+        roof = None
+        if dominant is not None:
+            # algorithmic bytes of the dominant kernel on rank 0 (DESIGN.md section 3.6): per pool voxel the packed key (8),
+            # owner (4) and cloud number (2) read once + one 16-byte table slot; per atom its 16-byte record
+            r0_entries = all_entries / world
+            r0_atoms = all_atoms / world
+            per_launch = (30.0 * r0_entries + 16.0 * r0_atoms) / max(dominant["launches"] / args.steps, 1)
+            t = dominant["ms_total"] / max(dominant["launches"], 1) * 1e-3
+            ach = per_launch / t / 1e9
+            roof = {"kernel": dominant["kernel"], "bound": "latency", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+                    "us_per_launch": dominant["us_per_launch"],
+                    "note": "hash-table neighbour probes of the pool voxels (14 per voxel) + union-find: random 16-byte accesses, "
+                            "bound by memory latency / L2 sector rate, not by streaming bandwidth; algorithmic bytes = 30 B per "
+                            "pool voxel + 16 B per atom on rank 0 (an even share of the pool is assumed)"}
+        value = all_units / (ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C3: multiple-structures mode, pool of %d synthetic structures (64^3-256^3 maps, P1 / P2(1) / P2(1)2(1)2(1) / "
+                                       "P4(3)2(1)2 / P6(5)22, %d atoms), cloud aggregation per structure (analyzePDBID) in batches + fused "
+                                       "all-reduce of the cumulative statistics + all-gather of the rows inside the timed region"
+                                       % (args.pool, int(all_atoms)),
+                           "parallelism": "structures sharded over %d GPUs longest-first (multi.shardStructures); no data-path collective" % world,
+                           "pool": args.pool, "pool_of_baseline": 4096,
+                           "l2": "inputs larger than L2 (%.1f GB of maps per pass over the pool); no explicit flush" % (all_h2d / 1e9)},
+                "units_per_step": {"atom_sphere_voxels": all_units, "cloud_voxels": all_entries, "atoms": all_atoms, "structures": args.pool,
+                                   "blob_ccl_voxels": 0.0},
+                "structures_per_s": args.pool / (ms * 1e-3),
+                "e2e": {"value": all_units / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": all_h2d, "d2h_bytes_per_step": all_d2h,
+                        "ms_per_step": ms_e2e, "structures_per_s": args.pool / (ms_e2e * 1e-3), "steps": e2e_steps},
+                "gpu_launches": int(launches), "roofline": roof, "kernels": kernels[:14], "ms_per_step_profiled": ms_prof,
+                "ms_per_step_host_clock": wall, "gpu_busy_frac_rank0": round(sum(k["ms_total"] for k in kernels) / (ms_prof * args.steps), 3),
+                "batches": int(all_batches), "setup_s_rank0": round(setup_s, 1), "summary": _summary_digest(summary),
+                "pool_on_one_gpu": one, "c4": c4, "clocks": clocks}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_c4(args, rank, world, device):
+    """BASELINE.json configs[3]: one n^3 Fo-Fc map (n = --c4-n, default 1024) slab-partitioned over the ranks with halo label
+    merge, against the whole map on one GPU (rank 0), timed in the same run; results compared on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from pdb_eda_b200 import _device, ccp4, slab
+    n = args.c4_n
+    hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), (n * 0.5,) * 3 + (90, 90, 90), (n, n, n)))
+    s0, s1 = slab.slabRanges(n, world)[rank]
+    vol = synthetic.smoothNoiseMapDevice(n, seed=4, device=device)           # every rank generates the same map, keeps its slab
+    mine = vol[s0:s1].contiguous()
+    if rank != 0:
+        del vol
+        torch.cuda.empty_cache()
+    cut = 3.0
+    for _ in range(2):
+        parts = slab.labelSlabDistributed(hdr, mine, s0, s1, cut, -cut)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        parts = slab.labelSlabDistributed(hdr, mine, s0, s1, cut, -cut)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        whole_dev = _device.DeviceMap(_device.geom_from_header(hdr), vol.reshape(-1))
+        whole = whole_dev.blob_label(cut, -cut)
+        e0.record()
+        for _ in range(reps):
+            whole = whole_dev.blob_label(cut, -cut)
+        e1.record()
+        torch.cuda.synchronize()
+        ok = all(w["n_blobs"] == p["n_blobs"] and torch.allclose(w["stats"], p["stats"], rtol=1e-9, atol=1e-9) for w, p in zip(whole, parts))
+        one_ms = e0.elapsed_time(e1) / reps
+        out = {"workload": "C4: %d^3 Fo-Fc map, +-3 sigma blobs, %d slabs along the section axis, halo label merge over NCCL" % (n, world),
+               "blob_ccl_voxels": float(n) ** 3, "ms_slabs": t.item(), "value_slabs": float(n) ** 3 / (t.item() * 1e-3),
+               "ms_whole_map_one_gpu": one_ms, "value_whole_map_one_gpu": float(n) ** 3 / (one_ms * 1e-3), "unit": "blob-CCL voxels/s",
+               "green_blobs": int(parts[0]["n_blobs"]), "red_blobs": int(parts[1]["n_blobs"]), "same_blobs_and_sums_as_whole_map": bool(ok)}
+    return out
 
 
 def main():
@@ -427,12 +679,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pool", type=int, default=1024, help="structures in the config-3 pool (BASELINE.json: 4,096)")
+    ap.add_argument("--c4-n", type=int, default=1024, help="edge of the config-4 map")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip timing the pool on one GPU")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the config-4 slab run")
+    ap.add_argument("--no-c3", action="store_true", help="N = 1: skip the config-3 pool key")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         main_reference(args, rank, world)
+    elif world > 1:
+        main_c3(args, rank, world, local_rank)
     else:
         main_gpu(args, rank, world, local_rank)
 

@@ -130,14 +130,14 @@ def gatherResults(results, indices, nStructures, atomTypes, device="cpu", group=
     return gatherPacked(cumulative, rows, atomTypes, device, group)
 
 
-def gatherPacked(cumulative, rows, atomTypes, device="cpu", group=None):
+def gatherPacked(cumulative, rows, atomTypes, device="cpu", group=None, local=False):
     """The two collectives on a rank's packed results (``_pack`` / ``packBatch``).  Returns the same summary on every rank:
     ``cumulative`` (dict), ``rows`` (n_ok x width float64, ordered by structure index), ``medianDiffs``, ``meanDiffs``,
     ``overallStdDevDiffs``, ``medianSlopes``, ``sizeDiffs``, ``atomTypeOverlapCompleteness`` --
     the quantities of ``calculateMedianDiffsSlopes`` (pdb_eda/optimizeParams.py:400-408)."""
     atomTypes = list(atomTypes)
     T = len(atomTypes)
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    world = dist.get_world_size(group) if (dist.is_initialized() and not local) else 1   # local: this rank's structures only
     width = 1 + len(STAT_COLUMNS) + 2 * T
     if world > 1:
         cum_t = torch.from_numpy(cumulative).to(device)
@@ -327,10 +327,11 @@ class PoolShard:
         width = 1 + len(STAT_COLUMNS) + 2 * T
         return cumulative, (np.concatenate(rows) if rows else np.zeros((0, width)))
 
-    def analyze(self, device=None, group=None, optimizer=False, minCloudElectrons=25.0, minTotalElectrons=400.0):
-        """One pass over the shard + the fused all-reduce and the all-gather; the same summary on every rank."""
+    def analyze(self, device=None, group=None, optimizer=False, minCloudElectrons=25.0, minTotalElectrons=400.0, local=False):
+        """One pass over the shard + the fused all-reduce and the all-gather; the same summary on every rank
+        (``local=True``: no collectives, this rank's structures only)."""
         self.launch(minCloudElectrons, minTotalElectrons)
         cumulative, rows = self.pack(optimizer)
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        return gatherPacked(cumulative, rows, self.atomTypes, device, group)
+        return gatherPacked(cumulative, rows, self.atomTypes, device, group, local)

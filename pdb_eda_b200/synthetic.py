@@ -311,3 +311,28 @@ def densityMapDevice(coords32, electronsPerAtom, n, cell, seed, sigma=1.2, devic
     gen.manual_seed(int(seed))
     vol = vol + 0.02 * vol.std() * torch.randn(vol.shape, generator=gen, device=device, dtype=torch.float32)
     return vol.contiguous()
+
+
+def buildPoolEntries(spec, params, device="cuda"):
+    """(pool index, cloudBatch.MapRef, cloudBatch.AtomTable) for every structure of ``spec`` (see ``poolSpec``): structure
+    and 2Fo-Fc map synthesised on the spot, map resident on ``device``, densityCutoff = mean + 1.5 sigma from the library's
+    own reduction (pdb_eda/densityAnalysis.py:131)."""
+    from . import _device, ccp4
+    from .cloudBatch import MapRef
+    electronsOf = np.array([ALA_ELECTRONS["ALA_" + a] for a, _, _ in _ALA_ATOMS])
+    entries = []
+    for sp in spec:
+        n, cell = sp["n"], sp["cell"]
+        coords, bf = fastPolyAla(sp["residues"], cell, sp["seed"])
+        table = polyAlaTable(coords, bf, params)
+        rho = densityMapDevice(coords, np.tile(electronsOf, sp["residues"]), n, cell, sp["seed"] + 1, device=device)
+        hdr = ccp4.DensityHeader.fromFileHeader(ccp4Header((n, n, n), cell, (n, n, n)))
+        dmap = _device.DeviceMap(_device.geom_from_header(hdr), rho.reshape(-1))
+        mean, std = dmap.mean_std()
+        entries.append((sp["index"], MapRef(dmap, mean + 1.5 * std, hdr.unitVolume, "s%05d" % sp["index"]), table))
+    return entries
+
+
+def poolCosts(spec):
+    """Cost estimate per structure for longest-first sharding: cloud voxels scale with the atom count."""
+    return [5.0 * sp["residues"] for sp in spec]
