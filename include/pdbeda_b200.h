@@ -176,6 +176,36 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
                   int64_t cap_blobs, int64_t *d_counts, uint32_t *d_key, float *d_value, int32_t *d_label,
                   double *d_stats, void *d_ws, void *stream);
 
+/* ---------------------------------------------------------------- slab-decomposed blob labelling ----------- */
+/* One very large map cut into slabs along the section axis (the slowest axis in memory, pdb_eda/ccp4.py:338), one slab per
+ * GPU.  The reference cannot run such maps at all (Python float per voxel, N x N cdist: pdb_eda/ccp4.py:123-124,
+ * pdb_eda/cutils.pyx:55); the result reproduced is the whole map's createFullBlobList (pdb_eda/ccp4.py:463-485).
+ * Every rank labels its slab [s0, s1) with pe_blob_label (geometry = the map's with ncrs[2] / unique_ncrs[2] = the slab's
+ * section counts), then:
+ *   pe_slab_boundary  fills this rank's exchange buffer (pe_slab_exchange_bytes(cap_blobs, cap_plane) bytes): per sign the
+ *                     local blob count, every blob's smallest key in the WHOLE map's canonical order and the (column, row,
+ *                     blob) voxels of the slab's first and last section (last_is_cut = 0 for the top slab);
+ *   the caller all-gathers the world's buffers into d_gathered (rank-major) -- the halo exchange;
+ *   pe_slab_merge     26-adjacency across every cut -> union-find over all ranks' blobs -> d_new_number[k*cap_blobs + b] =
+ *                     the whole-map blob number of this rank's local blob b of sign k, d_n_merged[k] = blobs of the whole map;
+ *   pe_slab_relabel   rewrites d_label in place and accumulates this rank's part of the per-blob sums (layout of
+ *                     pe_blob_label's d_stats, cap_merged rows per sign) with the whole map's geometry; the caller
+ *                     all-reduces the table.
+ * d_ws: >= pe_slab_workspace_bytes(world, cap_blobs, u0, u1), shared by the three calls; pe_slab_status reads its overflow
+ * flag (synchronises). */
+int64_t pe_slab_exchange_bytes(int64_t cap_blobs, int64_t cap_plane);
+int64_t pe_slab_workspace_bytes(int32_t world, int64_t cap_blobs, int32_t u0, int32_t u1);
+int pe_slab_boundary(const pe_geom *g_slab, int32_t u2_whole, int32_t s0, int32_t last_is_cut, const int64_t *d_counts,
+                     int64_t cap_voxels, const uint32_t *d_key, const int32_t *d_label, int64_t cap_blobs, int64_t cap_plane,
+                     void *d_exchange, void *d_ws, void *stream);
+int pe_slab_merge(int32_t world, int32_t rank, const void *d_gathered, int64_t cap_blobs, int64_t cap_plane, int32_t u0,
+                  int32_t u1, int32_t *d_new_number, int64_t *d_n_merged, void *d_ws, void *stream);
+int pe_slab_relabel(const pe_geom *g_whole, int32_t u2_slab, int32_t s0, const int64_t *d_counts, int64_t cap_voxels,
+                    const uint32_t *d_key, const float *d_value, int32_t *d_label, int64_t cap_blobs,
+                    const int32_t *d_new_number, const int64_t *d_n_merged, int64_t cap_merged, double *d_stats, void *d_ws,
+                    void *stream);
+int pe_slab_status(const void *d_ws, void *stream, int32_t *bad);
+
 /* ---------------------------------------------------------------- voxel-list set algebra ------------------- */
 /* createCrsLists (pdb_eda/cutils.pyx:41-70) on an arbitrary list of n un-wrapped voxels (d_crs n x 3 int32):
  * d_label[i] = cluster number in the reference's creation order (by first unused input index).

@@ -5,17 +5,19 @@ The reference holds a whole map in one process and clusters with an N x N distan
 (the slowest-varying axis in memory, pdb_eda/ccp4.py:338) is cut into one slab per rank:
 
   1. every rank labels its slab with the same fused threshold + CCL kernels as a whole map (``pe_blob_label``);
-  2. ONE exchange step: the first-section plane of every slab (sparse: column, row, blob id) is all-gathered over
-     NVLink and each rank pairs its last plane with its successor's first plane (``pe_overlap_pairs``:
-     26-adjacency across the cut) -> equivalences between blob ids of neighbouring slabs;
-  3. the (small) equivalence list and the per-blob smallest canonical keys are all-gathered; every rank runs the
-     same min-id union and ranks the merged blobs by their smallest canonical (column-slowest) key, which is the
-     reference's blob order (pdb_eda/cutils.pyx:59-69, SURVEY.md App. A.5);
-  4. per-blob sums (DensityBlob.fromCrsList, pdb_eda/ccp4.py:522-545) are all-reduced.
+  2. ``pe_slab_boundary`` packs one exchange buffer per rank (blob counts, every local blob's smallest whole-map key, the
+     voxels of the slab's first and last section) and ONE ``all_gather`` moves them over NVLink -- the halo exchange;
+  3. ``pe_slab_merge`` (every rank, redundantly): 26-adjacency across each cut, union-find over all ranks' blobs, and the
+     whole-map number of each local blob by binary searches in the gathered key arrays -- the reference's blob order
+     (pdb_eda/cutils.pyx:59-69, SURVEY.md App. A.5) without a global sort;
+  4. ``pe_slab_relabel`` rewrites the labels and accumulates the per-blob sums (DensityBlob.fromCrsList,
+     pdb_eda/ccp4.py:522-545) with the whole map's geometry; ONE ``all_reduce`` completes them.
 
-Steps 3-4 are device-agnostic torch code over a handful of collectives, so they are tested on CPU with gloo;
-steps 1-2 are CUDA.  ``labelSlabsEmulated`` runs all "ranks" one after another on a single GPU (no kernel ever
-waits on another), which is how the merge is verified against the whole-map labelling on one device.
+Two collectives and one host synchronisation (to size the all-reduce) per call: ``SlabLabeller``.
+``labelSlabsEmulated`` runs all "ranks" one after another on a single GPU through the same kernels (no kernel ever waits
+on another), which is how the merge is verified against the whole-map labelling on one device.
+``mergeBlobIds`` / ``mergeDistributed`` state the same merge in device-agnostic torch with ragged all-gathers: the gloo
+tests on CPU run them, and they are what the CUDA merge replaced (5 collectives, 3 host round trips).
 """
 import ctypes
 
@@ -25,7 +27,8 @@ import torch.distributed as dist
 
 from . import _device
 from . import cutils as utils
-from ._lib import PeGeom
+from ._device import _ptr, _stream
+from ._lib import PeGeom, check
 
 
 def slabRanges(nSections, world):
@@ -46,48 +49,6 @@ def _slabGeom(full, s0, s1):
     g.ncrs[2] = s1 - s0
     g.unique_ncrs[2] = max(min(s1, u2) - s0, 1)
     return g
-
-
-class LocalSlab:
-    """What one rank knows after labelling its slab: per sign (0 green, 1 red) the foreground voxels with global
-    (c, r, s), value, local blob number, and the first-plane / last-plane voxels."""
-
-    def __init__(self, fullGeom, rhoSlab, s0, s1, cutPos, cutNeg):
-        self.s0, self.s1 = s0, s1
-        self.U = (fullGeom.unique_ncrs[0], fullGeom.unique_ncrs[1], fullGeom.unique_ncrs[2])
-        covered = min(s1, self.U[2]) - s0
-        self.parts = []
-        if covered <= 0:                       # the slab lies entirely in the repeated part of the map
-            dev = rhoSlab.device
-            for _ in range(2):
-                self.parts.append({"crs": torch.zeros((0, 3), dtype=torch.int64, device=dev), "value": torch.zeros(0, device=dev),
-                                   "label": torch.zeros(0, dtype=torch.int64, device=dev), "n_blobs": 0})
-            return
-        dm = _device.DeviceMap(_slabGeom(fullGeom, s0, s1), rhoSlab.reshape(-1))
-        for part in dm.blob_label(cutPos, cutNeg):
-            if part is None:
-                dev = rhoSlab.device
-                self.parts.append({"crs": torch.zeros((0, 3), dtype=torch.int64, device=dev), "value": torch.zeros(0, device=dev),
-                                   "label": torch.zeros(0, dtype=torch.int64, device=dev), "n_blobs": 0})
-                continue
-            crs = part["crs"].long().clone()
-            crs[:, 2] += s0
-            self.parts.append({"crs": crs, "value": part["value"], "label": part["label"].long(), "n_blobs": part["n_blobs"]})
-
-    def plane(self, k, section):
-        """(column, row, local blob number) of the sign-k foreground voxels in global section ``section``."""
-        p = self.parts[k]
-        sel = p["crs"][:, 2] == section
-        return torch.cat((p["crs"][sel][:, :2], p["label"][sel][:, None]), dim=1)
-
-    def minKeys(self, k):
-        """Smallest canonical key (c*U1 + r)*U2 + s of every local blob."""
-        p = self.parts[k]
-        key = (p["crs"][:, 0] * self.U[1] + p["crs"][:, 1]) * self.U[2] + p["crs"][:, 2]
-        out = torch.full((p["n_blobs"],), torch.iinfo(torch.int64).max, dtype=torch.int64, device=key.device)
-        if len(key):
-            out.scatter_reduce_(0, p["label"], key, reduce="amin")
-        return out
 
 
 def boundaryPairs(lastPlane, firstPlaneNext, offsetHere, offsetNext):
@@ -163,61 +124,164 @@ def mergeDistributed(nLocalBlobs, firstPlane, lastPlane, minKeys, pairFn=boundar
     return number[int(offsets[rank]):int(offsets[rank + 1])], nMerged
 
 
-def _stats(fullDev, crs, value, label, nBlobs):
-    """Per-blob n, sum rho, sum rho*xyz, sum xyz from global voxel coordinates (xyz by the pe_crs2xyz kernel)."""
-    stats = torch.zeros((nBlobs, 8), dtype=torch.float64, device=crs.device)
-    if len(crs):
-        xyz = fullDev.crs2xyz(crs.to(torch.int32))
-        d = value.double()
-        cols = torch.cat((torch.ones_like(d)[:, None], d[:, None], d[:, None] * xyz, xyz), dim=1)
-        stats.index_add_(0, label, cols)
-    return stats
+class SlabLabeller:
+    """One rank's side of the slab-decomposed labelling with every buffer pre-allocated; ``label`` can be called repeatedly
+    (e.g. on the slabs of successive maps of one geometry) without allocating.
+
+    ``fullHeader``: the whole map's DensityHeader; [s0, s1): this rank's sections; ``world`` / ``rank`` / ``group``: the
+    ranks that hold the slabs in section order (``group=None``: the default process group; ``world == 1`` needs none)."""
+
+    def __init__(self, fullHeader, s0, s1, world=1, rank=0, device=None, origin=None, group=None, capVoxels=None, capBlobs=None,
+                 capPlane=None):
+        from ._lib import load
+        self.lib = load()
+        _device.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.world, self.rank, self.group = int(world), int(rank), group
+        self.s0, self.s1 = int(s0), int(s1)
+        self.geom = _device.geom_from_header(fullHeader, origin)
+        U = (self.geom.unique_ncrs[0], self.geom.unique_ncrs[1], self.geom.unique_ncrs[2])
+        self.U = U
+        self.covered = max(min(self.s1, U[2]) - self.s0, 0)          # sections of the slab inside the unique volume
+        self.slabGeom = _slabGeom(self.geom, self.s0, self.s1)
+        nvox = U[0] * U[1] * max(self.covered, 1)
+        self.capVoxels = int(capVoxels or max(4096, nvox // 64))
+        self.capBlobs = int(capBlobs or max(1024, self.capVoxels // 4))
+        self.capPlane = int(capPlane or max(4096, U[0] * U[1] // 16))
+        self.capMerged = self.capBlobs * self.world
+        dev = self.device
+        self.counts = torch.zeros(5, dtype=torch.int64, device=dev)
+        self.key = torch.empty(2 * self.capVoxels, dtype=torch.int32, device=dev)
+        self.value = torch.empty(2 * self.capVoxels, dtype=torch.float32, device=dev)
+        self.labelBuf = torch.empty(2 * self.capVoxels, dtype=torch.int32, device=dev)
+        self.localStats = torch.empty((2 * self.capBlobs, 8), dtype=torch.float64, device=dev)
+        self.blobWs = torch.empty(max(int(self.lib.pe_blob_workspace_bytes(ctypes.byref(self.slabGeom), self.capVoxels)), 256),
+                                  dtype=torch.uint8, device=dev)
+        self.exchange = torch.zeros(int(self.lib.pe_slab_exchange_bytes(self.capBlobs, self.capPlane)), dtype=torch.uint8, device=dev)
+        self.gathered = torch.zeros(self.world * self.exchange.numel(), dtype=torch.uint8, device=dev) if self.world > 1 else self.exchange
+        self.mergeWs = torch.empty(int(self.lib.pe_slab_workspace_bytes(self.world, self.capBlobs, U[0], U[1])), dtype=torch.uint8,
+                                   device=dev)
+        self.newNumber = torch.zeros(2 * self.capBlobs, dtype=torch.int32, device=dev)
+        self.tail = torch.zeros(8, dtype=torch.int64, device=dev)    # [0:2] blobs of the whole map per sign
+        self.stats = torch.empty((2, self.capMerged, 8), dtype=torch.float64, device=dev)
+        self.hostTail = torch.zeros(13, dtype=torch.int64).pin_memory()
+
+    # ---- the stages; each only enqueues on torch's current stream ------------------------------------------------------
+    def _labelLocal(self, rhoSlab, cutPos, cutNeg):
+        if self.covered <= 0:                                        # the slab lies entirely in the repeated part of the map
+            self.counts.zero_()
+            return
+        rho = rhoSlab.reshape(-1)
+        check(self.lib.pe_blob_label(ctypes.byref(self.slabGeom), _ptr(rho), ctypes.c_float(float(np.float32(cutPos))),
+                                     ctypes.c_float(float(np.float32(cutNeg))), self.capVoxels, self.capBlobs, _ptr(self.counts),
+                                     _ptr(self.key), _ptr(self.value), _ptr(self.labelBuf), _ptr(self.localStats), _ptr(self.blobWs),
+                                     _stream()), "pe_blob_label")
+
+    def _boundary(self):
+        lastIsCut = 1 if (self.rank + 1 < self.world and self.s1 <= self.U[2]) else 0
+        check(self.lib.pe_slab_boundary(ctypes.byref(self.slabGeom), self.U[2], self.s0, lastIsCut, _ptr(self.counts), self.capVoxels,
+                                        _ptr(self.key), _ptr(self.labelBuf), self.capBlobs, self.capPlane, _ptr(self.exchange),
+                                        _ptr(self.mergeWs), _stream()), "pe_slab_boundary")
+
+    def _mergeAndRelabel(self, gathered):
+        check(self.lib.pe_slab_merge(self.world, self.rank, _ptr(gathered), self.capBlobs, self.capPlane, self.U[0], self.U[1],
+                                     _ptr(self.newNumber), _ptr(self.tail), _ptr(self.mergeWs), _stream()), "pe_slab_merge")
+        check(self.lib.pe_slab_relabel(ctypes.byref(self.geom), max(self.covered, 1), self.s0, _ptr(self.counts), self.capVoxels,
+                                       _ptr(self.key), _ptr(self.value), _ptr(self.labelBuf), self.capBlobs, _ptr(self.newNumber),
+                                       _ptr(self.tail), self.capMerged, _ptr(self.stats), _ptr(self.mergeWs), _stream()),
+              "pe_slab_relabel")
+
+    def _readCounts(self):
+        """The one host synchronisation: voxel / blob counts of this slab, blobs of the whole map, overflow flags."""
+        self.hostTail[:5].copy_(self.counts, non_blocking=True)
+        self.hostTail[5:13].copy_(self.tail, non_blocking=True)
+        bad = ctypes.c_int32(0)
+        check(self.lib.pe_slab_status(_ptr(self.mergeWs), _stream(), ctypes.byref(bad)), "pe_slab_status")
+        c = self.hostTail.tolist()
+        if c[4] or bad.value:
+            raise RuntimeError("slab labelling: a capacity was exceeded (voxels %d / %d of %d, blobs %d / %d of %d, plane %d)"
+                               % (c[0], c[2], self.capVoxels, c[1], c[3], self.capBlobs, self.capPlane))
+        return c
+
+    def _result(self, c, stats):
+        U, out = self.U, []
+        uslab = max(self.covered, 1)
+        for k in range(2):
+            nfg, nMerged = int(c[2 * k]), int(c[5 + k])
+            v0 = k * self.capVoxels
+            kk = self.key[v0:v0 + nfg].long() & 0xFFFFFFFF
+            colrow = kk // uslab
+            crs = torch.stack((colrow // U[1], colrow % U[1], kk % uslab + self.s0), dim=1)
+            out.append({"crs": crs, "value": self.value[v0:v0 + nfg], "label": self.labelBuf[v0:v0 + nfg].long(), "n_blobs": nMerged,
+                        "stats": stats[k][:nMerged]})
+        return out
+
+    def label(self, rhoSlab, cutPos, cutNeg):
+        """Labels this rank's slab (``rhoSlab``: float32 CUDA tensor of its sections) and merges across the ranks.  Returns per
+        sign a dict with this rank's voxels (global crs, value, whole-map blob number) and the all-reduced per-blob sums."""
+        self._labelLocal(rhoSlab, cutPos, cutNeg)
+        self._boundary()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.exchange, group=self.group)      # the halo exchange
+        self._mergeAndRelabel(self.gathered)
+        c = self._readCounts()
+        n0, n1 = int(c[5]), int(c[6])
+        if self.world > 1:
+            packed = torch.cat((self.stats[0, :n0], self.stats[1, :n1]))
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+            stats = (packed[:n0], packed[n0:])
+        else:
+            stats = (self.stats[0], self.stats[1])
+        return self._result(c, stats)
+
+
+_labellers = {}
 
 
 def labelSlabDistributed(fullHeader, rhoSlab, s0, s1, cutPos, cutNeg, origin=None, group=None):
-    """One rank's call: label this rank's slab [s0, s1) of the map and merge across ranks.  Returns per sign a dict with
-    this rank's voxels (global crs, value, global blob number) and the all-reduced per-blob statistics."""
-    geom = _device.geom_from_header(fullHeader, origin)
-    local = LocalSlab(geom, rhoSlab, s0, s1, cutPos, cutNeg)
-    fullDev = _device.DeviceMap(_slabGeom(geom, s0, s1), rhoSlab.reshape(-1))
-    fullDev.geom = geom                                         # coordinates use the whole map's geometry
-    out = []
-    for k in range(2):
-        p = local.parts[k]
-        number, nMerged = mergeDistributed(p["n_blobs"], local.plane(k, s0), local.plane(k, s1 - 1), local.minKeys(k), group=group)
-        label = number[p["label"]] if len(p["label"]) else p["label"]
-        stats = _stats(fullDev, p["crs"], p["value"], label, nMerged)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-        out.append({"crs": p["crs"], "value": p["value"], "label": label, "n_blobs": nMerged, "stats": stats})
-    return out
+    """One rank's call: label this rank's slab [s0, s1) of the map and merge across ranks (a cached ``SlabLabeller`` per
+    geometry).  Returns per sign a dict with this rank's voxels (global crs, value, global blob number) and the all-reduced
+    per-blob statistics."""
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    keyOf = (tuple(fullHeader.ncrs), tuple(fullHeader.crsStart), tuple(fullHeader.xyzInterval), int(s0), int(s1), world, rank,
+             rhoSlab.device.index, id(group))
+    lab = _labellers.get(keyOf)
+    if lab is None:
+        _labellers.clear()                       # one geometry at a time: the buffers of a 1024^3 slab are large
+        lab = _labellers[keyOf] = SlabLabeller(fullHeader, s0, s1, world, rank, rhoSlab.device, origin, group)
+    return lab.label(rhoSlab, cutPos, cutNeg)
 
 
 def labelSlabsEmulated(fullHeader, rho, world, cutPos, cutNeg, origin=None):
-    """All ranks of ``labelSlabDistributed`` executed one after another on ONE GPU (``rho``: the whole map on the device).
-    Returns per sign the complete voxel list in canonical order with global blob numbers and statistics."""
+    """All ranks of ``SlabLabeller.label`` executed one after another on ONE GPU (``rho``: the whole map on the device) through
+    the same kernels; the exchange buffers are concatenated instead of all-gathered and the partial sums added instead of
+    all-reduced.  Returns per sign the complete voxel list in canonical order with whole-map blob numbers and statistics."""
     geom = _device.geom_from_header(fullHeader, origin)
     ns, nr, nc = geom.ncrs[2], geom.ncrs[1], geom.ncrs[0]
     vol = rho.reshape(ns, nr, nc)
     ranges = slabRanges(ns, world)
-    locals_ = [LocalSlab(geom, vol[s0:s1].contiguous(), s0, s1, cutPos, cutNeg) for s0, s1 in ranges]
-    fullDev = _device.DeviceMap(geom, rho.reshape(-1))
+    labs = [SlabLabeller(fullHeader, s0, s1, world, r, rho.device, origin) for r, (s0, s1) in enumerate(ranges)]
+    for lab, (s0, s1) in zip(labs, ranges):
+        lab._labelLocal(vol[s0:s1].contiguous(), cutPos, cutNeg)
+        lab._boundary()
+    gathered = torch.cat([lab.exchange for lab in labs]) if world > 1 else labs[0].exchange
+    parts, total = [], None
+    for lab in labs:
+        lab._mergeAndRelabel(gathered)
+        c = lab._readCounts()
+        stats = lab.stats[:, :max(int(c[5]), int(c[6]), 1)].clone()
+        total = stats if total is None else total + stats
+        parts.append((lab, c))
     out = []
+    U = labs[0].U
     for k in range(2):
-        counts = [l.parts[k]["n_blobs"] for l in locals_]
-        offsets = np.concatenate(([0], np.cumsum(counts)))
-        pairs = [boundaryPairs(locals_[r].plane(k, ranges[r][1] - 1), locals_[r + 1].plane(k, ranges[r + 1][0]), int(offsets[r]),
-                               int(offsets[r + 1])) for r in range(world - 1)]
-        dev = rho.device
-        allPairs = torch.cat(pairs) if pairs else torch.zeros((0, 2), dtype=torch.int64, device=dev)
-        allKeys = torch.cat([l.minKeys(k) for l in locals_])
-        number, nMerged = mergeBlobIds(int(offsets[-1]), allPairs, allKeys)
-        crs = torch.cat([l.parts[k]["crs"] for l in locals_])
-        value = torch.cat([l.parts[k]["value"] for l in locals_])
-        label = torch.cat([number[l.parts[k]["label"] + int(offsets[r])] for r, l in enumerate(locals_)])
-        U = locals_[0].U
+        res = [lab._result(c, (total[0], total[1]))[k] for lab, c in parts]
+        crs = torch.cat([r["crs"] for r in res])
+        value = torch.cat([r["value"] for r in res])
+        label = torch.cat([r["label"] for r in res])
         key = (crs[:, 0] * U[1] + crs[:, 1]) * U[2] + crs[:, 2]
         order = torch.argsort(key)
-        crs, value, label = crs[order], value[order], label[order]
-        out.append({"crs": crs, "value": value, "label": label, "n_blobs": nMerged,
-                    "stats": _stats(fullDev, crs, value, label, nMerged), "n_pairs": int(len(allPairs))})
+        nLocal = sum(int(c[2 * k + 1]) for _, c in parts)
+        out.append({"crs": crs[order], "value": value[order], "label": label[order], "n_blobs": res[0]["n_blobs"],
+                    "stats": res[0]["stats"], "n_pairs": nLocal - res[0]["n_blobs"]})
     return out
