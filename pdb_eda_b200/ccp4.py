@@ -156,6 +156,13 @@ class DensityHeader(object):
         """xyz of voxel (0,0,0) (pdb_eda/ccp4.py:272-286)."""
         if self.futureUse[-3] == 0.0 and self.futureUse[-2] == 0.0 and self.futureUse[-1] == 0.0:
             return np.dot(self.orthoMat, [self.crsStart[self.map2xyz[i]] / self.xyzInterval[i] for i in range(3)])
+        # The reference keeps this branch's origin as a Python LIST, so that `origin + [r, r, r]` in getSphereCrsFromXyz
+        # (pdb_eda/cutils.pyx:239) concatenates instead of adding and every sphere collapses to a 2-voxel-wide box (and
+        # raises in skewed cells): a latent bug (SURVEY.md App. A.8) that this library does NOT reproduce -- spheres on such
+        # maps are enumerated with their real radius.  DESIGN.md section 4 records the deviation.
+        import warnings
+        warnings.warn("CCP4 header carries a non-zero EM origin (words 50-52): the reference's sphere enumeration degenerates on "
+                      "such maps (pdb_eda/cutils.pyx:239); this library uses the real sphere radius", stacklevel=3)
         return [self.originEM[i] for i in range(3)]
 
     @property

@@ -240,8 +240,10 @@ def runMultipleStructures(items, loader, costs=None, atomTypes=None, device=None
 class OptimizeService:
     """The inner loop of parameter optimisation as a persistent service (pdb_eda/optimizeParams.py:341-448): the reference
     re-downloads nothing but re-parses and re-analyses every entry in a fresh Pool task per iteration; here every rank
-    loads its share of the structures ONCE, the maps stay resident in HBM, and an iteration only changes the radii table
-    (``setGlobals``) and re-runs the cloud aggregation on the GPU, followed by the two collectives of ``gatherResults``."""
+    loads its share of the structures ONCE, the maps stay resident in HBM and the atoms on the device as one ``PoolShard``;
+    an iteration only uploads the new radii / slopes and re-runs the batched cloud aggregation on the GPU, followed by the
+    two collectives of ``gatherPacked``.  Structures the batched layout cannot express (``AtomTable.supported`` false) make
+    the service fall back to ``DensityAnalysis.aggregateCloud`` per structure."""
 
     def __init__(self, items, loader, costs=None, device=None, group=None):
         self.group = group
@@ -258,6 +260,27 @@ class OptimizeService:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self.device = device
+        self.shard = None
+        self._names = None
+
+    def _shardFor(self, params):
+        """The device-resident shard; rebuilt only when the set of known atom names changes (never during an optimisation)."""
+        from .cloudBatch import AtomTable
+        names = frozenset(params["full_atom_name_map_atom_type"])
+        if self.shard is None or names != self._names:
+            entries = []
+            for idx, analyzer in self.analyzers.items():
+                if not analyzer:
+                    continue
+                table = AtomTable.fromStructure(analyzer.biopdbObj, params)
+                if not table.supported:
+                    return None
+                entries.append((idx, analyzer.densityObj, table))
+            self.shard = PoolShard(entries, params, device=self.device)
+            self._names = names
+        else:
+            self.shard.setRadii(params)
+        return self.shard
 
     def evaluate(self, params):
         """One optimiser iteration: (medianDiffs, meanDiffs, overallStdDevDiffs, medianSlopes, sizeDiffs,
@@ -265,6 +288,13 @@ class OptimizeService:
         from . import densityAnalysis
         densityAnalysis.setGlobals(params)
         types = list(params["radii"])
+        shard = self._shardFor(params) if torch.cuda.is_available() else None
+        if shard is not None:
+            s = shard.analyze(self.device, self.group, optimizer=True)
+            order = {t: k for k, t in enumerate(types)}                         # the shard keeps its types sorted
+            pick = lambda d: {t: d[t] for t in sorted(d, key=lambda t: order.get(t, 0))}
+            return (pick(s["medianDiffs"]), pick(s["meanDiffs"]), s["overallStdDevDiffs"], s["medianSlopes"], pick(s["sizeDiffs"]),
+                    pick(s["atomTypeOverlapCompleteness"]))
         results = {}
         for idx, analyzer in self.analyzers.items():
             if not analyzer:
@@ -272,7 +302,7 @@ class OptimizeService:
                 continue
             analyzer.resetCloud()
             try:
-                results[idx] = analyzeStructure(analyzer, types)
+                results[idx] = analyzeStructure(analyzer, types, optimizer=True)
             except Exception:
                 results[idx] = 0
         s = gatherResults(results, self.mine, self.n, types, self.device, self.group)

@@ -203,6 +203,36 @@ def test_rscc_rsr_metrics(pair):
     assert np.array_equal(np.asarray(m.fc.density), r.fc.density)
 
 
+def test_blue_blob_list(pair):
+    """blueBlobList: createFullBlobList(mean + 1.5 sigma) on the 2Fo-Fc map (pdb_eda/densityAnalysis.py:414-423) -- dense
+    foreground (the reference warns that it "uses a LOT OF MEMORY at 1.5sd", pdb_eda/singleStructure.py:30)."""
+    r, m = pair
+    rb, mb = r.blueBlobList, m.blueBlobList
+    assert len(rb) == len(mb) > 10
+    assert all(p.crsList == q.crsList for p, q in zip(rb, mb))                       # membership and order
+    gc.close([q.totalDensity for q in mb], [p.totalDensity for p in rb], rtol=1e-9)
+    gc.close([q.volume for q in mb], [p.volume for p in rb], rtol=1e-12)
+    gc.close([q.centroid for q in mb], [p.centroid for p in rb], rtol=1e-9, atol=1e-9)
+
+
+def test_fc_object_and_single_coordinate_regions(pair):
+    """the public ``fc`` attribute answers the calls the reference's deep copy answers, and the region methods
+    accept a single flat coordinate like findAberrantBlobs does (pdb_eda/ccp4.py:453)."""
+    r, m = pair
+    for crs in ([3, 4, 5], [-2, 70, 1], [10 ** 3, 0, 0]):
+        assert float(m.fc.getPointDensityFromCrs(crs)) == float(r.fc.getPointDensityFromCrs(crs))
+    cut = r.densityObj.densityCutoff
+    gc.close(m.fc.getTotalAbsDensity(cut), r.fc.getTotalAbsDensity(cut), rtol=1e-9)
+    assert m.fc.meanDensity == m.densityObj.meanDensity
+    blobs_r = r.fc.findAberrantBlobs(list(r.asymmetryAtoms[5].coord), 2.0, cut)
+    blobs_m = m.fc.findAberrantBlobs(list(m.asymmetryAtoms[5].coord), 2.0, cut)
+    assert len(blobs_r) == len(blobs_m)                                              # float32-narrowed Fc on the device: counts agree,
+    gc.close(sorted(b.totalDensity for b in blobs_m), sorted(b.totalDensity for b in blobs_r), rtol=1e-5)   # sums to float32 accuracy
+    one = [float(v) for v in m.asymmetryAtoms[7].coord]
+    gc.close(m.calculateRegionDensity(one, 2.5), r.calculateRegionDensity(one, 2.5), rtol=1e-9, atol=1e-12)
+    gc.close(m.calculateRegionDiscrepancy(one, 2.5), r.calculateRegionDiscrepancy(one, 2.5), rtol=1e-9, atol=1e-12)
+
+
 def test_from_pdbid_uses_the_cache(pair, tmp_path, monkeypatch):
     """fromPDBid with the files already in ./ccp4_data and ./pdb_data (no network), pdb_eda/densityAnalysis.py:88-179."""
     import gzip

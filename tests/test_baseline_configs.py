@@ -1,0 +1,193 @@
+"""GPU tier: BASELINE.json's configurations at their full sizes.
+
+  C1  96^3 P2(1)2(1)2(1), 2,500 atoms: every public call against the LIVE reference (oracle/_ref on the box's host CPU)
+  C4  1024^3 Fo-Fc: whole-map labelling against scipy.ndimage.label renumbered by first voxel in createFullCrsList order,
+      and the slab-decomposed labelling (all ranks emulated on one GPU through the CUDA merge) against the whole map
+  C5  hexagonal P6(5)22 cell, 120 x 120 x 240 intervals, 2,000 atoms: symmetry atoms, atom-mask region density,
+      atom-to-blob distances against the live reference
+(C2 at 384^3 / 40,000 atoms is in test_cuda_vs_oracle.py::test_sphere_properties_at_scale and the blob tests there; C3 in
+test_cloud_batch.py and test_multi_vs_reference.py.)
+Bars: counts, voxel sets, labels, orders bit-exact; float64 values within 1e-9 relative.
+"""
+import io
+
+import numpy as np
+import pytest
+
+import golden_checks as gc
+from pdb_eda_b200 import structure, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(ref, st, n, cell, sg, seed):
+    """(reference DensityAnalysis, this package's) on the same synthetic inputs, identical float32-narrowed cutoffs."""
+    ref_ccp4, ref_da, ref_cutils, ref_pp = ref
+    from pdb_eda_b200 import densityAnalysis
+    d1, d2 = synthetic.mapPair(st, n, cell, seed=seed)
+    b1, b2 = synthetic.ccp4Bytes(d1, cell, n), synthetic.ccp4Bytes(d2, cell, n)
+    text = structure.formatPDB(st, remark290=synthetic.cartesianOperators(sg, cell), cell=cell, spaceGroup=sg)
+    densityAnalysis.setGlobals(ref_da.paramsGlobal)
+    dens, diff = ref_ccp4.parse(io.BytesIO(b1), "t"), ref_ccp4.parse(io.BytesIO(b2), "t")
+    dens.densityCutoff = dens.meanDensity + 1.5 * dens.stdDensity
+    diff.diffDensityCutoff = diff.meanDensity + 3 * diff.stdDensity
+    r = ref_da.DensityAnalysis("t", dens, diff, st, ref_pp.readPDBfile(io.StringIO(text)))
+    m = densityAnalysis.fromFile(io.StringIO(text), io.BytesIO(b1), io.BytesIO(b2))
+    assert m != 0
+    m.densityObj.densityCutoff, m.diffDensityObj.diffDensityCutoff = dens.densityCutoff, diff.diffDensityCutoff
+    return r, m
+
+
+def _rows_close(mine, theirs, nExact):
+    assert len(mine) == len(theirs)
+    for x, y in zip(mine, theirs):
+        assert list(x[:nExact]) == list(y[:nExact])
+        for u, v in zip(x[nExact:], y[nExact:]):
+            if isinstance(u, (bool, np.bool_, str, tuple)):
+                assert u == v
+            else:
+                gc.close(np.asarray(u, dtype=np.float64), np.asarray(v, dtype=np.float64), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.timeout(900)
+def test_c1_full_size_against_the_live_reference(ref):
+    """BASELINE.json configs[0]: single-structure mode on a 96^3 P2(1)2(1)2(1) map pair with a 2,500-atom structure."""
+    n, cell = (96, 96, 96), (48.0, 48.0, 48.0, 90, 90, 90)
+    st = synthetic.polyAlaStructure(500, (0, 0, 0), cell[:3], seed=1, residuesPerChain=250)
+    r, m = _pair(ref, st, n, cell, "P 21 21 21", 7)
+    assert len(list(m.biopdbObj.get_atoms())) == 2500
+    r.aggregateCloud()
+    m.aggregateCloud()
+    assert r.numVoxelsAggregated == m.numVoxelsAggregated > 20000
+    gc.close([m.densityElectronRatio, m.totalAggregatedDensity, m.totalAggregatedElectrons],
+             [r.densityElectronRatio, r.totalAggregatedDensity, r.totalAggregatedElectrons], rtol=1e-9)
+    assert dict(r.atomTypeOverlapCompleteness) == dict(m.atomTypeOverlapCompleteness)
+    assert dict(r.atomTypeOverlapIncompleteness) == dict(m.atomTypeOverlapIncompleteness)
+    _rows_close(m.residueCloudDescriptions, r.residueCloudDescriptions, 3)
+    _rows_close(m.domainCloudDescriptions, r.domainCloudDescriptions, 3)
+    assert len(r.atomCloudDescriptions) == len(m.atomCloudDescriptions) > 2000
+    assert np.array_equal(r.atomCloudDescriptions["num_voxels"], m.atomCloudDescriptions["num_voxels"])
+    for column in r.medians:
+        gc.close([m.medians[column][t] for t in r.medians[column]], [r.medians[column][t] for t in r.medians[column]], rtol=1e-9, atol=1e-9)
+    for rb, mb in ((r.greenBlobList, m.greenBlobList), (r.redBlobList, m.redBlobList)):
+        assert len(rb) == len(mb) > 100
+        assert all(p.crsList == q.crsList for p, q in zip(rb, mb))                      # membership and blob order
+        gc.close([q.totalDensity for q in mb], [p.totalDensity for p in rb], rtol=1e-9)
+    rs, ms = r.symmetryAtoms, m.symmetryAtoms
+    assert [a.symmetry for a in rs] == [a.symmetry for a in ms] and len(rs) > 10000
+    gc.close(m.symmetryAtomCoords, r.symmetryAtomCoords, rtol=1e-12, atol=1e-10)
+    blobs_r, blobs_m = r.greenBlobList + r.redBlobList, m.greenBlobList + m.redBlobList
+    _rows_close([row[:10] for row in m.calculateAtomSpecificBlobStatistics(blobs_m)],
+                [row[:10] for row in r.calculateAtomSpecificBlobStatistics(blobs_r)], 0)
+    mask = {"ALA": ["N", "CA", "C"]}
+    # the reference needs ~0.17 s per residue at 3.5 A: the first 120 residues through the public method via its type-free path
+    sub = lambda an: [res for k, res in enumerate(an.biopdbObj.get_residues()) if k < 120]
+    _rows_close(m.calculateResidueRegionDensity(3.5, 1.5, "", mask)[:120], _residue_density(r, sub(r), 3.5, 1.5, mask), 4)
+    _rows_close(m.calculateResidueRegionDiscrepancies(3.5, 3.0, "ALA", mask)[:120], _residue_discrepancy(r, sub(r), 3.5, 3.0, mask), 4)
+
+
+def _residue_density(an, residues, radius, numSD, atomMask):
+    """calculateResidueRegionDensity of the reference restricted to some residues (pdb_eda/densityAnalysis.py:1019-1034)."""
+    results = []
+    for residue in residues:
+        atoms = [atom for atom in residue.get_atoms() if not atomMask or residue.resname not in atomMask or atom.name in atomMask[residue.resname]]
+        if atoms:
+            result = an.calculateRegionDensity([atom.coord for atom in atoms], radius, numSD)
+            results.append([residue.parent.parent.id, residue.parent.id, residue.id[1], residue.resname,
+                            np.mean([atom.get_occupancy() for atom in atoms])] + result)
+    return results
+
+
+def _residue_discrepancy(an, residues, radius, numSD, atomMask):
+    """calculateResidueRegionDiscrepancies of the reference restricted to some residues (pdb_eda/densityAnalysis.py:1148-1157)."""
+    results = []
+    for residue in residues:
+        atoms = [atom for atom in residue.get_atoms() if not atomMask or (residue.resname in atomMask and atom.name in atomMask[residue.resname])]
+        result = an.calculateRegionDiscrepancy([atom.coord for atom in atoms], radius, numSD)
+        results.append([residue.parent.parent.id, residue.parent.id, residue.id[1], residue.resname,
+                        np.mean([atom.get_occupancy() for atom in atoms])] + result)
+    return results
+
+
+@pytest.mark.timeout(900)
+def test_c5_symmetry_heavy_hexagonal_cell(ref):
+    """BASELINE.json configs[4]: P6(5)22, cell 60 x 60 x 120 A (gamma = 120), 120 x 120 x 240 intervals, 2,000 atoms:
+    324 images per atom, atom-mask density around the residues, blob distances over the generated symmetry atoms."""
+    n, cell = (120, 120, 240), (60.0, 60.0, 120.0, 90, 90, 120)
+    omat = synthetic.orthoMatrix(cell)
+    lo, hi = omat @ np.array([0.3, 0.3, 0.1]), omat @ np.array([0.6, 0.7, 0.9])
+    lo, hi = np.minimum(lo, hi), np.maximum(lo, hi)
+    st = synthetic.polyAlaStructure(400, lo - 3, hi + 3, seed=9, residuesPerChain=100)
+    r, m = _pair(ref, st, n, cell, "P 65 2 2", 13)
+    assert len(r.pdbObj.header.rotationMats) == 12
+    rs, ms = r.symmetryAtoms, m.symmetryAtoms
+    assert len(rs) == len(ms) > 20000
+    assert [a.symmetry for a in rs] == [a.symmetry for a in ms]
+    assert [(a.name, a.parent.id) for a in rs] == [(a.name, a.parent.id) for a in ms]
+    gc.close(m.symmetryAtomCoords, r.symmetryAtomCoords, rtol=1e-12, atol=1e-10)
+    r.aggregateCloud()
+    m.aggregateCloud()
+    assert r.numVoxelsAggregated == m.numVoxelsAggregated
+    gc.close(m.densityElectronRatio, r.densityElectronRatio, rtol=1e-9)
+    blobs_r, blobs_m = r.greenBlobList + r.redBlobList, m.greenBlobList + m.redBlobList
+    assert len(blobs_r) == len(blobs_m) > 1000
+    assert all(p.crsList == q.crsList for p, q in zip(blobs_r, blobs_m))
+    _rows_close([row[:10] for row in m.calculateAtomSpecificBlobStatistics(blobs_m)],
+                [row[:10] for row in r.calculateAtomSpecificBlobStatistics(blobs_r)], 0)
+    mask = {"ALA": ["N", "CA", "C"]}
+    sub = [res for k, res in enumerate(r.biopdbObj.get_residues()) if k < 80]
+    _rows_close(m.calculateResidueRegionDensity(3.5, 1.5, "", mask)[:80], _residue_density(r, sub, 3.5, 1.5, mask), 4)
+    # symmetry-atom variant (fully-within-map flag, testValidXyzList) on the first images
+    mine = m.calculateSymmetryAtomRegionDensity(2.0, 1.5, "CA")
+    theirs = _symmetry_density(r, [a for a in r.symmetryAtoms if a.name == "CA"][:150], 2.0, 1.5)
+    _rows_close([row[:6] + row[7:] for row in mine[:150]], [row[:6] + row[7:] for row in theirs], 6)
+    gc.close(np.array([np.asarray(row[6], dtype=np.float64) for row in mine[:150]]),
+             np.array([np.asarray(row[6], dtype=np.float64) for row in theirs]), rtol=1e-12, atol=1e-10)
+
+
+def _symmetry_density(an, atoms, radius, numSD):
+    """calculateSymmetryAtomRegionDensity of the reference on some atoms (pdb_eda/densityAnalysis.py:988-998)."""
+    results = []
+    for atom in atoms:
+        result, valid = an.calculateRegionDensity([atom.coord], radius, numSD, testValidCrs=True)
+        results.append([atom.parent.parent.parent.id, atom.parent.parent.id, atom.parent.id[1], atom.parent.resname, atom.name, atom.symmetry,
+                        atom.coord, valid] + result)
+    return results
+
+
+@pytest.mark.timeout(900)
+def test_c4_1024_cubed_labelling_and_slabs():
+    """BASELINE.json configs[3] at full size: +-3 sigma blobs of a 1024^3 map."""
+    import scipy.ndimage as ndi
+    import torch
+    from pdb_eda_b200 import _device, ccp4, slab
+    n = 1024
+    vol = synthetic.smoothNoiseMapDevice(n, seed=4)
+    hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), (n * 0.5,) * 3 + (90, 90, 90), (n, n, n)))
+    whole = _device.DeviceMap(_device.geom_from_header(hdr), vol.reshape(-1)).blob_label(3.0, -3.0)
+    assert whole[0]["n_blobs"] > 300000 and whole[1]["n_blobs"] > 300000
+    # (1) the slab path (4 ranks emulated on this GPU through pe_slab_boundary / merge / relabel) against the whole map
+    parts = slab.labelSlabsEmulated(hdr, vol, 4, 3.0, -3.0)
+    for w, p in zip(whole, parts):
+        assert p["n_pairs"] > 0
+        assert torch.equal(w["crs"].long(), p["crs"]) and torch.equal(w["label"].long(), p["label"]) and w["n_blobs"] == p["n_blobs"]
+        gc.close(p["stats"].cpu().numpy(), w["stats"].cpu().numpy(), rtol=1e-9, atol=1e-9)
+    del parts
+    # (2) the green blobs against scipy.ndimage.label (26-connectivity), renumbered by first voxel in createFullCrsList order
+    host = vol.cpu().numpy()
+    del vol
+    torch.cuda.empty_cache()
+    mask = np.ascontiguousarray((host >= np.float32(3.0)).transpose(2, 1, 0))          # [c][r][s]: C order = createFullCrsList order
+    del host
+    lab, nlab = ndi.label(mask, structure=np.ones((3, 3, 3), dtype=bool))
+    flat = lab[mask]
+    part = whole[0]
+    assert part["n_voxels"] == flat.size and part["n_blobs"] == nlab
+    _, first = np.unique(flat, return_index=True)
+    remap = np.empty(nlab + 1, dtype=np.int64)
+    remap[1 + np.argsort(first)] = np.arange(nlab)
+    assert np.array_equal(part["label"].cpu().numpy().astype(np.int64), remap[flat])
+    key = np.flatnonzero(mask.reshape(-1))
+    crs = part["crs"].cpu().numpy().astype(np.int64)
+    assert np.array_equal((crs[:, 0] * n + crs[:, 1]) * n + crs[:, 2], key)
+    assert np.array_equal(np.bincount(remap[flat], minlength=nlab), part["stats"][:, 0].cpu().numpy().astype(np.int64))

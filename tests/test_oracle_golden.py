@@ -58,3 +58,19 @@ def test_symmetry_and_nearest(case):
     gold, dm, impl = case
     gc.check_symmetry(gold, impl, dm)
     gc.check_nearest(gold, impl)
+
+
+def test_em_origin_is_flagged():
+    """A header with non-zero words 47-49 takes the reference's originEM branch (pdb_eda/ccp4.py:281-284), on which its sphere
+    enumeration degenerates; the loader says so instead of reproducing the bug silently."""
+    import struct
+    import warnings
+    from pdb_eda_b200 import ccp4, synthetic
+    raw = bytearray(synthetic.ccp4Header((8, 8, 8), (4.0, 4.0, 4.0, 90, 90, 90), (8, 8, 8)))
+    struct.pack_into("<3f", raw, 4 * 46, 1.0, 1.0, 1.0)        # futureUse[-3:]
+    struct.pack_into("<3f", raw, 4 * 49, 2.0, 3.0, 4.0)        # originEM
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        hdr = ccp4.DensityHeader.fromFileHeader(bytes(raw))
+    assert isinstance(hdr.origin, list) and hdr.origin == [2.0, 3.0, 4.0]
+    assert any("EM origin" in str(w.message) for w in caught)
