@@ -127,6 +127,9 @@ int64_t pe_sphere_workspace_bytes(int64_t n_atoms);
  * over all CTAs since the last call; synchronises and resets.  All zeros unless the library was built with
  * -DPE_UNION_PHASE_CYCLES=1 (the counters cost the kernel registers). */
 int pe_sphere_union_cycles(unsigned long long *out4);
+/* The same for the warp-per-group kernel (the default): boxes + bounding box, tile offsets + per-atom tables, membership,
+ * gather, reduction + output; zeros unless built with -DPE_UNION_PHASE_CYCLES=1. */
+int pe_sphere_union_warp_cycles(unsigned long long *out5);
 int pe_sphere_sums(const pe_geom *g, const float *d_rho, int32_t n_atoms, const double *d_xyz,
                    const float *d_radius, int32_t n_groups, const int32_t *d_group_start, float cut_pos,
                    float cut_neg, double *d_out, void *d_ws, void *stream);

@@ -124,4 +124,119 @@ __device__ __forceinline__ void for_each_inside(const pe_geom &g, const float *_
 // Density predicate of getSphereCrsFromXyz (pdb_eda/cutils.pyx:245); all operands are exact float32 values.
 __device__ __forceinline__ bool passes(float v, float cut) { return (0.f < cut && cut < v) || (v < cut && cut < 0.f) || cut == 0.f; }
 
+// float -> double widening.  An integer-pipe bit-twiddling version was tried when F2F.F64.F32 showed up as the top
+// stall of the first capture (profiles/r01a_first_path.md); once the gather loops kept four independent loads in
+// flight the plain conversion (one issue slot, its latency hidden) became the faster one again: 257 -> 231 us on
+// the C2 region pass.
+__device__ __forceinline__ double widen(float v) { return (double)v; }
+
+// Effective cutoffs: a class whose cutoff is 0 is switched off by an unreachable threshold.
+__device__ __forceinline__ float eff_pos(float cp) { return cp > 0.f ? cp : __int_as_float(0x7f800000); }
+__device__ __forceinline__ float eff_neg(float cn) { return cn < 0.f ? cn : __int_as_float(0xff800000); }
+
+struct SphereAcc {
+    int n_all = 0, n_pos = 0, n_neg = 0, bad = 0;
+    double s_all = 0.0, s_pos = 0.0, s_neg = 0.0;
+    // v must be 0 when the voxel is not taken; cp / cn are the effective cutoffs (cp > 0 > cn).
+    __device__ __forceinline__ void add(bool take, float v, float cp, float cn) {
+        const double d = widen(v);
+        s_all += d;
+        if (take) ++n_all;
+        if (v > cp) {
+            ++n_pos;
+            s_pos += d;
+        }
+        if (v < cn) {
+            ++n_neg;
+            s_neg += d;
+        }
+    }
+    // the same with the negative class switched off (cn == -inf): a third less work per voxel
+    __device__ __forceinline__ void add_pos(bool take, float v, float cp) {
+        const double d = widen(v);
+        s_all += d;
+        if (take) ++n_all;
+        if (v > cp) {
+            ++n_pos;
+            s_pos += d;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ exact chords
+// MODE 0: z is carried by the row axis, 1: by the section axis, 2: by the column axis.
+// Squared distance of column k of a box row exactly as the reference adds it: fl(fl(X2 + Y2) + Z2).
+template <int MODE>
+__device__ __forceinline__ bool row_pred(const double *sqc, int k, double A, double B, double T) {
+    // MODE 0/1: A = square of the non-z axis among (row, section), B = square of the z axis;
+    // MODE 2  : A = fl(row square + section square), the column carries z.
+    const double d2 = (MODE == 2) ? __dadd_rn(A, sqc[k]) : __dadd_rn(__dadd_rn(sqc[k], A), B);
+    return d2 <= T;
+}
+
+// In-sphere columns [kl, kh] of one box row, exactly.  Along the columns of a box row the squared distance falls to the
+// column nearest the atom (km) and rises again (every rounding step is monotone), so the in-sphere columns are one
+// interval around that column.  The interval is GUESSED in float32 from the chord of the sphere along the row
+// (half-width sqrt(T - A - B) in columns around the atom's fractional column xc) and then VERIFIED with the exact
+// float64 predicate: inside at kl and kh, outside at kl - 1 and kh + 1 -- four independent tests that, by unimodality,
+// prove the guess.  A guess that fails (an end within ~1e-5 columns of a grid point, or a row that only just misses the
+// sphere) falls back to two binary searches with the same exact predicate.  Rows that miss the sphere leave after one
+// exact test without touching the table: every rounding step is monotone and the column term is >= 0, so
+// d2 >= fl(A + B) for every column of the row.  Returns false when no column of the row is inside.
+// 1 / sqrt(x) for the chord guess only: the bare MUFU.RSQ (rsqrtf() wraps it in denormal scaling, six more instructions
+// per box row; a denormal remainder just yields a guess that the exact tests reject)
+__device__ __forceinline__ float rsqrt_guess(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool row_chord(const double *sqc, int nC, int km, float xc, float inv_gl, double A, double B, double T,
+                                          int &kl, int &kh) {
+    const double AB = (MODE == 2) ? A : __dadd_rn(A, B);
+    if (!(AB <= T)) return false;  // exact: the row misses the sphere
+    const float rem = (float)__dsub_rn(T, AB);
+    const float h = rem > 0.f ? rem * rsqrt_guess(rem) * inv_gl : 0.f;
+    const float xl = xc - h, xr = xc + h;
+    const float fl_ = ceilf(xl), fr_ = floorf(xr);
+    // The float32 guess is within 2e-5 columns of the real chord ends (|xc|, h <= 64 columns; rsqrt.approx 2^-22 relative), and the
+    // reference's rounded float64 predicate moves an end by less than 1e-8 columns once the half chord exceeds 1e-6 columns.  So
+    // when both guessed ends are more than kChordEps away from every grid point the interval is PROVEN without evaluating the
+    // predicate (the exact tests below only run for the ~0.1 % of ends that fall within kChordEps of a column).
+    constexpr float kChordEps = 2.5e-4f;
+    if (h > 0.01f && fl_ - xl > kChordEps && xl - (fl_ - 1.f) > kChordEps && xr - fr_ > kChordEps && (fr_ + 1.f) - xr > kChordEps) {
+        kl = max((int)fl_, 0);
+        kh = min((int)fr_, nC - 1);
+        return kl <= kh;
+    }
+    kl = min(max((int)fl_, 0), km);
+    kh = max(min((int)fr_, nC - 1), km);
+    const bool in_l = row_pred<MODE>(sqc, kl, A, B, T), in_h = row_pred<MODE>(sqc, kh, A, B, T);
+    const bool out_l = kl == 0 || !row_pred<MODE>(sqc, kl - 1, A, B, T);
+    const bool out_h = kh == nC - 1 || !row_pred<MODE>(sqc, kh + 1, A, B, T);
+    if (in_l && in_h && out_l && out_h) return true;
+    if (!row_pred<MODE>(sqc, km, A, B, T)) return false;  // the row misses the sphere
+    int lo = 0, hi = km;  // smallest k in [0, km] inside
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (row_pred<MODE>(sqc, mid, A, B, T))
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    kl = lo;
+    lo = km;
+    hi = nC - 1;  // largest k in [km, nC) inside
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (row_pred<MODE>(sqc, mid, A, B, T))
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    kh = lo;
+    return true;
+}
+
 }  // namespace pe

@@ -62,3 +62,9 @@ _lib.load().pe_sphere_union_cycles(u)
 tot = float(sum(u)) or 1.0
 if sum(u):  # only when the library was built with -DPE_UNION_PHASE_CYCLES=1
     print("union kernel cycles by phase (prologue, membership, gather, epilogue): %s" % [round(x / tot, 3) for x in u])
+u = (ctypes.c_ulonglong * 5)()
+_lib.load().pe_sphere_union_warp_cycles(u)
+if sum(u):
+    tot = float(sum(u))
+    print("warp-per-group union kernel, warp cycles by phase (boxes, offsets + tables, membership, gather, reduce): %s; "
+          "cycles per group %.0f" % ([round(x / tot, 3) for x in u], tot / (13 + steps * 2) / nres))
