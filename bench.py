@@ -197,6 +197,101 @@ def run_cpu_sample(steps, warmup):
     return value, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}, total / len(times) * 1e3
 
 
+WORK_C2 = {
+    "cloud": {"b200": "pe_sphere_sums per atom: sphere enumeration + wrapped density gather + sums (all, > cutoff, < -cutoff), valid flag",
+              "reference": "DensityMatrix.findAberrantBlobs(atom.coord, radius, cutoff): the same enumeration and gather, then 26-connected "
+                           "clustering of the voxels into DensityBlobs (centroids, totals) -- more than the B200 leg; ~1 % of the reference's step"},
+    "region": {"b200": "pe_sphere_sums per residue (set-union of its atoms' 3.5 A spheres): sums, counts, valid flag",
+               "reference": "DensityMatrix.findAberrantBlobs(list of coords, 3.5, cutoff): set-union enumeration + clustering into blobs, whose "
+                            "totals the caller adds up (calculateRegionDensity) -- the sum is what both legs deliver"},
+    "blobs": {"b200": "pe_blob_label: +-cutoff threshold of the whole Fo-Fc map, 26-connected labelling in createCrsLists order, per-blob sums",
+              "reference": "createFullBlobList(+cutoff) and createFullBlobList(-cutoff): createFullCrsList + createCrsLists (N x N cdist) + "
+                           "DensityBlob.fromCrsList"}}
+
+
+def reference_c1_full_pass(ref_mods):
+    """BASELINE.json configs[0] at full size through the reference's public methods, once: 96^3 P2(1)2(1)2(1), 2,500 atoms."""
+    work = build_workload(dict(n=96, cell=48.0, residues=500), seed=1)
+    units = sum(oracle_units(work))
+    dt, counts = reference_step(ref_mods, work)
+    return {"workload": "C1: 96^3 map pair, 2,500 atoms / 500 residues; cloud + region (3.5 A) + green/red blobs, one pass", "seconds": round(dt, 2),
+            "units": units, "value": units / dt, "unit": UNIT, "cores": 1, "green_red_blobs": [counts[2], counts[3]]}
+
+
+# ---- config 3 on the host: the reference's multiple-structures mode on a bounded sample of the pool, all host cores
+_REF_C3 = {}
+
+
+def _ref_c3_init():
+    from oracle import refload
+    _REF_C3["mods"] = refload.load()
+    _REF_C3["mods"][1].setGlobals(synthetic.defaultParams())
+
+
+def _ref_c3_analyze(item):
+    """analyzePDBID's voxel work on one entry (pdb_eda/multipleStructures.py:320-346): parse the map, aggregateCloud, read the ratio."""
+    import io
+    ref_ccp4, ref_da = _REF_C3["mods"][0], _REF_C3["mods"][1]
+    st, data = item
+    dens = ref_ccp4.parse(io.BytesIO(data), "pool")
+    dens.densityCutoff = dens.meanDensity + 1.5 * dens.stdDensity
+    an = ref_da.DensityAnalysis("pool", dens, None, st, None)
+    an.aggregateCloud()
+    return (an.densityElectronRatio or 0.0, an.numVoxelsAggregated or 0)
+
+
+def structure_from_arrays(coords32, bfactor):
+    """A poly-ALA Structure (the duck-typed Biopython surface) from the arrays of synthetic.fastPolyAla."""
+    from pdb_eda_b200 import structure as _st
+    st = _st.Structure("pool")
+    st.header["resolution"] = 2.0
+    chain = st.add(_st.Model(0)).add(_st.Chain("A"))
+    names = [(a, e) for a, _, e in synthetic._ALA_ATOMS]
+    for k in range(len(coords32) // 5):
+        res = chain.add(_st.Residue((" ", k + 1, " "), "ALA"))
+        for j, (name, element) in enumerate(names):
+            res.add(_st.Atom(name, coords32[5 * k + j], float(bfactor[5 * k + j]), 1.0, element=element))
+    return st
+
+
+def run_cpu_c3_sample(steps, warmup, cores):
+    """The 64^3 structures of the pool, `cores` of them per step, one per worker of a multiprocessing.Pool like
+    pdb_eda/multipleStructures.py:167-168.  Returns (value, cpu_baseline dict, ms per step)."""
+    import multiprocessing as mp
+    from oracle import orc
+    from pdb_eda_b200 import ccp4
+    import io
+    params = synthetic.defaultParams()
+    spec = [sp for sp in synthetic.poolSpec(4096) if sp["n"] == 64 and sp["cell"][5] == 90.0][:cores]
+    items, units = [], 0.0
+    electronsOf = np.array([synthetic.ALA_ELECTRONS["ALA_" + a] for a, _, _ in synthetic._ALA_ATOMS])
+    for sp in spec:
+        coords, bf = synthetic.fastPolyAla(sp["residues"], sp["cell"], sp["seed"])
+        st = structure_from_arrays(coords, bf)
+        n = sp["n"]
+        fofc2, _ = synthetic.mapPair(st, (n, n, n), sp["cell"], seed=sp["seed"] + 1)
+        data = synthetic.ccp4Bytes(fofc2, sp["cell"], (n, n, n))
+        dm = ccp4.parse(io.BytesIO(data), "pool")
+        radii = np.array([params["radii"][params["full_atom_name_map_atom_type"]["ALA_" + a]] for a, _, _ in synthetic._ALA_ATOMS] * sp["residues"],
+                         dtype=np.float32)
+        units += float(orc.sphere_sums_batch(orc.geom(dm.header, dm.origin), fofc2, coords.astype(np.float64), radii)[:, 0].sum())
+        items.append((st, data))
+    times = []
+    with mp.get_context("fork").Pool(cores, initializer=_ref_c3_init) as pool:
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = pool.map(_ref_c3_analyze, items, chunksize=1)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = units * len(times) / total
+    sample = ("%d structures of the pool per step (64^3 maps, %d atoms each on average), one per worker of a multiprocessing.Pool(%d): parse + "
+              "aggregateCloud (analyzePDBID, pdb_eda/multipleStructures.py:320-346); %d steps, %.1f s/step, %d structures with a ratio"
+              % (len(items), int(np.mean([5 * sp["residues"] for sp in spec])), cores, len(times), total / len(times), sum(1 for r in out if r[0])))
+    return value, {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                   "structures_per_s": len(items) * len(times) / total}, total / len(times) * 1e3
+
+
 def api_timing(work):
     """Wall-clock of the public DensityAnalysis calls on the full C2 structure (context for the kernel-level numbers;
     not part of the timed step): the reference cannot run these at this size at all."""
@@ -236,12 +331,45 @@ def api_timing(work):
 def main_reference(args, rank, world):
     if rank != 0:
         return
+    if world > 1 or args.gpus > 1:
+        # the N > 1 arm runs config 3: the reference's multiple-structures mode on all host cores
+        cores = max(1, len(os.sched_getaffinity(0)))
+        value, cpu, ms = run_cpu_c3_sample(args.steps, min(args.warmup, 1), cores)   # ~10 s per step: one warm-up pass is enough
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": "C3 (bounded sample: %s)" % cpu["sample"]},
+                "structures_per_s": cpu["structures_per_s"],
+                "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
     value, cpu, ms = run_cpu_sample(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": "C2 (bounded sample: %s)" % cpu["sample"]},
+            "work": {k: v["reference"] for k, v in WORK_C2.items()},
             "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    ref_mods = load_reference()
+    if ref_mods is not None and not args.no_c1:
+        line["c1_full_size"] = reference_c1_full_pass(ref_mods)       # BASELINE.json configs[0] as it stands, one pass (~70 s)
     print(json.dumps(line))
+
+
+def bind_to_gpu(local_rank):
+    """Pins this process to the CPU cores NVML reports as local to its GPU (same NUMA node / PCIe root), BEFORE any pinned host
+    buffer is allocated, so that the staging memory of a rank lives next to its GPU.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"cores": len(allowed or os.sched_getaffinity(0)), "first": min(allowed) if allowed else None,
+                "last": max(allowed) if allowed else None, "bound": bool(allowed)}
+    except Exception as exc:                      # NVML absent or not permitted: run unbound and say so
+        return {"bound": False, "error": str(exc)[:80]}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -368,24 +496,39 @@ def main_gpu(args, rank, world, local_rank):
         algo = {"threshold_bitmap_kernel": 4.0 * blob_units,                               # 4 N_vox
                 "sphere_union_kernel": 4.0 * region_union + 52.0 * vp.n_atoms,            # 4 V_in + 52 A (region pass)
                 "sphere_sums_kernel": 4.0 * cloud_units + 52.0 * vp.n_atoms}              # 4 V_in + 52 A (cloud pass)
-        notes = {"sphere_union_kernel": "bound by instruction issue and dependent shared-memory / L2 latency (exact row chords, bitmap "
-                                        "compaction, sector-granular gathers), not by HBM; V_in = union voxels",
-                 "sphere_sums_kernel": "bound by latency of the per-atom chain (box, tables, exact row chords, 32-byte gathers), not by HBM"}
+        # what actually limits each kernel (profiles/r02_union_phases.md, profiles/r01_v10_c2_step.md): the HBM fraction is the
+        # contract number; kernels that are not HBM-bound also carry the ceiling that applies to them
+        bounds = {"threshold_bitmap_kernel": "hbm", "sphere_union_kernel": "latency", "sphere_sums_kernel": "latency", "blob_sparse_kernel": "latency"}
+        notes = {"sphere_union_kernel": "one warp per residue: exact row chords -> bitmap -> compaction -> sector-granular gathers; bound by the "
+                                        "length of each warp's dependent instruction chains at 28 warps / SM, not by HBM (issue slots 64 % busy; "
+                                        "ALU 38 %, LSU 32 %, XU 20 %, FP64 12 %); V_in = union voxels",
+                 "sphere_sums_kernel": "bound by latency of the per-atom chain (box, tables, exact row chords, 32-byte gathers), not by HBM",
+                 "blob_sparse_kernel": "sparse union-find over the bit planes with 3 grid barriers: latency of dependent 4-byte L2 transactions"}
         kernels = []
         for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             kernels.append({"kernel": name, "launches": count, "ms_total": round(ms, 4), "us_per_launch": round(ms * 1e3 / max(count, 1), 2)})
-        try:  # DRAM traffic per launch from the committed ncu capture of this workload (profiles/)
+        try:  # DRAM traffic and warp instructions per launch from the committed ncu capture of this workload (profiles/)
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             traffic = {}
+        inst = traffic.get("_warp_instructions", {})
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        issue_peak = 148 * 4 * sm_mhz * 1e6                         # warp instructions / s: 148 SMs x 4 schedulers x clock
+        algo["blob_sparse_kernel"] = 8.0 * n_fg + 64.0 * n_blob      # 8 N_fg + 64 N_blob
         roofs = []
         for k in kernels:
             if k["kernel"] in algo:
                 t = k["ms_total"] / max(k["launches"], 1) * 1e-3
                 ach = algo[k["kernel"]] / t / 1e9
-                r = {"kernel": k["kernel"], "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                r = {"kernel": k["kernel"], "bound": bounds.get(k["kernel"], "hbm"), "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 4), "traffic": traffic.get(k["kernel"]), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo[k["kernel"]], "us_per_launch": k["us_per_launch"]}
+                if k["kernel"] in inst:
+                    r["issue_roofline"] = {"warp_instructions_per_launch": inst[k["kernel"]], "achieved": round(inst[k["kernel"]] / t, 1),
+                                           "peak": issue_peak, "unit": "warp instructions/s", "frac": round(inst[k["kernel"]] / t / issue_peak, 4),
+                                           "source": "smsp__inst_executed.sum of the committed ncu capture (profiles/traffic.json)"}
+                    if k["kernel"] == "sphere_union_kernel":
+                        r["issue_roofline"]["warp_instructions_per_32_voxels"] = round(inst[k["kernel"]] / (region_union / 32.0), 1)
                 if k["kernel"] in notes:
                     r["note"] = notes[k["kernel"]]
                 roofs.append(r)
@@ -411,6 +554,7 @@ def main_gpu(args, rank, world, local_rank):
                                        % (vp.n_atoms, vp.n_res),
                            "parallelism": "replicas x%d (single structure does not shard)" % world,
                            "l2": "inputs larger than L2 (2 x 226 MB maps per pass); no explicit flush"},
+                "work": {k: v["b200"] for k, v in WORK_C2.items()},
                 "units_per_step": {"cloud_atom_sphere_voxels": cloud_units, "cloud_box_candidates": cloud_candidates,
                                    "region_atom_sphere_voxels": region_pairs, "region_box_candidates": region_candidates,
                                    "region_union_voxels": region_union, "blob_ccl_voxels": blob_units,
@@ -422,7 +566,13 @@ def main_gpu(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             _, cpu, _ = run_cpu_sample(1, 0)
             line["cpu_baseline"] = cpu
-            line["api_c2"] = api_timing(work)
+            api = api_timing(work)
+            line["api_c2"] = api
+            calls = ("load_parse_upload_meanstd_s", "aggregateCloud_s", "green_red_blob_lists_s", "blob_statistics_s", "residue_region_density_s")
+            line["e2e_api"] = {"seconds": round(sum(api[c] for c in calls), 4), "calls": {c: api[c] for c in calls},
+                               "what": "pdb_eda_b200.densityAnalysis on the C2 structure, host CCP4 / PDB bytes in, Python rows out: fromFile-equivalent "
+                                       "load -> aggregateCloud -> greenBlobList + redBlobList -> calculateAtomSpecificBlobStatistics -> "
+                                       "calculateResidueRegionDensity(3.5)"}
         if world == 1 and not args.no_c3:
             # BASELINE.json configs[2] on this one GPU: the pool the N > 1 runs shard (their strong-scaling reference point)
             del vp, dens, diff, d_dens, d_diff
@@ -495,6 +645,7 @@ def main_c3(args, rank, world, local_rank):
     import torch.distributed as dist
     from pdb_eda_b200 import _device, _lib, multi
 
+    affinity = bind_to_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
@@ -615,7 +766,8 @@ def main_c3(args, rank, world, local_rank):
                                    "blob_ccl_voxels": 0.0},
                 "structures_per_s": args.pool / (ms * 1e-3),
                 "e2e": {"value": all_units / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": all_h2d, "d2h_bytes_per_step": all_d2h,
-                        "ms_per_step": ms_e2e, "structures_per_s": args.pool / (ms_e2e * 1e-3), "steps": e2e_steps},
+                        "ms_per_step": ms_e2e, "structures_per_s": args.pool / (ms_e2e * 1e-3), "steps": e2e_steps,
+                        "h2d_gb_per_s_per_rank": round(all_h2d / world / (ms_e2e * 1e-3) / 1e9, 2), "cpu_affinity_rank0": affinity},
                 "gpu_launches": int(launches), "roofline": roof, "kernels": kernels[:14], "ms_per_step_profiled": ms_prof,
                 "ms_per_step_host_clock": wall, "gpu_busy_frac_rank0": round(sum(k["ms_total"] for k in kernels) / (ms_prof * args.steps), 3),
                 "batches": int(all_batches), "setup_s_rank0": round(setup_s, 1), "summary": _summary_digest(summary),
@@ -692,6 +844,7 @@ def main():
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip timing the pool on one GPU")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the config-4 slab run")
     ap.add_argument("--no-c3", action="store_true", help="N = 1: skip the config-3 pool key")
+    ap.add_argument("--no-c1", action="store_true", help="reference arm: skip the full-size config-1 pass")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
