@@ -274,7 +274,7 @@ int pe_overlap_pairs(int64_t n, const int32_t *d_crs, const int32_t *d_owner, co
  *   d_map_out[m*8..]   numVoxelsAggregated, totalAggregatedDensity, totalAggregatedElectrons, domain clouds, domain clouds
  *                      with >= min_cloud_electrons, residue clouds, residue clouds with >= min_cloud_electrons,
  *                      centroidDistanceCutoff (pdb_eda/densityAnalysis.py:609, :681, :712-724)
- * d_ws: >= pe_cloud_workspace_bytes(n_atoms, n_entries, n_residues).  pe_cloud_status reads the workspace's error flag
+ * d_ws: >= pe_cloud_workspace_bytes(n_atoms, n_entries, n_residues, n_maps).  pe_cloud_status reads the workspace's error flag
  * (un-wrapped index outside +-8190 or inconsistent counts) and synchronises. */
 typedef struct pe_batch_map {
     pe_geom geom;
@@ -283,7 +283,7 @@ typedef struct pe_batch_map {
     int32_t atom_begin, atom_end;
     int32_t reserved;
 } pe_batch_map;
-int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues);
+int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues, int64_t n_maps);
 int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
                    const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, void *stream);
 int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map,

@@ -384,7 +384,7 @@ class CloudBatch:
                                       _ptr(self.d_offset), _ptr(self.d_totals), _ptr(self.d_scan), _stream()), "pe_cloud_count")
         nEntries, maxBox = self.d_totals.tolist()
         self.nEntries = int(nEntries)
-        need = int(self.lib.pe_cloud_workspace_bytes(nA, nEntries, self.nResidues))
+        need = int(self.lib.pe_cloud_workspace_bytes(nA, nEntries, self.nResidues, nS))
         if self.ws is None or self.ws.numel() < need:
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         check(self.lib.pe_cloud_aggregate(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomMap), _ptr(self.d_xyz), _ptr(self.d_radius),

@@ -37,23 +37,44 @@ constexpr uint32_t kAggNil = 0xffffffffu;
 constexpr int kKeyBits = 14;                 // per crs axis, offset 2^13: |index| < 8192
 constexpr int kKeyOff = 1 << (kKeyBits - 1);
 
+// Hash table of the pool voxels.  Every structure owns a REGION of the slot array (twice its number of cloud voxels), so the
+// probes of a thread block -- entries are ordered structure by structure -- stay inside a few megabytes that L2 holds, instead of
+// scattering over one table of the whole batch (hundreds of megabytes: every probe a DRAM access).  A slot is 16 bytes (key,
+// head of the chain of entries at that voxel), read with one load.
+struct AggSlot {
+    unsigned long long key;
+    uint32_t head;
+    uint32_t pad;
+};
 struct AggTable {
-    unsigned long long *key;
-    uint32_t *head;
-    uint32_t *next;  // per entry
-    int log2cap;
+    AggSlot *slot;
+    const uint32_t *offset;       // n_atoms + 1: first cloud voxel of every atom
+    const pe_batch_map *maps;     // atom ranges of the structures
+    uint2 *node;                  // per entry: (next entry of the same voxel, owning atom)
 };
 
-__device__ __forceinline__ uint64_t agg_hash(uint64_t key, int log2cap) { return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2cap); }
+__device__ __forceinline__ void agg_region(const AggTable &t, uint64_t key, uint64_t &base, uint32_t &size) {
+    const pe_batch_map *m = t.maps + (key >> (3 * kKeyBits));
+    const uint64_t e0 = t.offset[m->atom_begin], e1 = t.offset[m->atom_end];
+    base = 2 * e0 + 16ull * (key >> (3 * kKeyBits));
+    size = (uint32_t)(2 * (e1 - e0) + 16);
+}
+__device__ __forceinline__ uint32_t agg_start(uint64_t key, uint32_t size) {
+    const uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32);
+    return (uint32_t)(((uint64_t)h * size) >> 32);
+}
 
 __device__ __forceinline__ uint32_t agg_lookup(const AggTable &t, uint64_t key) {
-    const uint64_t mask = (1ull << t.log2cap) - 1;
-    uint64_t h = agg_hash(key, t.log2cap);
+    uint64_t base;
+    uint32_t size;
+    agg_region(t, key, base, size);
+    uint32_t h = agg_start(key, size);
     for (;;) {
-        const unsigned long long k = t.key[h];
-        if (k == key) return t.head[h];
+        const uint4 s = __ldcg(reinterpret_cast<const uint4 *>(t.slot + base + h));
+        const unsigned long long k = ((unsigned long long)s.y << 32) | s.x;
+        if (k == key) return s.z;
         if (k == kAggEmpty) return kAggNil;
-        h = (h + 1) & mask;
+        h = h + 1 == size ? 0 : h + 1;
     }
 }
 
@@ -350,23 +371,38 @@ __global__ void __launch_bounds__(kAggThreads)
 __global__ void __launch_bounds__(kAggThreads)
     pool_insert_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
                        const double *__restrict__ atom_out, AggTable t) {
-    const uint64_t mask = (1ull << t.log2cap) - 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        t.next[i] = kAggNil;
-        if (atom_out[(int64_t)e_atom[i] * 8 + 7] == 0.0) continue;  // the atom does not contribute
-        const unsigned long long key = e_key[i];
-        uint64_t h = agg_hash(key, t.log2cap);
-        for (;;) {
-            unsigned long long old = t.key[h];
-            if (old == kAggEmpty) old = atomicCAS(t.key + h, (unsigned long long)kAggEmpty, key);
-            if (old == kAggEmpty || old == key) {
-                t.next[i] = atomicExch(t.head + h, (uint32_t)i);
-                break;
+        const uint32_t atom = e_atom[i];
+        uint32_t next = kAggNil;
+        if (atom_out[(int64_t)atom * 8 + 7] != 0.0) {  // the atom contributes
+            const unsigned long long key = e_key[i];
+            uint64_t base;
+            uint32_t size;
+            agg_region(t, key, base, size);
+            uint32_t h = agg_start(key, size);
+            for (;;) {
+                AggSlot *sl = t.slot + base + h;
+                unsigned long long old = sl->key;
+                if (old == kAggEmpty) old = atomicCAS(&sl->key, (unsigned long long)kAggEmpty, key);
+                if (old == kAggEmpty || old == key) {
+                    next = atomicExch(&sl->head, (uint32_t)i);
+                    break;
+                }
+                h = h + 1 == size ? 0 : h + 1;
             }
-            h = (h + 1) & mask;
         }
+        t.node[i] = make_uint2(next, atom);
     }
+}
+
+// per atom: (first cloud id, residue, index inside the residue, contributes) in one 16-byte record
+__global__ void __launch_bounds__(kAggThreads)
+    atom_info_kernel(int n_atoms, const uint32_t *__restrict__ cloud_start, const int32_t *__restrict__ atom_residue,
+                     const int32_t *__restrict__ atom_local, const double *__restrict__ atom_out, int4 *__restrict__ info) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_atoms) return;
+    info[a] = make_int4((int)cloud_start[a], atom_residue[a], atom_local[a], atom_out[(int64_t)a * 8 + 7] != 0.0 ? 1 : 0);
 }
 
 // Every pool voxel looks at its own position and at 13 of its 26 neighbours (adjacency is symmetric): clouds that share or
@@ -374,18 +410,16 @@ __global__ void __launch_bounds__(kAggThreads)
 // mark each other in the per-atom adjacency masks (the overlap matrix of pdb_eda/densityAnalysis.py:646-649 reduced to
 // what the completeness test of :653-659 reads).
 __global__ void __launch_bounds__(kAggThreads)
-    cloud_merge_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
-                       const uint16_t *__restrict__ e_lab, const double *__restrict__ atom_out,
-                       const uint32_t *__restrict__ cloud_start, const int32_t *__restrict__ atom_residue,
-                       const int32_t *__restrict__ atom_local, AggTable t, uint32_t *parent_dom, uint32_t *parent_res,
-                       unsigned long long *adj) {
+    cloud_merge_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint16_t *__restrict__ e_lab,
+                       const int4 *__restrict__ info, AggTable t, uint32_t *parent_dom, uint32_t *parent_res, unsigned long long *adj) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t ai = e_atom[i];
-        if (atom_out[(int64_t)ai * 8 + 7] == 0.0) continue;
+        const uint32_t ai = t.node[i].y;
+        const int4 me = info[ai];
+        if (!me.w) continue;
         const unsigned long long key = e_key[i];
-        const uint32_t ci = cloud_start[ai] + e_lab[i];
-        const int ri = atom_residue[ai];
+        const uint32_t ci = (uint32_t)me.x + e_lab[i];
+        uint32_t root_dom = ci;  // a known ancestor of ci in the domain forest, carried from one hook to the next
 #pragma unroll 1
         for (int q = 0; q < 14; ++q) {
             // q = 0: the voxel itself; q = 1..13: the neighbours that precede it in (c, r, s) order
@@ -394,17 +428,22 @@ __global__ void __launch_bounds__(kAggThreads)
             const int dr = q == 0 ? 0 : (p < 9 ? (p / 3) - 1 : (p < 12 ? -1 : 0));
             const int ds = q == 0 ? 0 : (p < 9 ? (p % 3) - 1 : (p < 12 ? (p - 9) - 1 : -1));
             const unsigned long long nk = key + (long long)dc * (1ll << (2 * kKeyBits)) + (long long)dr * (1ll << kKeyBits) + (long long)ds;
-            for (uint32_t j = agg_lookup(t, nk); j != kAggNil; j = t.next[j]) {
-                if (j == (uint32_t)i) continue;
-                const uint32_t aj = e_atom[j];
-                if (aj == ai) continue;  // clouds of one atom are disjoint components: never adjacent
-                const uint32_t cj = cloud_start[aj] + e_lab[j];
-                uf_union(parent_dom, ci, cj);
-                if (atom_residue[aj] == ri) {
+            for (uint32_t j = agg_lookup(t, nk); j != kAggNil;) {
+                const uint2 nd = t.node[j];
+                const uint32_t jj = j;
+                j = nd.x;
+                if (nd.y == ai) continue;  // clouds of one atom are disjoint components: never adjacent
+                const int4 other = info[nd.y];
+                const uint32_t cj = (uint32_t)other.x + e_lab[jj];
+                if (__ldcg(parent_dom + cj) != root_dom || __ldcg(parent_dom + root_dom) != root_dom) {  // cheap "already one set" test
+                    uf_union(parent_dom, root_dom, cj);
+                    root_dom = __ldcg(parent_dom + root_dom);
+                }
+                if (other.y == me.y) {
                     uf_union(parent_res, ci, cj);
-                    const unsigned long long bi = 1ull << atom_local[ai], bj = 1ull << atom_local[aj];
+                    const unsigned long long bi = 1ull << me.z, bj = 1ull << other.z;
                     if (!(adj[ai] & bj)) atomicOr(adj + ai, bj);
-                    if (!(adj[aj] & bi)) atomicOr(adj + aj, bi);
+                    if (!(adj[nd.y] & bi)) atomicOr(adj + nd.y, bi);
                 }
             }
         }
@@ -413,14 +452,14 @@ __global__ void __launch_bounds__(kAggThreads)
 
 // first[i] = 1 iff entry i is the first pool entry of its voxel: the SET semantics of DensityBlob.merge (pdb_eda/ccp4.py:575-586)
 __global__ void __launch_bounds__(kAggThreads)
-    cloud_first_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
-                       const double *__restrict__ atom_out, AggTable t, uint8_t *__restrict__ first) {
+    cloud_first_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const int4 *__restrict__ info, AggTable t,
+                       uint8_t *__restrict__ first) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint8_t f = 0;
-        if (atom_out[(int64_t)e_atom[i] * 8 + 7] != 0.0) {
+        if (info[t.node[i].y].w) {
             uint32_t mn = kAggNil;
-            for (uint32_t j = agg_lookup(t, e_key[i]); j != kAggNil; j = t.next[j]) mn = min(mn, j);
+            for (uint32_t j = agg_lookup(t, e_key[i]); j != kAggNil; j = t.node[j].x) mn = min(mn, j);
             f = mn == (uint32_t)i ? 1 : 0;
         }
         first[i] = f;
@@ -519,12 +558,6 @@ __global__ void __launch_bounds__(kAggThreads) iota_kernel(int64_t n, uint32_t *
     }
 }
 
-static int agg_log2cap(int64_t n) {
-    int l = 6;
-    while ((1ll << l) < 2 * n + 16) ++l;
-    return l;
-}
-
 static int agg_grid(int64_t n) {
     int64_t blocks = (n + kAggThreads - 1) / kAggThreads;
     const int64_t max_blocks = (int64_t)sm_count() * 16;
@@ -533,11 +566,11 @@ static int agg_grid(int64_t n) {
 }
 
 struct AggLayout {
-    int64_t cloud_count, cloud_start, scan, key, val, atom, lab, next, first, tkey, thead, parent_dom, parent_res, elec_dom,
+    int64_t cloud_count, cloud_start, scan, key, val, atom, lab, node, first, slots, info, parent_dom, parent_res, elec_dom,
         elec_res, adj, res_mask, flags, total;
 };
 
-static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residues) {
+static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residues, int64_t n_maps) {
     AggLayout L;
     int64_t p = 0;
     auto take = [&](int64_t bytes) {
@@ -545,7 +578,7 @@ static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residu
         p += align_up(bytes > 0 ? bytes : 1, 256);
         return at;
     };
-    const int64_t cap = 1ll << agg_log2cap(n_entries);
+    const int64_t cap = 2 * n_entries + 16 * n_maps;  // slots: every structure's region is twice its cloud voxels (+ 16)
     L.flags = take(256);
     L.cloud_count = take((n_atoms + 1) * 4);
     L.cloud_start = take((n_atoms + 1) * 4);
@@ -554,10 +587,10 @@ static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residu
     L.val = take(n_entries * 4);
     L.atom = take(n_entries * 4);
     L.lab = take(n_entries * 2);
-    L.next = take(n_entries * 4);
+    L.node = take(n_entries * 8);
     L.first = take(n_entries);
-    L.tkey = take(cap * 8);
-    L.thead = take(cap * 4);
+    L.slots = take(cap * 16);
+    L.info = take(n_atoms * 16);
     L.parent_dom = take(n_entries * 4);
     L.parent_res = take(n_entries * 4);
     L.elec_dom = take(n_entries * 8);
@@ -574,9 +607,9 @@ using namespace pe;
 
 extern "C" {
 
-int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues) {
-    if (n_atoms < 0 || n_entries < 0 || n_residues < 0) return -1;
-    return agg_layout(n_atoms, n_entries, n_residues).total;
+int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues, int64_t n_maps) {
+    if (n_atoms < 0 || n_entries < 0 || n_residues < 0 || n_maps < 0) return -1;
+    return agg_layout(n_atoms, n_entries, n_residues, n_maps).total;
 }
 
 int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
@@ -613,7 +646,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     PE_CHECK_ARG(n_entries < (1ll << 31), "pe_cloud_aggregate: too many cloud voxels in one batch");
     PE_CHECK_ARG(max_box_voxels > 0 && max_box_voxels <= 16384, "pe_cloud_aggregate: atom boxes of %d voxels are not supported (1..16384)",
                  max_box_voxels);
-    const AggLayout L = agg_layout(n_atoms, n_entries, n_residues);
+    const AggLayout L = agg_layout(n_atoms, n_entries, n_residues, n_maps);
     char *ws = (char *)d_ws;
     int *d_bad = (int *)(ws + L.flags);
     uint32_t *cloud_count = (uint32_t *)(ws + L.cloud_count);
@@ -624,18 +657,18 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     uint16_t *e_lab = (uint16_t *)(ws + L.lab);
     uint8_t *first = (uint8_t *)(ws + L.first);
     AggTable t;
-    t.log2cap = agg_log2cap(n_entries);
-    t.key = (unsigned long long *)(ws + L.tkey);
-    t.head = (uint32_t *)(ws + L.thead);
-    t.next = (uint32_t *)(ws + L.next);
+    t.slot = (AggSlot *)(ws + L.slots);
+    t.offset = d_offset;
+    t.maps = d_maps;
+    t.node = (uint2 *)(ws + L.node);
+    int4 *info = (int4 *)(ws + L.info);
     uint32_t *parent_dom = (uint32_t *)(ws + L.parent_dom), *parent_res = (uint32_t *)(ws + L.parent_res);
     double *elec_dom = (double *)(ws + L.elec_dom), *elec_res = (double *)(ws + L.elec_res);
     unsigned long long *adj = (unsigned long long *)(ws + L.adj), *res_mask = (unsigned long long *)(ws + L.res_mask);
-    const int64_t cap = 1ll << t.log2cap;
+    const int64_t cap = 2 * n_entries + 16 * (int64_t)n_maps;
 
     PE_CUDA(cudaMemsetAsync(d_bad, 0, 256, st));
-    PE_CUDA(cudaMemsetAsync(t.key, 0xff, (size_t)cap * 8, st));
-    PE_CUDA(cudaMemsetAsync(t.head, 0xff, (size_t)cap * 4, st));
+    PE_CUDA(cudaMemsetAsync(t.slot, 0xff, (size_t)cap * sizeof(AggSlot), st));
     PE_CUDA(cudaMemsetAsync(elec_dom, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
     PE_CUDA(cudaMemsetAsync(elec_res, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
     PE_CUDA(cudaMemsetAsync(adj, 0, (size_t)n_atoms * 8, st));
@@ -660,10 +693,12 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     if (n_entries > 0) {
         const int grid = agg_grid(n_entries);
         PE_LAUNCH("iota_kernel", st, iota_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, parent_dom, parent_res));
+        PE_LAUNCH("atom_info_kernel", st, atom_info_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
+            n_atoms, cloud_start, d_atom_residue, d_atom_local, d_atom_out, info));
         PE_LAUNCH("pool_insert_kernel", st, pool_insert_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t));
-        PE_LAUNCH("cloud_merge_kernel", st, cloud_merge_kernel<<<grid, kAggThreads, 0, st>>>(
-            n_entries, e_key, e_atom, e_lab, d_atom_out, cloud_start, d_atom_residue, d_atom_local, t, parent_dom, parent_res, adj));
-        PE_LAUNCH("cloud_first_kernel", st, cloud_first_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t, first));
+        PE_LAUNCH("cloud_merge_kernel", st, cloud_merge_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_lab, info, t, parent_dom,
+                                                                                           parent_res, adj));
+        PE_LAUNCH("cloud_first_kernel", st, cloud_first_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, info, t, first));
     }
     PE_LAUNCH("cloud_roots_kernel", st, cloud_roots_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
         n_atoms, d_atom_out, cloud_start, d_atom_electrons, parent_dom, parent_res, elec_dom, elec_res));
@@ -679,7 +714,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
 int pe_cloud_status(const void *d_ws, void *stream, int32_t *bad) {
     PE_CHECK_ARG(d_ws && bad, "pe_cloud_status: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const AggLayout L = agg_layout(0, 0, 0);
+    const AggLayout L = agg_layout(0, 0, 0, 0);
     PE_CUDA(cudaMemcpyAsync(bad, (const char *)d_ws + L.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PE_CUDA(cudaStreamSynchronize(st));
     return PE_OK;
