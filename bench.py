@@ -310,20 +310,23 @@ def api_timing(work):
         out[label] = round(time.perf_counter() - t, 4)
         return res
 
+    # the files a user would hold: CCP4 bytes of both maps and the PDB text (synthesised outside the timed calls)
+    b1 = synthetic.ccp4Bytes(work["fofc2"], cell, (n, n, n))
+    b2 = synthetic.ccp4Bytes(work["fofc"], cell, (n, n, n))
+    text = structure.formatPDB(work["structure"], remark290=synthetic.cartesianOperators("P 1", cell), cell=cell, spaceGroup="P 1")
+
     def load():
-        dens = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc2"], cell, (n, n, n))), "c2")
-        diff = ccp4.parse(io.BytesIO(synthetic.ccp4Bytes(work["fofc"], cell, (n, n, n))), "c2")
-        densityAnalysis._attachCutoffs(dens, diff)
-        text = structure.formatPDB(work["structure"], remark290=synthetic.cartesianOperators("P 1", cell), cell=cell, spaceGroup="P 1")
-        return densityAnalysis.DensityAnalysis("c2", dens, diff, work["structure"], pdbParser.readPDBfile(io.StringIO(text)))
+        an = densityAnalysis.fromFile(io.StringIO(text), io.BytesIO(b1), io.BytesIO(b2))
+        an.densityObj.meanDensity, an.diffDensityObj.meanDensity      # the cutoffs are part of loading (pdb_eda/densityAnalysis.py:131,148)
+        return an
 
     an = timed("load_parse_upload_meanstd_s", load)
     timed("aggregateCloud_s", an.aggregateCloud)
     blobs = timed("green_red_blob_lists_s", lambda: (an.greenBlobList, an.redBlobList))
     timed("blob_statistics_s", lambda: an.calculateAtomSpecificBlobStatistics(blobs[0] + blobs[1]))
     timed("residue_region_density_s", lambda: an.calculateResidueRegionDensity(REGION_RADIUS))
-    out.update({"atoms_analysed": len(an.atomCloudDescriptions), "residue_clouds": len(an.residueCloudDescriptions),
-                "domain_clouds": len(an.domainCloudDescriptions), "green_blobs": len(blobs[0]), "red_blobs": len(blobs[1]),
+    out.update({"atoms_analysed": len(an.atomCloudDescriptions), "residue_clouds": an.numResidueCloudsAnalyzed,
+                "domain_clouds": an.numDomainCloudsAnalyzed, "green_blobs": len(blobs[0]), "red_blobs": len(blobs[1]),
                 "density_electron_ratio": an.densityElectronRatio})
     return out
 

@@ -420,7 +420,8 @@ class CloudBatch:
         ok = mapStats[:, 3] != 0
         out = {"ok": ok, "ratio": mapStats[:, 1].copy(), "numVoxels": mapOut[:, 0].copy(), "totalDensity": mapOut[:, 1].copy(),
                "totalElectrons": mapOut[:, 2].copy(), "analysed": mapStats[:, 0].copy(), "domainClouds": mapOut[:, 4].copy(),
-               "residueClouds": mapOut[:, 6].copy(), "centroidCutoff": mapOut[:, 7].copy(), "unitVolume": self.unitVolume}
+               "residueClouds": mapOut[:, 6].copy(), "centroidCutoff": mapOut[:, 7].copy(), "centroidCutoff2": mapStats[:, 2].copy(),
+               "unitVolume": self.unitVolume}
         sm, stp = self.segMap, self.segType
         present = np.zeros((nS, nT), dtype=bool)
         present[sm, stp] = (seg[:, 0] > 0) & ok[sm]

@@ -233,13 +233,11 @@ def _make_blobs(densityMatrix, crs, label, stats):
         center = stats[:, 5:8] / n[:, None]
     unit = densityMatrix.header.unitVolume
     order = np.argsort(label, kind="stable")
-    bounds = np.searchsorted(label[order], np.arange(len(stats) + 1))
-    blobs = []
-    for b in range(len(stats)):
-        members = crs[order[bounds[b]:bounds[b + 1]]]
-        blobs.append(DensityBlob(centroid[b].tolist(), center[b].tolist(), float(total[b]), unit * len(members), members,
-                                 densityMatrix))
-    return blobs
+    bounds = np.searchsorted(label[order], np.arange(len(stats) + 1)).tolist()
+    grouped = crs[order]                              # one gather; every blob's members are a slice (a view) of it
+    centroids, centers, totals = centroid.tolist(), center.tolist(), total.tolist()
+    return [DensityBlob(centroids[b], centers[b], totals[b], unit * (bounds[b + 1] - bounds[b]), grouped[bounds[b]:bounds[b + 1]],
+                        densityMatrix) for b in range(len(stats))]
 
 
 def fullBlobs(densityMatrix, positiveCutoff, negativeCutoff):

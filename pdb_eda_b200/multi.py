@@ -58,8 +58,10 @@ def analyzeStructure(analyzer, atomTypes, optimizer=False):
     stats = {'density_electron_ratio': ratio, 'voxel_volume': analyzer.densityObj.header.unitVolume,
              'num_voxels_aggregated': analyzer.numVoxelsAggregated, 'total_aggregated_electrons': analyzer.totalAggregatedElectrons,
              'total_aggregated_density': analyzer.totalAggregatedDensity, 'num_atoms_analyzed': len(analyzer.atomCloudDescriptions),
-             'num_residue_clouds_analyzed': len(analyzer.residueCloudDescriptions),
-             'num_domain_clouds_analyzed': len(analyzer.domainCloudDescriptions), 'atom_overlap_completeness': completeness}
+             'num_residue_clouds_analyzed': getattr(analyzer, "numResidueCloudsAnalyzed", None) if hasattr(analyzer, "numResidueCloudsAnalyzed")
+             else len(analyzer.residueCloudDescriptions),
+             'num_domain_clouds_analyzed': getattr(analyzer, "numDomainCloudsAnalyzed", None) if hasattr(analyzer, "numDomainCloudsAnalyzed")
+             else len(analyzer.domainCloudDescriptions), 'atom_overlap_completeness': completeness}
     stats['execution_time'] = time.process_time() - start
     return {"pdbid": analyzer.pdbid, "diffs": diffs, "slopes": slopes, "stats": stats,
             "atomtype_overlap_completeness": dict(analyzer.atomTypeOverlapCompleteness),

@@ -14,7 +14,7 @@ class Atom:
     def __init__(self, name, coord, bfactor, occupancy, altloc=" ", fullname=None, serial_number=0, element=""):
         self.name = name
         self.fullname = fullname if fullname is not None else name
-        self.coord = np.asarray(coord, dtype=np.float32)
+        self.coord = coord if (type(coord) is np.ndarray and coord.dtype == np.float32) else np.asarray(coord, dtype=np.float32)
         self.bfactor = float(bfactor)
         self.occupancy = float(occupancy)
         self.altloc = altloc
@@ -118,6 +118,97 @@ class Structure(_Entity):
             yield from residue.child_list
 
 
+def _parsePDBColumns(lines, structureId):
+    """Fast path of ``parsePDB`` for the common case -- one model, no alternate locations: the fixed-width columns of all
+    ATOM / HETATM records are converted with numpy in one go (coordinates, occupancies, b-factors, residue numbers, names);
+    the Python loop that remains only creates the objects.  Returns None when the file needs the general reader."""
+    atomLines = []
+    resolution = None
+    for line in lines:
+        rec = line[0:6]
+        if rec == "ATOM  " or rec == "HETATM":
+            atomLines.append(line)
+        elif rec == "MODEL " or rec == "ENDMDL":
+            return None
+        elif rec == "REMARK" and line.startswith("REMARK   2 RESOLUTION."):
+            try:
+                resolution = float(line[23:30])
+            except ValueError:
+                pass
+    structure = Structure(structureId)
+    structure.header["resolution"] = resolution
+    n = len(atomLines)
+    if n == 0:
+        return structure
+    try:
+        width = len(atomLines[0])
+        if width >= 79 and all(len(line) == width for line in atomLines):       # the usual case: every record is 80 columns wide
+            raw = np.frombuffer("".join(atomLines).encode("ascii"), dtype="S1").reshape(n, width)
+            if width < 80:
+                raw = np.concatenate((raw, np.full((n, 80 - width), b" ", dtype="S1")), axis=1)
+        else:
+            raw = np.frombuffer("".join(line.rstrip("\n").ljust(80)[:80] for line in atomLines).encode("ascii"), dtype="S1").reshape(n, 80)
+    except UnicodeEncodeError:
+        return None
+    col = lambda a, b: np.ascontiguousarray(raw[:, a:b]).view("S%d" % (b - a)).ravel()
+
+    def text(a, b, fn=lambda t: t):
+        """Column a:b as a list of str, fn applied once per DISTINCT value (atom names, residue names ... repeat)."""
+        values, inverse = np.unique(col(a, b), return_inverse=True)
+        table = np.empty(len(values), dtype=object)
+        table[:] = [fn(v.decode("ascii")) for v in values.tolist()]
+        return table[np.asarray(inverse).reshape(-1)]
+
+    if (col(16, 17) != b" ").any():
+        return None                                   # alternate locations: the general reader picks the highest occupancy
+    try:
+        coords = np.stack([col(30, 38).astype(np.float64), col(38, 46).astype(np.float64), col(46, 54).astype(np.float64)], axis=1).astype(np.float32)
+        number = lambda a, b, blank: np.where(col(a, b) == b" " * (b - a), blank.rjust(b - a), col(a, b))
+        occ = number(54, 60, b"1.0").astype(np.float64).tolist()
+        bfac = number(60, 66, b"0.0").astype(np.float64).tolist()
+        serial = number(6, 11, b"0").astype(np.int64).tolist()
+        resseq = col(22, 26).astype(np.int64)
+    except ValueError:
+        return None
+    fullnames = text(12, 16).tolist()
+    names = text(12, 16, str.strip).tolist()
+    resnames = text(17, 20, str.strip)
+    chainIds = text(21, 22)
+    icodes = text(26, 27)
+    elements = text(76, 78, lambda t: t.strip().upper()).tolist()
+    hetatm = col(0, 6) == b"HETATM"
+    hetflags = np.full(n, " ", dtype=object)
+    if hetatm.any():
+        hetflags[hetatm] = [("W" if r in ("HOH", "WAT") else "H_" + r) for r in resnames[hetatm].tolist()]
+    # a new residue starts where (chain, hetero flag, number, insertion code) changes; a key that comes back later in the file
+    # (interleaved residues) needs the general reader's dictionary
+    change = np.ones(n, dtype=bool)
+    change[1:] = (chainIds[1:] != chainIds[:-1]) | (hetflags[1:] != hetflags[:-1]) | (resseq[1:] != resseq[:-1]) | (icodes[1:] != icodes[:-1])
+    starts = np.flatnonzero(change)
+    keys = set()
+    for k in starts.tolist():
+        key = (chainIds[k], hetflags[k], int(resseq[k]), icodes[k])
+        if key in keys:
+            return None
+        keys.add(key)
+    model = structure.add(Model(0))
+    chains = {}
+    resnameList, chainList, hetList, icodeList, resseqList = resnames.tolist(), chainIds.tolist(), hetflags.tolist(), icodes.tolist(), resseq.tolist()
+    bounds = starts.tolist() + [n]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        chain = chains.get(chainList[a])
+        if chain is None:
+            chain = chains[chainList[a]] = model.add(Chain(chainList[a]))
+        residue = chain.add(Residue((hetList[a], resseqList[a], icodeList[a]), resnameList[a]))
+        seen = set()
+        for k in range(a, b):
+            if names[k] in seen:
+                return None                           # a repeated atom name inside a residue: general reader
+            seen.add(names[k])
+            residue.add(Atom(names[k], coords[k], bfac[k], occ[k], " ", fullnames[k], serial[k], elements[k]))
+    return structure
+
+
 def parsePDB(handle, structureId="xxxx"):
     """Reads ATOM / HETATM / MODEL records of a PDB-format text handle (or file name) into a Structure.
 
@@ -126,6 +217,11 @@ def parsePDB(handle, structureId="xxxx"):
     if isinstance(handle, str):
         with open(handle, "r") as fh:
             return parsePDB(fh, structureId)
+    lines = handle.readlines() if hasattr(handle, "readlines") else list(handle)
+    fast = _parsePDBColumns(lines, structureId)
+    if fast is not None:
+        return fast
+    handle = lines
     structure = Structure(structureId)
     model = None
     chains = {}
