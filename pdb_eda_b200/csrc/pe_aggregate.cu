@@ -202,7 +202,72 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         }
     }
     __syncwarp();
-    // 4. 26-connected clusters of the listed voxels: min-label propagation with pointer jumping
+    // 4 + 5. 26-connected clusters of the listed voxels, numbered by their first member (the order createCrsLists creates them in)
+    int nroots = 0;
+    if (nw <= 32) {
+        // Bit-parallel flood fill: the box is at most 32 words, one per lane.  A cluster grows from the lowest unlabelled voxel by
+        // repeated 3 x 3 x 3 dilation -- three separable +-1 shifts of the whole bit string (multi-word shifts across lanes), with
+        // masks that stop a shift from wrapping into the next row / plane -- intersected with the unlabelled voxels, until it stops
+        // growing; clusters therefore come out in the order of their first member.  (The min-label propagation this replaces was
+        // 56 % of the kernel's instructions: 27 bit tests and label look-ups per voxel and round.)
+        uint32_t nfs = 0u, nls = 0u, nfr = 0u, nlr = 0u;  // source voxels that may move -1 / +1 along sections, -1 / +1 along rows
+        {
+            const int p0 = 32 * lane;
+            int is = p0 % D2, ir = (p0 / D2) % D1;
+            for (int j = 0; j < 32; ++j) {
+                nfs |= (is != 0 ? 1u : 0u) << j;
+                nls |= (is != D2 - 1 ? 1u : 0u) << j;
+                nfr |= (ir != 0 ? 1u : 0u) << j;
+                nlr |= (ir != D1 - 1 ? 1u : 0u) << j;
+                if (++is == D2) {
+                    is = 0;
+                    if (++ir == D1) ir = 0;
+                }
+            }
+        }
+        auto shl = [&](uint32_t v, int k) {  // the bit string moved k positions up
+            const int q = k >> 5, r = k & 31;
+            uint32_t a = __shfl_up_sync(kFull, v, q), c = __shfl_up_sync(kFull, v, q + 1);
+            if (lane < q) a = 0u;
+            if (lane < q + 1) c = 0u;
+            return r ? ((a << r) | (c >> (32 - r))) : a;
+        };
+        auto shr = [&](uint32_t v, int k) {
+            const int q = k >> 5, r = k & 31;
+            uint32_t a = __shfl_down_sync(kFull, v, q), c = __shfl_down_sync(kFull, v, q + 1);
+            if (lane + q > 31) a = 0u;
+            if (lane + q + 1 > 31) c = 0u;
+            return r ? ((a >> r) | (c << (32 - r))) : a;
+        };
+        const uint32_t mine = lane < nw ? bits[lane] : 0u;
+        const int mybase = lane < nw ? (int)pref[lane] : 0;
+        uint32_t todo = mine;
+        const int plane = D1 * D2;
+        for (;;) {
+            const unsigned has = __ballot_sync(kFull, todo != 0u);
+            if (!has) break;
+            uint32_t comp = (lane == __ffs((int)has) - 1) ? (todo & (0u - todo)) : 0u;  // the lowest unlabelled voxel
+            for (;;) {
+                const uint32_t x = comp | shl(comp & nls, 1) | shr(comp & nfs, 1);
+                const uint32_t y = x | shl(x & nlr, D2) | shr(x & nfr, D2);
+                const uint32_t z = (y | (plane < 1024 ? (shl(y, plane) | shr(y, plane)) : 0u)) & todo;
+                const bool grew = z != comp;
+                comp = z;
+                if (!__any_sync(kFull, grew)) break;
+            }
+            for (uint32_t c = comp; c;) {
+                const int bit = __ffs((int)c) - 1;
+                c &= c - 1u;
+                const int j = mybase + __popc(mine & ((1u << bit) - 1u));
+                lab[j] = (uint16_t)j;
+                rnk[j] = (uint16_t)nroots;  // rnk[lab[j]] is the cluster number below
+            }
+            todo &= ~comp;
+            ++nroots;
+        }
+        __syncwarp();
+    } else {
+    // min-label propagation with pointer jumping (boxes of more than 1,024 voxels)
     for (int j = lane; j < n; j += 32) lab[j] = (uint16_t)j;
     __syncwarp();
     for (;;) {
@@ -237,8 +302,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         __syncwarp();
         if (!__any_sync(kFull, changed)) break;
     }
-    // 5. number the clusters by their first member (the order createCrsLists creates them in)
-    int nroots = 0;
+    // number the clusters by their first member
     for (int j0 = 0; j0 < n; j0 += 32) {
         const int j = j0 + lane;
         const int isroot = (j < n && lab[j] == j) ? 1 : 0;
@@ -247,6 +311,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         nroots += __shfl_sync(kFull, ex + isroot, 31);
     }
     __syncwarp();
+    }
     // 6. entries: packed key (structure, un-wrapped crs), density, owning atom, cloud number inside the atom
     bool bad = false;
     for (int j = lane; j < n; j += 32) {
