@@ -25,7 +25,9 @@
 // Batch layout: atoms of one structure are contiguous (pe_batch_map::atom_begin/end); every atom carries its structure
 // index, a residue id that is unique over the batch, its index inside the residue (< 64) and the bit mask of its bonded
 // atoms' indices inside the residue.
+#include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include "pe_select.cuh"
 #include "pe_sphere_dev.cuh"
 
@@ -36,6 +38,9 @@ constexpr uint64_t kAggEmpty = ~0ull;
 constexpr uint32_t kAggNil = 0xffffffffu;
 constexpr int kKeyBits = 14;                 // per crs axis, offset 2^13: |index| < 8192
 constexpr int kKeyOff = 1 << (kKeyBits - 1);
+constexpr int kPairClouds = 8;               // clouds per atom the pair kernel's byte masks can name
+constexpr int kPairWarps = 4;
+constexpr int kPairCand = 64;                // candidate atoms a warp collects before it walks their entries
 
 // Hash table of the pool voxels.  Every structure owns a REGION of the slot array (twice its number of cloud voxels), so the
 // probes of a thread block -- entries are ordered structure by structure -- stay inside a few megabytes that L2 holds, instead of
@@ -126,7 +131,8 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
                                   const double *__restrict__ xyz, const float *__restrict__ radius,
                                   const uint32_t *__restrict__ offset, int max_box, unsigned long long *__restrict__ e_key,
                                   float *__restrict__ e_val, uint32_t *__restrict__ e_atom, uint16_t *__restrict__ e_lab,
-                                  uint32_t *__restrict__ n_clouds, double *__restrict__ atom_out, int *__restrict__ d_bad) {
+                                  uint32_t *__restrict__ n_clouds, double *__restrict__ atom_out, int *__restrict__ d_bad,
+                                  unsigned long long *__restrict__ abox, int dil_cap) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ AxisTab tabs[kSphereWarps][2];
     __shared__ pe_geom geoms[kSphereWarps];
@@ -314,10 +320,17 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
     }
     // 6. entries: packed key (structure, un-wrapped crs), density, owning atom, cloud number inside the atom
     bool bad = false;
+    int lo_c = INT_MAX, lo_r = INT_MAX, lo_s = INT_MAX, hi_c = INT_MIN, hi_r = INT_MIN, hi_s = INT_MIN;
     for (int j = lane; j < n; j += 32) {
         const int p = pidx[j];
         const int is = p % D2, t = p / D2, ir = t % D1, ic = t / D1;
         const int c = b.lo[0] + ic, r = b.lo[1] + ir, s = b.lo[2] + is;
+        lo_c = min(lo_c, c);
+        hi_c = max(hi_c, c);
+        lo_r = min(lo_r, r);
+        hi_r = max(hi_r, r);
+        lo_s = min(lo_s, s);
+        hi_s = max(hi_s, s);
         const unsigned uc = (unsigned)(c + kKeyOff), ur = (unsigned)(r + kKeyOff), us = (unsigned)(s + kKeyOff);
         // neighbours (+-1) must stay inside the field: 1 <= u < 2^14 - 1
         if (uc - 1u >= (1u << kKeyBits) - 2u || ur - 1u >= (1u << kKeyBits) - 2u || us - 1u >= (1u << kKeyBits) - 2u) bad = true;
@@ -329,6 +342,26 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         e_lab[obase + j] = rnk[lab[j]];
     }
     if (__any_sync(kFull, bad) && lane == 0) *d_bad = 1;
+    if (n > 0) {
+        // bounding box of the atom's cloud voxels for the pair kernel (key-offset corner, dimensions).  A batch with a cloud the
+        // pair kernel's shared-memory frame cannot hold takes the hash-table path (d_bad[1]); d_bad[2] = widest bounding box edge
+        // of the batch = cell edge of the atom grid.
+        lo_c = __reduce_min_sync(kFull, lo_c);
+        lo_r = __reduce_min_sync(kFull, lo_r);
+        lo_s = __reduce_min_sync(kFull, lo_s);
+        hi_c = __reduce_max_sync(kFull, hi_c);
+        hi_r = __reduce_max_sync(kFull, hi_r);
+        hi_s = __reduce_max_sync(kFull, hi_s);
+        if (lane == 0) {
+            const int d0 = hi_c - lo_c + 1, d1 = hi_r - lo_r + 1, d2 = hi_s - lo_s + 1;
+            const int dmax = max(d0, max(d1, d2));
+            if (dmax > *(volatile int *)(d_bad + 2)) atomicMax(d_bad + 2, dmax);  // one hot address: only the rare increases go to the atomic unit
+            if (dmax > 15 || n > 1024 || (d0 + 2) * (d1 + 2) * (d2 + 2) > dil_cap) d_bad[1] = 1;
+            abox[a] = ((unsigned long long)(unsigned)(lo_c + kKeyOff) << 40) | ((unsigned long long)(unsigned)(lo_r + kKeyOff) << 26) |
+                      ((unsigned long long)(unsigned)(lo_s + kKeyOff) << 12) | ((unsigned long long)(d0 & 15) << 8) |
+                      ((unsigned long long)(d1 & 15) << 4) | (unsigned long long)(d2 & 15);
+        }
+    }
     // 7. per-cloud sums (fromCrsList) -> centroid distance; the nearest cloud (first minimum, :630-634)
     double best_dist = 0.0, best_sum = 0.0, bcx = 0.0, bcy = 0.0, bcz = 0.0;
     int best_n = 0;
@@ -368,6 +401,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         }
     }
     if (lane == 0) {
+        if (nroots > kPairClouds) d_bad[1] = 1;
         n_clouds[a] = (uint32_t)nroots;
         rec[0] = (double)nroots;
         rec[1] = (double)best_n;
@@ -435,7 +469,8 @@ __global__ void __launch_bounds__(kAggThreads)
 // ------------------------------------------------------------------------------------------------ pool voxel table
 __global__ void __launch_bounds__(kAggThreads)
     pool_insert_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint32_t *__restrict__ e_atom,
-                       const double *__restrict__ atom_out, AggTable t) {
+                       const double *__restrict__ atom_out, AggTable t, const int *__restrict__ flags) {
+    if (!flags[1]) return;  // the pair kernel handles this batch
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t atom = e_atom[i];
@@ -476,7 +511,9 @@ __global__ void __launch_bounds__(kAggThreads)
 // what the completeness test of :653-659 reads).
 __global__ void __launch_bounds__(kAggThreads)
     cloud_merge_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const uint16_t *__restrict__ e_lab,
-                       const int4 *__restrict__ info, AggTable t, uint32_t *parent_dom, uint32_t *parent_res, unsigned long long *adj) {
+                       const int4 *__restrict__ info, AggTable t, uint32_t *parent_dom, uint32_t *parent_res, unsigned long long *adj,
+                       const int *__restrict__ flags) {
+    if (!flags[1]) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t ai = t.node[i].y;
@@ -518,7 +555,8 @@ __global__ void __launch_bounds__(kAggThreads)
 // first[i] = 1 iff entry i is the first pool entry of its voxel: the SET semantics of DensityBlob.merge (pdb_eda/ccp4.py:575-586)
 __global__ void __launch_bounds__(kAggThreads)
     cloud_first_kernel(int64_t n, const unsigned long long *__restrict__ e_key, const int4 *__restrict__ info, AggTable t,
-                       uint8_t *__restrict__ first) {
+                       uint8_t *__restrict__ first, const int *__restrict__ flags) {
+    if (!flags[1]) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint8_t f = 0;
@@ -528,6 +566,257 @@ __global__ void __launch_bounds__(kAggThreads)
             f = mn == (uint32_t)i ? 1 : 0;
         }
         first[i] = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pair path
+// The same merge without a voxel table.  Clouds of two atoms can only touch when the atoms' boxes touch, an atom has a handful
+// of such neighbours, and a box is a few hundred voxels -- so instead of hashing every cloud voxel of the batch (55 M entries,
+// 14 dependent probes each: 45 of the 84 ms of a 256-structure pass) the ATOMS are binned into a grid of cells one box edge wide
+// (a hash table of n_atoms entries, one region per structure), and a warp that owns atom j
+//   1. lays j's clouds out in shared memory over the box grown by one voxel: per voxel a byte mask of the clouds of j that
+//      hold or touch it (27 ORs per cloud voxel) and the number of j's own entry at that voxel;
+//   2. looks up the 27 cells around j (one lane each) and, for every contributing atom i < j whose box touches j's, walks i's
+//      entries: a voxel that falls on a non-empty mask byte makes (cloud of i, clouds of j) pairs -- collected as a 64-bit
+//      mask and united ONCE per pair after the walk -- and a voxel that j holds too is not j's first entry (the SET semantics
+//      of DensityBlob.merge, pdb_eda/ccp4.py:575-586).
+// Union-find forests, adjacency masks and first flags are what cloud_merge_kernel / cloud_first_kernel produce.  Batches the
+// frame cannot hold (a box edge above 15 voxels, more than 1,024 box voxels, more than kPairClouds clouds on an atom) are flagged
+// by cloud_fill_kernel (flags[1]) and take the hash-table kernels instead.
+__device__ __forceinline__ void atom_region(const pe_batch_map *maps, uint32_t map_id, uint64_t &base, uint32_t &size) {
+    const pe_batch_map *m = maps + map_id;
+    base = 2ull * (uint64_t)m->atom_begin + 16ull * map_id;
+    size = (uint32_t)(2 * (m->atom_end - m->atom_begin) + 16);
+}
+__device__ __forceinline__ unsigned long long cell_key(uint32_t map_id, uint32_t cc, uint32_t cr, uint32_t cs) {
+    return ((unsigned long long)map_id << (3 * kKeyBits)) | ((unsigned long long)cc << (2 * kKeyBits)) | ((unsigned long long)cr << kKeyBits) |
+           (unsigned long long)cs;
+}
+
+__global__ void __launch_bounds__(kAggThreads)
+    atom_cell_insert_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
+                            const int4 *__restrict__ info, const unsigned long long *__restrict__ abox, AggSlot *aslot,
+                            uint32_t *__restrict__ anext, const int *__restrict__ flags) {
+    if (flags[1]) return;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_atoms) return;
+    uint32_t next = kAggNil;
+    if (info[a].w) {
+        const uint32_t E = (uint32_t)max(flags[2], 1);
+        const unsigned long long bx = abox[a];
+        const uint32_t map_id = (uint32_t)atom_map[a];
+        const unsigned long long key = cell_key(map_id, (uint32_t)(bx >> 40) / E, (uint32_t)((bx >> 26) & 0x3fffu) / E, (uint32_t)((bx >> 12) & 0x3fffu) / E);
+        uint64_t base;
+        uint32_t size;
+        atom_region(maps, map_id, base, size);
+        uint32_t h = agg_start(key, size);
+        for (;;) {
+            AggSlot *sl = aslot + base + h;
+            unsigned long long old = sl->key;
+            if (old == kAggEmpty) old = atomicCAS(&sl->key, (unsigned long long)kAggEmpty, key);
+            if (old == kAggEmpty || old == key) {
+                next = atomicExch(&sl->head, (uint32_t)a);
+                break;
+            }
+            h = h + 1 == size ? 0 : h + 1;
+        }
+    }
+    anext[a] = next;
+}
+
+__global__ void __launch_bounds__(kPairWarps * 32)
+    cloud_pair_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
+                      const uint32_t *__restrict__ offset, const unsigned long long *__restrict__ e_key, const uint16_t *__restrict__ e_lab,
+                      const int4 *__restrict__ info, const unsigned long long *__restrict__ abox, const AggSlot *__restrict__ aslot,
+                      const uint32_t *__restrict__ anext, uint32_t *parent_dom, uint32_t *parent_res, unsigned long long *adj,
+                      uint8_t *__restrict__ first, const int *__restrict__ flags, int dil_cap) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    if (flags[1]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kPairWarps + warp;
+    if (j >= n_atoms) return;
+    const int dil_bytes = (dil_cap + 3) & ~3, ent_bytes = 2 * ((dil_cap + 1) & ~1);
+    unsigned char *base = dyn_smem + (size_t)(dil_bytes + ent_bytes + 128 + 24 * kPairCand) * warp;
+    uint32_t *dil32 = reinterpret_cast<uint32_t *>(base);
+    const uint8_t *dil = base;
+    uint16_t *ent = reinterpret_cast<uint16_t *>(base + dil_bytes);
+    uint32_t *dup = reinterpret_cast<uint32_t *>(base + dil_bytes + ent_bytes);
+    const int4 me = info[j];
+    const uint32_t e0 = offset[j];
+    const int n = (int)(offset[j + 1] - e0);
+    if (!me.w) {
+        for (int e = lane; e < n; e += 32) first[e0 + e] = 0;
+        return;
+    }
+    const unsigned long long bx = abox[j];
+    const int uc0 = (int)(bx >> 40), ur0 = (int)((bx >> 26) & 0x3fffu), us0 = (int)((bx >> 12) & 0x3fffu);
+    const int D0 = (int)((bx >> 8) & 15u), D1 = (int)((bx >> 4) & 15u), D2 = (int)(bx & 15u);
+    const int G0 = D0 + 2, G1 = D1 + 2, G2 = D2 + 2, gvol = G0 * G1 * G2;
+    const int fc = uc0 - 1, fr = ur0 - 1, fs = us0 - 1;  // corner of the grown box
+    for (int w = lane; w < (gvol + 3) / 4; w += 32) dil32[w] = 0u;
+    for (int w = lane; w < (gvol + 1) / 2; w += 32) reinterpret_cast<uint32_t *>(ent)[w] = 0u;
+    dup[lane] = 0u;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+        const unsigned long long key = e_key[e0 + e];
+        const int x = (int)((key >> (2 * kKeyBits)) & 0x3fffu) - fc, y = (int)((key >> kKeyBits) & 0x3fffu) - fr, z = (int)(key & 0x3fffu) - fs;
+        const int p = (x * G1 + y) * G2 + z;
+        ent[p] = (uint16_t)(e + 1);
+        const uint32_t m = 1u << e_lab[e0 + e];
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc)
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+                for (int ds = -1; ds <= 1; ++ds) {
+                    const int q = p + (dc * G1 + dr) * G2 + ds;
+                    atomicOr(dil32 + (q >> 2), m << (8 * (q & 3)));
+                }
+    }
+    __syncwarp();
+    // Phase A: the 27 cells around j, one lane each; contributing atoms i < j whose box touches j's go to the warp's candidate
+    // list together with what phase B needs of them (all of a chain element's loads are independent: one round trip per element).
+    // Phase B: candidates four at a time, lanes over a candidate's entries (coalesced loads, four candidates in flight).
+    uint32_t *cand = dup + 32;  // kPairCand x 6 words: atom, first entry, entries, first cloud id, residue, index inside the residue
+    int ncand = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        for (int c0 = 0; c0 < ncand; c0 += 4) {
+            unsigned long long key[4];
+            uint32_t lab[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                key[u] = 0ull;
+                lab[u] = 0u;
+                if (c0 + u < ncand) {
+                    const uint32_t ei0 = cand[6 * (c0 + u) + 1], ni = cand[6 * (c0 + u) + 2];
+                    if ((uint32_t)lane < ni) {
+                        key[u] = e_key[ei0 + lane];
+                        lab[u] = e_lab[ei0 + lane];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (c0 + u >= ncand) break;  // warp-uniform
+                const uint32_t *cd = cand + 6 * (c0 + u);
+                const uint32_t i = cd[0], ei0 = cd[1], ni = cd[2];
+                uint32_t plo = 0u, phi = 0u;  // bit 8 * (cloud of i) + (cloud of j), as two words
+                for (uint32_t eb = 0; eb < ni; eb += 32) {
+                    unsigned long long k = key[u];
+                    uint32_t l = lab[u];
+                    const bool live = eb + lane < ni;
+                    if (eb > 0 && live) {  // more than 32 entries: the rest is loaded here
+                        k = e_key[ei0 + eb + lane];
+                        l = e_lab[ei0 + eb + lane];
+                    }
+                    if (live) {
+                        const int x = (int)((k >> (2 * kKeyBits)) & 0x3fffu) - fc, y = (int)((k >> kKeyBits) & 0x3fffu) - fr,
+                                  z = (int)(k & 0x3fffu) - fs;
+                        if ((unsigned)x < (unsigned)G0 && (unsigned)y < (unsigned)G1 && (unsigned)z < (unsigned)G2) {
+                            const int p = (x * G1 + y) * G2 + z;
+                            const uint32_t m = dil[p];
+                            if (m) {
+                                if (l < 4)
+                                    plo |= m << (8 * l);
+                                else
+                                    phi |= m << (8 * (l - 4));
+                                const uint32_t en = ent[p];
+                                if (en) atomicOr(dup + ((en - 1) >> 5), 1u << ((en - 1) & 31));
+                            }
+                        }
+                    }
+                }
+                plo = __reduce_or_sync(kFull, plo);
+                phi = __reduce_or_sync(kFull, phi);
+                if (!(plo | phi)) continue;
+                const bool same_res = cd[4] == (uint32_t)me.y;
+                // lane b unites the pair of bit b (and of bit b + 32)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (((h ? phi : plo) >> lane) & 1u) {
+                        const int bit = 32 * h + lane;
+                        const uint32_t ci = cd[3] + (uint32_t)(bit >> 3), cj = (uint32_t)me.x + (uint32_t)(bit & 7);
+                        uf_union(parent_dom, ci, cj);
+                        if (same_res) uf_union(parent_res, ci, cj);
+                    }
+                }
+                if (same_res && lane == 0) {
+                    const unsigned long long mi = 1ull << cd[5], mj = 1ull << me.z;
+                    if (!(adj[j] & mi)) atomicOr(adj + j, mi);
+                    if (!(adj[i] & mj)) atomicOr(adj + i, mj);
+                }
+            }
+        }
+        __syncwarp();
+        ncand = 0;
+    };
+    {
+        uint32_t i = kAggNil;
+        if (lane < 27) {
+            const int E = max(flags[2], 1);
+            const int cc = uc0 / E + lane / 9 - 1, cr = ur0 / E + (lane / 3) % 3 - 1, cs = us0 / E + lane % 3 - 1;
+            if (cc >= 0 && cr >= 0 && cs >= 0) {
+                const uint32_t map_id = (uint32_t)atom_map[j];
+                const unsigned long long key = cell_key(map_id, (uint32_t)cc, (uint32_t)cr, (uint32_t)cs);
+                uint64_t rbase;
+                uint32_t size;
+                atom_region(maps, map_id, rbase, size);
+                uint32_t h = agg_start(key, size);
+                for (;;) {
+                    const uint4 sl = __ldcg(reinterpret_cast<const uint4 *>(aslot + rbase + h));
+                    const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
+                    if (k == key) {
+                        i = sl.z;
+                        break;
+                    }
+                    if (k == kAggEmpty) break;
+                    h = h + 1 == size ? 0 : h + 1;
+                }
+            }
+        }
+        while (__any_sync(kFull, i != kAggNil)) {
+            bool take = false;
+            uint32_t cur = i, ei0 = 0u, ei1 = 0u;
+            int4 other = make_int4(0, 0, 0, 0);
+            if (i != kAggNil) {
+                const uint32_t nx = anext[i];
+                if ((int)i < j) {
+                    other = info[i];
+                    const unsigned long long bi = abox[i];
+                    ei0 = offset[i];
+                    ei1 = offset[i + 1];
+                    const int ic0 = (int)(bi >> 40), ir0 = (int)((bi >> 26) & 0x3fffu), is0 = (int)((bi >> 12) & 0x3fffu);
+                    take = other.w && !(ic0 > uc0 + D0 || uc0 > ic0 + (int)((bi >> 8) & 15u) || ir0 > ur0 + D1 || ur0 > ir0 + (int)((bi >> 4) & 15u) ||
+                                        is0 > us0 + D2 || us0 > is0 + (int)(bi & 15u));
+                }
+                i = nx;
+            }
+            const unsigned tm = __ballot_sync(kFull, take);
+            if (take) {
+                uint32_t *cd = cand + 6 * (ncand + __popc(tm & ((1u << lane) - 1u)));
+                cd[0] = cur;
+                cd[1] = ei0;
+                cd[2] = ei1 - ei0;
+                cd[3] = (uint32_t)other.x;
+                cd[4] = (uint32_t)other.y;
+                cd[5] = (uint32_t)other.z;
+            }
+            ncand += __popc(tm);
+            if (ncand > kPairCand - 32) flush();
+        }
+        flush();
+    }
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) first[e0 + e] = ((dup[e >> 5] >> (e & 31)) & 1u) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(kAggThreads) slot_clear_kernel(AggSlot *slot, int64_t n, const int *__restrict__ flags) {
+    if (!flags[1]) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        slot[i].key = kAggEmpty;
+        slot[i].head = kAggNil;
     }
 }
 
@@ -632,7 +921,7 @@ static int agg_grid(int64_t n) {
 
 struct AggLayout {
     int64_t cloud_count, cloud_start, scan, key, val, atom, lab, node, first, slots, info, parent_dom, parent_res, elec_dom,
-        elec_res, adj, res_mask, flags, total;
+        elec_res, adj, res_mask, flags, abox, aslot, anext, total;
 };
 
 static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residues, int64_t n_maps) {
@@ -662,6 +951,9 @@ static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residu
     L.elec_res = take(n_entries * 8);
     L.adj = take(n_atoms * 8);
     L.res_mask = take(n_residues * 8);
+    L.abox = take(n_atoms * 8);
+    L.aslot = take((2 * n_atoms + 16 * n_maps) * 16);  // atom grid of the pair path: every structure's region is twice its atoms (+ 16)
+    L.anext = take(n_atoms * 4);
     L.total = p;
     return L;
 }
@@ -732,8 +1024,21 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     unsigned long long *adj = (unsigned long long *)(ws + L.adj), *res_mask = (unsigned long long *)(ws + L.res_mask);
     const int64_t cap = 2 * n_entries + 16 * (int64_t)n_maps;
 
+    unsigned long long *abox = (unsigned long long *)(ws + L.abox);
+    AggSlot *aslot = (AggSlot *)(ws + L.aslot);
+    uint32_t *anext = (uint32_t *)(ws + L.anext);
+    // shared-memory frame of the pair kernel: the largest box grown by one voxel on every side (an atom whose grown box is larger
+    // sends the batch down the hash-table path)
+    int dil_cap = 5 * max_box_voxels + 64;
+    if (dil_cap > 4096) dil_cap = 4096;
+
     PE_CUDA(cudaMemsetAsync(d_bad, 0, 256, st));
-    PE_CUDA(cudaMemsetAsync(t.slot, 0xff, (size_t)cap * sizeof(AggSlot), st));
+    {
+        // PE_CLOUD_FORCE_HASH=1 sends every batch down the hash-table path (tests compare the two paths)
+        const char *force = getenv("PE_CLOUD_FORCE_HASH");
+        if (force && force[0] == '1') PE_CUDA(cudaMemsetAsync(d_bad + 1, 1, 1, st));
+    }
+    PE_CUDA(cudaMemsetAsync(aslot, 0xff, (size_t)(2 * (int64_t)n_atoms + 16 * (int64_t)n_maps) * sizeof(AggSlot), st));
     PE_CUDA(cudaMemsetAsync(elec_dom, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
     PE_CUDA(cudaMemsetAsync(elec_res, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
     PE_CUDA(cudaMemsetAsync(adj, 0, (size_t)n_atoms * 8, st));
@@ -748,7 +1053,8 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     const size_t smem = per_warp * warps;
     PE_CUDA(cudaFuncSetAttribute(cloud_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PE_LAUNCH("cloud_fill_kernel", st, cloud_fill_kernel<<<(n_atoms + warps - 1) / warps, warps * 32, smem, st>>>(
-        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, max_box_voxels, e_key, e_val, e_atom, e_lab, cloud_count, d_atom_out, d_bad));
+        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, max_box_voxels, e_key, e_val, e_atom, e_lab, cloud_count, d_atom_out, d_bad,
+        abox, dil_cap));
     PE_LAUNCH("cutoff_kernel", st, cutoff_kernel<<<n_maps, kAggThreads, 0, st>>>(d_maps, d_atom_out, d_map_out));
     // pass 2: contributing atoms, cloud ids
     PE_LAUNCH("accept_kernel", st, accept_kernel<<<(n_atoms + 1 + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
@@ -760,10 +1066,20 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
         PE_LAUNCH("iota_kernel", st, iota_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, parent_dom, parent_res));
         PE_LAUNCH("atom_info_kernel", st, atom_info_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
             n_atoms, cloud_start, d_atom_residue, d_atom_local, d_atom_out, info));
-        PE_LAUNCH("pool_insert_kernel", st, pool_insert_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t));
+        // pair path (atom grid + one warp per atom); the hash-table kernels return at once unless cloud_fill_kernel flagged the batch
+        PE_LAUNCH("atom_cell_insert_kernel", st, atom_cell_insert_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
+            d_maps, n_atoms, d_atom_map, info, abox, aslot, anext, d_bad));
+        {
+            const size_t pair_smem = (size_t)(((dil_cap + 3) & ~3) + 2 * ((dil_cap + 1) & ~1) + 128 + 24 * kPairCand) * kPairWarps;
+            PE_CUDA(cudaFuncSetAttribute(cloud_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+            PE_LAUNCH("cloud_pair_kernel", st, cloud_pair_kernel<<<(n_atoms + kPairWarps - 1) / kPairWarps, kPairWarps * 32, pair_smem, st>>>(
+                d_maps, n_atoms, d_atom_map, d_offset, e_key, e_lab, info, abox, aslot, anext, parent_dom, parent_res, adj, first, d_bad, dil_cap));
+        }
+        PE_LAUNCH("slot_clear_kernel", st, slot_clear_kernel<<<grid, kAggThreads, 0, st>>>(t.slot, cap, d_bad));
+        PE_LAUNCH("pool_insert_kernel", st, pool_insert_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t, d_bad));
         PE_LAUNCH("cloud_merge_kernel", st, cloud_merge_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_lab, info, t, parent_dom,
-                                                                                           parent_res, adj));
-        PE_LAUNCH("cloud_first_kernel", st, cloud_first_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, info, t, first));
+                                                                                           parent_res, adj, d_bad));
+        PE_LAUNCH("cloud_first_kernel", st, cloud_first_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, info, t, first, d_bad));
     }
     PE_LAUNCH("cloud_roots_kernel", st, cloud_roots_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
         n_atoms, d_atom_out, cloud_start, d_atom_electrons, parent_dom, parent_res, elec_dom, elec_res));

@@ -12,6 +12,7 @@ workspaces) and enqueues, without host synchronisation, the three voxel workload
 It is what ``bench.py`` times and what ``DensityAnalysis`` uses for its batched queries.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -35,6 +36,8 @@ class VoxelPass:
         self.region_radii = torch.full((self.n_atoms,), float(np.float32(regionRadius)), dtype=torch.float32, device=dev)
         self.res_start = _device._as_dev(residueStart, torch.int32, dev, (-1,))
         self.n_res = self.res_start.numel() - 1
+        self.overlap = os.environ.get("PE_STEP_OVERLAP", "1") != "0"
+        self.overlap_order = int(os.environ.get("PE_STEP_ORDER", "0"))
         if densityCutoff is None:
             m, s = densityDev.mean_std()
             densityCutoff = m + 1.5 * s
@@ -79,9 +82,34 @@ class VoxelPass:
                                      _ptr(self.blob_ws), _stream()), "pe_blob_label")
 
     def step(self):
-        self.cloud()
-        self.region()
-        self.blobs()
+        """One pass.  The blob pass reads only the Fo-Fc map and the sphere passes only the 2Fo-Fc map, so the two run on two
+        streams (fork / join by events): the HBM-bound threshold kernel overlaps the issue-bound sphere kernels, and the sphere
+        kernels fill the SMs that the latency-bound sparse labelling leaves idle.  ``overlap = False`` serialises them."""
+        if not self.overlap:
+            self.cloud()
+            self.region()
+            self.blobs()
+            return
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._fork.record(main)
+        self._side.wait_event(self._fork)
+        order = self.overlap_order
+        with torch.cuda.stream(self._side):
+            if order == 0:
+                self.blobs()
+            else:
+                self.cloud()
+                self.region()
+        if order == 0:
+            self.cloud()
+            self.region()
+        else:
+            self.blobs()
+        self._join.record(self._side)
+        main.wait_event(self._join)
 
     def stepFromHost(self, hostDensity, hostDiff, hostXyz=None):
         """One pass with HOST inputs (pinned float32 map payloads as read from the CCP4 files, optional float64 atom
