@@ -266,7 +266,9 @@ int pe_overlap_pairs(int64_t n, const int32_t *d_crs, const int32_t *d_owner, co
  *
  * pe_cloud_count:  d_offset (n_atoms + 1 uint32) = exclusive prefix sum of every atom's number of cloud voxels
  *                  (len(getSphereCrsFromXyz(dm, xyz, r, cutoff))); d_totals[0] = total, d_totals[1] = largest candidate box.
- *                  d_scan_ws: >= 256 + 4 * (n_atoms / 1024 + 2) bytes.
+ *                  d_scan_ws: >= 256 + 4 * (n_atoms / 1024 + 2) bytes.  d_box_bits (may be NULL; 8 uint32 per atom): the count
+ *                  pass leaves the membership bitmap of every candidate box of at most 256 voxels there, and pe_cloud_aggregate,
+ *                  given the same pointer, starts from it instead of enumerating the spheres a second time.
  * pe_cloud_aggregate (n_entries = d_totals[0], max_box_voxels = d_totals[1]) writes
  *   d_atom_out[a*8..]  number of clouds, voxels of the best (nearest-centroid) cloud, its centroid distance, its total
  *                      density, its centroid x y z, flags (0: does not contribute, 1: contributes, 3: contributes and is
@@ -285,12 +287,13 @@ typedef struct pe_batch_map {
 } pe_batch_map;
 int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_residues, int64_t n_maps);
 int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
-                   const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, void *stream);
+                   const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, uint32_t *d_box_bits, void *stream);
 int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map,
                        const double *d_xyz, const float *d_radius, const int32_t *d_atom_residue,
                        const int32_t *d_atom_local, const uint64_t *d_atom_bonded, const double *d_atom_electrons,
                        int32_t n_residues, const uint32_t *d_offset, int64_t n_entries, int32_t max_box_voxels,
-                       double min_cloud_electrons, double *d_atom_out, double *d_map_out, void *d_ws, void *stream);
+                       double min_cloud_electrons, const uint32_t *d_box_bits, double *d_atom_out, double *d_map_out, void *d_ws,
+                       void *stream);
 int pe_cloud_status(const void *d_ws, void *stream, int32_t *bad);
 /* The per-atom-type statistics block of aggregateCloud (pdb_eda/densityAnalysis.py:734-766) for every structure of a batch,
  * from the outputs of pe_cloud_aggregate: the second centroid filter (:746-748), then per (structure, atom type) the medians of

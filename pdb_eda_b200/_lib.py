@@ -86,8 +86,8 @@ SIGNATURES = {
     "pe_slab_relabel": (ctypes.c_int, [_GEOM, _I32, _I32, _P, _I64, _P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P]),
     "pe_slab_status": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32)]),
     "pe_cloud_workspace_bytes": (_I64, [_I64, _I64, _I64, _I64]),
-    "pe_cloud_count": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
-    "pe_cloud_aggregate": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, ctypes.c_double, _P, _P,
+    "pe_cloud_count": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pe_cloud_aggregate": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, ctypes.c_double, _P, _P, _P,
                                           _P, _P]),
     "pe_cloud_status": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32)]),
     "pe_cloud_statistics": (ctypes.c_int, [_I32, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, ctypes.c_double, _P, _P,

@@ -349,6 +349,7 @@ class CloudBatch:
         self.d_offset = torch.empty(nA + 1, dtype=torch.int32, device=device)
         self.d_totals = torch.zeros(2, dtype=torch.int64, device=device)
         self.d_scan = torch.empty(256 + 4 * (nA // 1024 + 4), dtype=torch.uint8, device=device)
+        self.d_boxBits = torch.empty((max(nA, 1), 8), dtype=torch.int32, device=device)  # count pass -> fill pass (pe_cloud_count)
         self.d_atomOut = torch.empty((nA, 8), dtype=torch.float64, device=device)
         self.d_mapOut = torch.empty((max(nS, 1), 8), dtype=torch.float64, device=device)
         self.d_scratch = torch.empty((9, max(nA, 1)), dtype=torch.float64, device=device)
@@ -381,7 +382,8 @@ class CloudBatch:
         if nS == 0:
             return
         check(self.lib.pe_cloud_count(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomMap), _ptr(self.d_xyz), _ptr(self.d_radius),
-                                      _ptr(self.d_offset), _ptr(self.d_totals), _ptr(self.d_scan), _stream()), "pe_cloud_count")
+                                      _ptr(self.d_offset), _ptr(self.d_totals), _ptr(self.d_scan), _ptr(self.d_boxBits), _stream()),
+              "pe_cloud_count")
         nEntries, maxBox = self.d_totals.tolist()
         self.nEntries = int(nEntries)
         need = int(self.lib.pe_cloud_workspace_bytes(nA, nEntries, self.nResidues, nS))
@@ -390,7 +392,7 @@ class CloudBatch:
         check(self.lib.pe_cloud_aggregate(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomMap), _ptr(self.d_xyz), _ptr(self.d_radius),
                                           _ptr(self.d_residue), _ptr(self.d_local), _ptr(self.d_bonded), _ptr(self.d_electrons),
                                           self.nResidues, _ptr(self.d_offset), nEntries, max(int(maxBox), 1),
-                                          ctypes.c_double(minCloudElectrons), _ptr(self.d_atomOut), _ptr(self.d_mapOut),
+                                          ctypes.c_double(minCloudElectrons), _ptr(self.d_boxBits), _ptr(self.d_atomOut), _ptr(self.d_mapOut),
                                           _ptr(self.ws), _stream()), "pe_cloud_aggregate")
         check(self.lib.pe_cloud_statistics(nS, _ptr(self.d_maps), nA, _ptr(self.d_atomOut), _ptr(self.d_mapOut), _ptr(self.d_static),
                                            _ptr(self.d_perm), self.nSegments, _ptr(self.d_segMap), _ptr(self.d_segType),

@@ -38,8 +38,10 @@ constexpr uint64_t kAggEmpty = ~0ull;
 constexpr uint32_t kAggNil = 0xffffffffu;
 constexpr int kKeyBits = 14;                 // per crs axis, offset 2^13: |index| < 8192
 constexpr int kKeyOff = 1 << (kKeyBits - 1);
+constexpr int kBoxBitWords = 8;              // candidate boxes of up to 256 voxels hand their bitmap from the count pass to the fill pass
 constexpr int kPairClouds = 8;               // clouds per atom the pair kernel's byte masks can name
 constexpr int kPairWarps = 4;
+constexpr int kPairList = 64;                // (cloud, cloud) pairs a warp collects before it unites them
 constexpr int kPairCand = 64;                // candidate atoms a warp collects before it walks their entries
 
 // Hash table of the pool voxels.  Every structure owns a REGION of the slot array (twice its number of cloud voxels), so the
@@ -96,9 +98,10 @@ __device__ __forceinline__ void load_geom(pe_geom *dst, const pe_batch_map *m, i
 __global__ void __launch_bounds__(kSphereWarps * 32)
     cloud_count_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
                        const double *__restrict__ xyz, const float *__restrict__ radius, uint32_t *__restrict__ count,
-                       unsigned long long *__restrict__ d_maxbox) {
+                       unsigned long long *__restrict__ d_maxbox, uint32_t *__restrict__ box_bits) {
     __shared__ AxisTab tabs[kSphereWarps][2];
     __shared__ pe_geom geoms[kSphereWarps];
+    __shared__ uint32_t wbits[kSphereWarps][kBoxBitWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a = blockIdx.x * kSphereWarps + warp;
     if (a >= n_atoms) return;
@@ -112,9 +115,28 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     double T;
     atom_box(g, ax, ay, az, radius[a], b, T);
     int n = 0;
-    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane,
-                    [&](int, int, int, bool, float v) { n += passes(v, cutoff) ? 1 : 0; });
+    // boxes of at most 32 * kBoxBitWords candidates also hand their membership bitmap (the reference's product order) to the
+    // fill pass, which then neither enumerates the sphere nor reads the candidates' densities a second time
+    const int D1 = b.dim[1], D2 = b.dim[2];
+    const bool keep = box_bits != nullptr && b.dim[0] * D1 * D2 <= 32 * kBoxBitWords;
+    if (keep) {
+        if (lane < kBoxBitWords) wbits[warp][lane] = 0u;
+        __syncwarp();
+    }
+    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
+        if (passes(v, cutoff)) {
+            ++n;
+            if (keep) {
+                const int p = (ic * D1 + ir) * D2 + is;
+                atomicOr(&wbits[warp][p >> 5], 1u << (p & 31));
+            }
+        }
+    });
     n = warp_sum(n);
+    if (keep) {
+        __syncwarp();
+        if (lane < kBoxBitWords) box_bits[(int64_t)a * kBoxBitWords + lane] = wbits[warp][lane];
+    }
     if (lane == 0) {
         count[a] = (uint32_t)n;
         atomicMax(d_maxbox, (unsigned long long)b.dim[0] * (unsigned long long)b.dim[1] * (unsigned long long)b.dim[2]);
@@ -132,7 +154,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
                                   const uint32_t *__restrict__ offset, int max_box, unsigned long long *__restrict__ e_key,
                                   float *__restrict__ e_val, uint32_t *__restrict__ e_atom, uint16_t *__restrict__ e_lab,
                                   uint32_t *__restrict__ n_clouds, double *__restrict__ atom_out, int *__restrict__ d_bad,
-                                  unsigned long long *__restrict__ abox, int dil_cap) {
+                                  unsigned long long *__restrict__ abox, int dil_cap, const uint32_t *__restrict__ box_bits) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ AxisTab tabs[kSphereWarps][2];
     __shared__ pe_geom geoms[kSphereWarps];
@@ -174,13 +196,18 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
     const int nw = (vol + 31) / 32;
     for (int w = lane; w < nw; w += 32) bits[w] = 0u;
     __syncwarp();
-    // 1. membership bits in the reference's order: p = (ic*D1 + ir)*D2 + is
-    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
-        if (passes(v, cutoff)) {
-            const int p = (ic * D1 + ir) * D2 + is;
-            atomicOr(bits + (p >> 5), 1u << (p & 31));
-        }
-    });
+    // 1. membership bits in the reference's order: p = (ic*D1 + ir)*D2 + is (from the count pass when it kept them)
+    if (box_bits != nullptr && vol <= 32 * kBoxBitWords) {
+        if (lane < nw) bits[lane] = box_bits[(int64_t)a * kBoxBitWords + lane];
+        __syncwarp();
+    } else {
+        for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
+            if (passes(v, cutoff)) {
+                const int p = (ic * D1 + ir) * D2 + is;
+                atomicOr(bits + (p >> 5), 1u << (p & 31));
+            }
+        });
+    }
     // 2. per-word prefix counts
     int running = 0;
     for (int w0 = 0; w0 < nw; w0 += 32) {
@@ -635,8 +662,8 @@ __global__ void __launch_bounds__(kPairWarps * 32)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * kPairWarps + warp;
     if (j >= n_atoms) return;
-    const int dil_bytes = (dil_cap + 3) & ~3, ent_bytes = 2 * ((dil_cap + 1) & ~1);
-    unsigned char *base = dyn_smem + (size_t)(dil_bytes + ent_bytes + 128 + 24 * kPairCand) * warp;
+    const int dil_bytes = (dil_cap + 7) & ~7, ent_bytes = 2 * ((dil_cap + 3) & ~3);
+    unsigned char *base = dyn_smem + (size_t)(dil_bytes + ent_bytes + 128 + 24 * kPairCand + 8 * kPairList) * warp;
     uint32_t *dil32 = reinterpret_cast<uint32_t *>(base);
     const uint8_t *dil = base;
     uint16_t *ent = reinterpret_cast<uint16_t *>(base + dil_bytes);
@@ -679,6 +706,25 @@ __global__ void __launch_bounds__(kPairWarps * 32)
     // Phase B: candidates four at a time, lanes over a candidate's entries (coalesced loads, four candidates in flight).
     uint32_t *cand = dup + 32;  // kPairCand x 6 words: atom, first entry, entries, first cloud id, residue, index inside the residue
     int ncand = 0;
+    uint2 *plist = reinterpret_cast<uint2 *>(cand + 6 * kPairCand);
+    int npair = 0;
+    unsigned long long adj_j = 0ull;  // atoms of j's residue whose clouds touch j's (warp-uniform)
+    // Pairs are united lane-parallel, two lanes per pair (domain forest / residue forest): a union-find operation is half a dozen
+    // dependent loads, and doing them one pair after the other was 4 of the kernel's 19 ms.  (Recording the pairs in a global
+    // edge list and uniting them in a kernel of their own, one thread per edge, was slower in total: 10.8 + 5.2 ms against 14.9 ms.)
+    auto drain = [&]() {
+        __syncwarp();
+        for (int t = lane; t < 2 * npair; t += 32) {
+            const uint2 pr = plist[t >> 1];
+            const uint32_t ci = pr.x & 0x7fffffffu;
+            if (!(t & 1))
+                uf_union(parent_dom, ci, pr.y);
+            else if (pr.x >> 31)
+                uf_union(parent_res, ci, pr.y);
+        }
+        __syncwarp();
+        npair = 0;
+    };
     auto flush = [&]() {
         __syncwarp();
         for (int c0 = 0; c0 < ncand; c0 += 4) {
@@ -731,23 +777,27 @@ __global__ void __launch_bounds__(kPairWarps * 32)
                 phi = __reduce_or_sync(kFull, phi);
                 if (!(plo | phi)) continue;
                 const bool same_res = cd[4] == (uint32_t)me.y;
-                // lane b unites the pair of bit b (and of bit b + 32)
+                // the (cloud of i, cloud of j) pairs go to the warp's pair list; they are united lane-parallel (drain) so that the
+                // dependent loads of one union-find operation overlap those of the others instead of following them
+                const int nlo = __popc(plo), nhi = __popc(phi);
+                if (npair + nlo + nhi > kPairList) drain();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (((h ? phi : plo) >> lane) & 1u) {
+                    const uint32_t w = h ? phi : plo;
+                    if ((w >> lane) & 1u) {
                         const int bit = 32 * h + lane;
-                        const uint32_t ci = cd[3] + (uint32_t)(bit >> 3), cj = (uint32_t)me.x + (uint32_t)(bit & 7);
-                        uf_union(parent_dom, ci, cj);
-                        if (same_res) uf_union(parent_res, ci, cj);
+                        const int at = npair + (h ? nlo : 0) + __popc(w & ((1u << lane) - 1u));
+                        plist[at] = make_uint2((cd[3] + (uint32_t)(bit >> 3)) | (same_res ? 0x80000000u : 0u), (uint32_t)me.x + (uint32_t)(bit & 7));
                     }
                 }
-                if (same_res && lane == 0) {
-                    const unsigned long long mi = 1ull << cd[5], mj = 1ull << me.z;
-                    if (!(adj[j] & mi)) atomicOr(adj + j, mi);
-                    if (!(adj[i] & mj)) atomicOr(adj + i, mj);
+                npair += nlo + nhi;
+                if (same_res) {
+                    adj_j |= 1ull << cd[5];
+                    if (lane == 0) atomicOr(adj + i, 1ull << me.z);  // result unused: a fire-and-forget reduction
                 }
             }
         }
+        drain();
         __syncwarp();
         ncand = 0;
     };
@@ -808,6 +858,7 @@ __global__ void __launch_bounds__(kPairWarps * 32)
         flush();
     }
     __syncwarp();
+    if (lane == 0 && adj_j) atomicOr(adj + j, adj_j);
     for (int e = lane; e < n; e += 32) first[e0 + e] = ((dup[e >> 5] >> (e & 31)) & 1u) ? 0 : 1;
 }
 
@@ -970,7 +1021,7 @@ int64_t pe_cloud_workspace_bytes(int64_t n_atoms, int64_t n_entries, int64_t n_r
 }
 
 int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
-                   const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, void *stream) {
+                   const float *d_radius, uint32_t *d_offset, int64_t *d_totals, void *d_scan_ws, uint32_t *d_box_bits, void *stream) {
     PE_CHECK_ARG(n_maps >= 0 && n_atoms >= 0 && d_totals, "pe_cloud_count: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     PE_CUDA(cudaMemsetAsync(d_totals, 0, 2 * sizeof(int64_t), st));
@@ -981,7 +1032,7 @@ int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, 
     PE_CUDA(cudaMemsetAsync(d_offset + n_atoms, 0, sizeof(uint32_t), st));
     const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
     PE_LAUNCH("cloud_count_kernel", st, cloud_count_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(
-        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, (unsigned long long *)(d_totals + 1)));
+        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, (unsigned long long *)(d_totals + 1), d_box_bits));
     PE_LAUNCH_CHECK();
     return exclusive_scan_u32(d_offset, d_offset, (int64_t)n_atoms + 1, nullptr, d_totals, d_scan_ws, st, false);
 }
@@ -989,8 +1040,8 @@ int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, 
 int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, const int32_t *d_atom_map, const double *d_xyz,
                        const float *d_radius, const int32_t *d_atom_residue, const int32_t *d_atom_local,
                        const uint64_t *d_atom_bonded, const double *d_atom_electrons, int32_t n_residues, const uint32_t *d_offset,
-                       int64_t n_entries, int32_t max_box_voxels, double min_cloud_electrons, double *d_atom_out, double *d_map_out,
-                       void *d_ws, void *stream) {
+                       int64_t n_entries, int32_t max_box_voxels, double min_cloud_electrons, const uint32_t *d_box_bits,
+                       double *d_atom_out, double *d_map_out, void *d_ws, void *stream) {
     PE_CHECK_ARG(n_maps >= 0 && n_atoms >= 0 && n_residues >= 0 && n_entries >= 0, "pe_cloud_aggregate: negative size");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_maps == 0) return PE_OK;
@@ -1054,7 +1105,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     PE_CUDA(cudaFuncSetAttribute(cloud_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PE_LAUNCH("cloud_fill_kernel", st, cloud_fill_kernel<<<(n_atoms + warps - 1) / warps, warps * 32, smem, st>>>(
         d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, max_box_voxels, e_key, e_val, e_atom, e_lab, cloud_count, d_atom_out, d_bad,
-        abox, dil_cap));
+        abox, dil_cap, d_box_bits));
     PE_LAUNCH("cutoff_kernel", st, cutoff_kernel<<<n_maps, kAggThreads, 0, st>>>(d_maps, d_atom_out, d_map_out));
     // pass 2: contributing atoms, cloud ids
     PE_LAUNCH("accept_kernel", st, accept_kernel<<<(n_atoms + 1 + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
@@ -1070,7 +1121,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
         PE_LAUNCH("atom_cell_insert_kernel", st, atom_cell_insert_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
             d_maps, n_atoms, d_atom_map, info, abox, aslot, anext, d_bad));
         {
-            const size_t pair_smem = (size_t)(((dil_cap + 3) & ~3) + 2 * ((dil_cap + 1) & ~1) + 128 + 24 * kPairCand) * kPairWarps;
+            const size_t pair_smem = (size_t)(((dil_cap + 7) & ~7) + 2 * ((dil_cap + 3) & ~3) + 128 + 24 * kPairCand + 8 * kPairList) * kPairWarps;
             PE_CUDA(cudaFuncSetAttribute(cloud_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
             PE_LAUNCH("cloud_pair_kernel", st, cloud_pair_kernel<<<(n_atoms + kPairWarps - 1) / kPairWarps, kPairWarps * 32, pair_smem, st>>>(
                 d_maps, n_atoms, d_atom_map, d_offset, e_key, e_lab, info, abox, aslot, anext, parent_dom, parent_res, adj, first, d_bad, dil_cap));
