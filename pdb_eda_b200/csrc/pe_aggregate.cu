@@ -681,16 +681,47 @@ __global__ void __launch_bounds__(kPairWarps * 32)
     const int D0 = (int)((bx >> 8) & 15u), D1 = (int)((bx >> 4) & 15u), D2 = (int)(bx & 15u);
     const int G0 = D0 + 2, G1 = D1 + 2, G2 = D2 + 2, gvol = G0 * G1 * G2;
     const int fc = uc0 - 1, fr = ur0 - 1, fs = us0 - 1;  // corner of the grown box
+    // the loads of j's own entries are issued first and used after the cell look-up below, whose round trip they share
+    unsigned long long own_key = 0ull;
+    uint32_t own_lab = 0u;
+    if (lane < n) {
+        own_key = e_key[e0 + lane];
+        own_lab = e_lab[e0 + lane];
+    }
+    // the 27 cells around j, one lane each: head of the cell's chain of atoms
+    uint32_t i = kAggNil;
+    if (lane < 27) {
+        const int E = max(flags[2], 1);
+        const int cc = uc0 / E + lane / 9 - 1, cr = ur0 / E + (lane / 3) % 3 - 1, cs = us0 / E + lane % 3 - 1;
+        if (cc >= 0 && cr >= 0 && cs >= 0) {
+            const uint32_t map_id = (uint32_t)atom_map[j];
+            const unsigned long long key = cell_key(map_id, (uint32_t)cc, (uint32_t)cr, (uint32_t)cs);
+            uint64_t rbase;
+            uint32_t size;
+            atom_region(maps, map_id, rbase, size);
+            uint32_t h = agg_start(key, size);
+            for (;;) {
+                const uint4 sl = __ldcg(reinterpret_cast<const uint4 *>(aslot + rbase + h));
+                const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
+                if (k == key) {
+                    i = sl.z;
+                    break;
+                }
+                if (k == kAggEmpty) break;
+                h = h + 1 == size ? 0 : h + 1;
+            }
+        }
+    }
     for (int w = lane; w < (gvol + 3) / 4; w += 32) dil32[w] = 0u;
     for (int w = lane; w < (gvol + 1) / 2; w += 32) reinterpret_cast<uint32_t *>(ent)[w] = 0u;
     dup[lane] = 0u;
     __syncwarp();
     for (int e = lane; e < n; e += 32) {
-        const unsigned long long key = e_key[e0 + e];
+        const unsigned long long key = e < 32 ? own_key : e_key[e0 + e];
         const int x = (int)((key >> (2 * kKeyBits)) & 0x3fffu) - fc, y = (int)((key >> kKeyBits) & 0x3fffu) - fr, z = (int)(key & 0x3fffu) - fs;
         const int p = (x * G1 + y) * G2 + z;
         ent[p] = (uint16_t)(e + 1);
-        const uint32_t m = 1u << e_lab[e0 + e];
+        const uint32_t m = 1u << (e < 32 ? own_lab : (uint32_t)e_lab[e0 + e]);
 #pragma unroll
         for (int dc = -1; dc <= 1; ++dc)
 #pragma unroll
@@ -803,29 +834,6 @@ __global__ void __launch_bounds__(kPairWarps * 32)
         ncand = 0;
     };
     {
-        uint32_t i = kAggNil;
-        if (lane < 27) {
-            const int E = max(flags[2], 1);
-            const int cc = uc0 / E + lane / 9 - 1, cr = ur0 / E + (lane / 3) % 3 - 1, cs = us0 / E + lane % 3 - 1;
-            if (cc >= 0 && cr >= 0 && cs >= 0) {
-                const uint32_t map_id = (uint32_t)atom_map[j];
-                const unsigned long long key = cell_key(map_id, (uint32_t)cc, (uint32_t)cr, (uint32_t)cs);
-                uint64_t rbase;
-                uint32_t size;
-                atom_region(maps, map_id, rbase, size);
-                uint32_t h = agg_start(key, size);
-                for (;;) {
-                    const uint4 sl = __ldcg(reinterpret_cast<const uint4 *>(aslot + rbase + h));
-                    const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
-                    if (k == key) {
-                        i = sl.z;
-                        break;
-                    }
-                    if (k == kAggEmpty) break;
-                    h = h + 1 == size ? 0 : h + 1;
-                }
-            }
-        }
         while (__any_sync(kFull, i != kAggNil)) {
             bool take = false;
             uint32_t cur = i, ei0 = 0u, ei1 = 0u;
