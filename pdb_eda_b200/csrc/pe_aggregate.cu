@@ -246,17 +246,18 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         // 56 % of the kernel's instructions: 27 bit tests and label look-ups per voxel and round.)
         uint32_t nfs = 0u, nls = 0u, nfr = 0u, nlr = 0u;  // source voxels that may move -1 / +1 along sections, -1 / +1 along rows
         {
-            const int p0 = 32 * lane;
-            int is = p0 % D2, ir = (p0 / D2) % D1;
-            for (int j = 0; j < 32; ++j) {
+            // only the lane's own voxels ever move, so the masks are formed for its set bits only (the loop over all 32 positions
+            // of every lane was 27 % of the kernel's instructions); p / D by multiplication: exact for p < 1,024, D <= 32
+            const uint32_t m2 = (65536u + (uint32_t)D2 - 1u) / (uint32_t)D2, m1 = (65536u + (uint32_t)D1 - 1u) / (uint32_t)D1;
+            for (uint32_t c = lane < nw ? bits[lane] : 0u; c; c &= c - 1u) {
+                const int j = __ffs((int)c) - 1;
+                const uint32_t p = 32u * (uint32_t)lane + (uint32_t)j;
+                const uint32_t q = D2 <= 32 ? (p * m2) >> 16 : p / (uint32_t)D2;
+                const int is = (int)(p - q * (uint32_t)D2), ir = (int)(D1 <= 32 ? q - ((q * m1) >> 16) * (uint32_t)D1 : q % (uint32_t)D1);
                 nfs |= (is != 0 ? 1u : 0u) << j;
                 nls |= (is != D2 - 1 ? 1u : 0u) << j;
                 nfr |= (ir != 0 ? 1u : 0u) << j;
                 nlr |= (ir != D1 - 1 ? 1u : 0u) << j;
-                if (++is == D2) {
-                    is = 0;
-                    if (++ir == D1) ir = 0;
-                }
             }
         }
         auto shl = [&](uint32_t v, int k) {  // the bit string moved k positions up

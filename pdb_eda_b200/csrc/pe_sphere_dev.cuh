@@ -89,15 +89,40 @@ __device__ __forceinline__ void for_each_inside(const pe_geom &g, const float *_
                 const double sqo = to.sq[ko];
                 const int offo = to.off[ko];
                 const double P = __dadd_rn(sqc, sqo);
-                for (int ki = 0; ki < Di; ++ki) {
-                    const double sqi = ti.sq[ki];
-                    const int offi = ti.off[ki];
-                    const double d2 = caseb ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
-                    if (!(d2 <= T)) continue;
-                    const bool ok = (offc | offo | offi) >= 0;
-                    const float v = ok ? __ldg(rho + (offc + offo + offi)) : 0.f;
-                    const int ir = inner == 1 ? ki : ko, is = inner == 2 ? ki : ko;
-                    f(ic, ir, is, ok, v);
+                // membership of the whole line first, then the gathers four at a time: with the load behind the distance test of
+                // its own iteration a lane paid one memory round trip per in-sphere voxel (24 % of the count pass's stall samples)
+                for (int kb = 0; kb < Di; kb += 32) {
+                    uint32_t inside = 0u;
+                    const int ke = min(Di - kb, 32);
+                    for (int ki = 0; ki < ke; ++ki) {
+                        const double sqi = ti.sq[kb + ki];
+                        const double d2 = caseb ? __dadd_rn(__dadd_rn(sqo, sqi), sqc) : __dadd_rn(P, sqi);
+                        inside |= (d2 <= T ? 1u : 0u) << ki;
+                    }
+                    while (inside) {
+                        int kk[4];
+                        float vv[4];
+                        bool okk[4], has[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            has[u] = inside != 0u;
+                            kk[u] = kb + __ffs((int)inside) - 1;
+                            inside &= inside - 1u;
+                            vv[u] = 0.f;
+                            okk[u] = false;
+                            if (has[u]) {
+                                const int offi = ti.off[kk[u]];
+                                okk[u] = (offc | offo | offi) >= 0;
+                                if (okk[u]) vv[u] = __ldg(rho + (offc + offo + offi));
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!has[u]) continue;
+                            const int ir = inner == 1 ? kk[u] : ko, is = inner == 2 ? kk[u] : ko;
+                            f(ic, ir, is, okk[u], vv[u]);
+                        }
+                    }
                 }
             }
         }

@@ -36,7 +36,7 @@ class VoxelPass:
         self.region_radii = torch.full((self.n_atoms,), float(np.float32(regionRadius)), dtype=torch.float32, device=dev)
         self.res_start = _device._as_dev(residueStart, torch.int32, dev, (-1,))
         self.n_res = self.res_start.numel() - 1
-        self.overlap = os.environ.get("PE_STEP_OVERLAP", "1") != "0"
+        self.overlap = os.environ.get("PE_STEP_OVERLAP", "0") != "0"
         self.overlap_order = int(os.environ.get("PE_STEP_ORDER", "0"))
         if densityCutoff is None:
             m, s = densityDev.mean_std()
