@@ -741,20 +741,36 @@ def main_c3(args, rank, world, local_rank):
         # rank 0's share of the pool for the per-kernel lines (kernel times are rank 0's)
         dominant = kernels[0] if kernels else None
         roof = None
+        # algorithmic bytes per launch on rank 0: (bytes per pool voxel, per atom, per sphere voxel)
+        c3_bytes = {
+            "cloud_pair_kernel": (11.0, 48.0, 0.0, "latency",
+                                  "one warp per atom: its clouds as byte masks in shared memory, neighbour atoms from the per-structure "
+                                  "cell grid, their voxels tested against the masks, (cloud, cloud) pairs united in two union-find "
+                                  "forests: dependent random loads (cell slot -> chain -> entries -> parents), bound by their latency; "
+                                  "algorithmic bytes = key + cloud number (10 B) read and first flag (1 B) written per pool voxel, "
+                                  "48 B of records per atom"),
+            "cloud_fill_kernel": (22.0, 132.0, 0.0, "issue",
+                                  "one warp per atom: bitmap from the count pass -> ordered voxel list -> bit-parallel flood fill -> "
+                                  "entries (key, density, owner, cloud: 18 B written + 4 B gathered per pool voxel) -> per-cloud sums; "
+                                  "issue slots 60 % busy (profiles/r02_c3_pool.md), not a streaming kernel"),
+            "cloud_count_kernel": (0.0, 64.0, 4.0, "issue",
+                                   "one warp per atom: sphere enumeration with exact float64 distance tests + one 4-byte gather per "
+                                   "in-sphere voxel; 64 B per atom (coordinates, radius, count, bitmap for the fill pass)"),
+            "cloud_merge_kernel": (30.0, 16.0, 0.0, "latency",
+                                   "hash-table path (batches the pair kernel cannot hold): 14 table probes per pool voxel + union-find"),
+        }
         if dominant is not None:
-            # algorithmic bytes of the dominant kernel on rank 0: per pool voxel the packed key (8),
-            # owner (4) and cloud number (2) read once + one 16-byte table slot; per atom its 16-byte record
             r0_entries = all_entries / world
             r0_atoms = all_atoms / world
-            per_launch = (30.0 * r0_entries + 16.0 * r0_atoms) / max(dominant["launches"] / args.steps, 1)
+            r0_sphere = all_units / world
+            pe, pa, ps, bound, note = c3_bytes.get(dominant["kernel"], (0.0, 0.0, 0.0, "latency", "no algorithmic byte model for this kernel"))
+            per_launch = (pe * r0_entries + pa * r0_atoms + ps * r0_sphere) / max(dominant["launches"] / args.steps, 1)
             t = dominant["ms_total"] / max(dominant["launches"], 1) * 1e-3
             ach = per_launch / t / 1e9
-            roof = {"kernel": dominant["kernel"], "bound": "latency", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            roof = {"kernel": dominant["kernel"], "bound": bound, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
                     "us_per_launch": dominant["us_per_launch"],
-                    "note": "hash-table neighbour probes of the pool voxels (14 per voxel) + union-find: random 16-byte accesses, "
-                            "bound by memory latency / L2 sector rate, not by streaming bandwidth; algorithmic bytes = 30 B per "
-                            "pool voxel + 16 B per atom on rank 0 (an even share of the pool is assumed)"}
+                    "note": note + "; rank 0's share of the pool (an even share is assumed)"}
         value = all_units / (ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -155,7 +155,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
                                   const uint32_t *__restrict__ offset, int max_box, unsigned long long *__restrict__ e_key,
                                   float *__restrict__ e_val, uint32_t *__restrict__ e_atom, uint16_t *__restrict__ e_lab,
                                   uint32_t *__restrict__ n_clouds, double *__restrict__ atom_out, int *__restrict__ d_bad,
-                                  unsigned long long *__restrict__ abox, int dil_cap, const uint32_t *__restrict__ box_bits) {
+                                  unsigned long long *__restrict__ abox, int dil_cap, const uint32_t *__restrict__ box_bits, int *__restrict__ cell_edge) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ AxisTab tabs[kSphereWarps][2];
     __shared__ pe_geom geoms[kSphereWarps];
@@ -373,7 +373,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
     if (__any_sync(kFull, bad) && lane == 0) *d_bad = 1;
     if (n > 0) {
         // bounding box of the atom's cloud voxels for the pair kernel (key-offset corner, dimensions).  A batch with a cloud the
-        // pair kernel's shared-memory frame cannot hold takes the hash-table path (d_bad[1]); d_bad[2] = widest bounding box edge
+        // pair kernel's shared-memory frame cannot hold takes the hash-table path (d_bad[1]); cell_edge[structure] = widest bounding box edge
         // of the batch = cell edge of the atom grid.
         lo_c = __reduce_min_sync(kFull, lo_c);
         lo_r = __reduce_min_sync(kFull, lo_r);
@@ -384,7 +384,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         if (lane == 0) {
             const int d0 = hi_c - lo_c + 1, d1 = hi_r - lo_r + 1, d2 = hi_s - lo_s + 1;
             const int dmax = max(d0, max(d1, d2));
-            if (dmax > *(volatile int *)(d_bad + 2)) atomicMax(d_bad + 2, dmax);  // one hot address: only the rare increases go to the atomic unit
+            if (dmax > *(volatile int *)(cell_edge + map_id)) atomicMax(cell_edge + map_id, dmax);  // hot addresses: only the rare increases go to the atomic unit
             if (dmax > 15 || n > 1024 || (d0 + 2) * (d1 + 2) * (d2 + 2) > dil_cap) d_bad[1] = 1;
             abox[a] = ((unsigned long long)(unsigned)(lo_c + kKeyOff) << 40) | ((unsigned long long)(unsigned)(lo_r + kKeyOff) << 26) |
                       ((unsigned long long)(unsigned)(lo_s + kKeyOff) << 12) | ((unsigned long long)(d0 & 15) << 8) |
@@ -625,13 +625,13 @@ __device__ __forceinline__ unsigned long long cell_key(uint32_t map_id, uint32_t
 __global__ void __launch_bounds__(kAggThreads)
     atom_cell_insert_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
                             const int4 *__restrict__ info, const unsigned long long *__restrict__ abox, AggSlot *aslot,
-                            uint32_t *__restrict__ anext, const int *__restrict__ flags) {
+                            uint32_t *__restrict__ anext, const int *__restrict__ flags, const int *__restrict__ cell_edge) {
     if (flags[1]) return;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n_atoms) return;
     uint32_t next = kAggNil;
     if (info[a].w) {
-        const uint32_t E = (uint32_t)max(flags[2], 1);
+        const uint32_t E = (uint32_t)max(cell_edge[atom_map[a]], 1);
         const unsigned long long bx = abox[a];
         const uint32_t map_id = (uint32_t)atom_map[a];
         const unsigned long long key = cell_key(map_id, (uint32_t)(bx >> 40) / E, (uint32_t)((bx >> 26) & 0x3fffu) / E, (uint32_t)((bx >> 12) & 0x3fffu) / E);
@@ -653,12 +653,15 @@ __global__ void __launch_bounds__(kAggThreads)
     anext[a] = next;
 }
 
-__global__ void __launch_bounds__(kPairWarps * 32)
+#ifndef PE_PAIR_MINB
+#define PE_PAIR_MINB 1
+#endif
+__global__ void __launch_bounds__(kPairWarps * 32, PE_PAIR_MINB)
     cloud_pair_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
                       const uint32_t *__restrict__ offset, const unsigned long long *__restrict__ e_key, const uint16_t *__restrict__ e_lab,
                       const int4 *__restrict__ info, const unsigned long long *__restrict__ abox, const AggSlot *__restrict__ aslot,
                       const uint32_t *__restrict__ anext, uint32_t *parent_dom, uint32_t *parent_res, unsigned long long *adj,
-                      uint8_t *__restrict__ first, const int *__restrict__ flags, int dil_cap) {
+                      uint8_t *__restrict__ first, const int *__restrict__ flags, int dil_cap, const int *__restrict__ cell_edge) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     if (flags[1]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -692,7 +695,7 @@ __global__ void __launch_bounds__(kPairWarps * 32)
     // the 27 cells around j, one lane each: head of the cell's chain of atoms
     uint32_t i = kAggNil;
     if (lane < 27) {
-        const int E = max(flags[2], 1);
+        const int E = max(cell_edge[atom_map[j]], 1);
         const int cc = uc0 / E + lane / 9 - 1, cr = ur0 / E + (lane / 3) % 3 - 1, cs = us0 / E + lane % 3 - 1;
         if (cc >= 0 && cr >= 0 && cs >= 0) {
             const uint32_t map_id = (uint32_t)atom_map[j];
@@ -987,7 +990,7 @@ static int agg_grid(int64_t n) {
 
 struct AggLayout {
     int64_t cloud_count, cloud_start, scan, key, val, atom, lab, node, first, slots, info, parent_dom, parent_res, elec_dom,
-        elec_res, adj, res_mask, flags, abox, aslot, anext, total;
+        elec_res, adj, res_mask, flags, abox, aslot, anext, cell_edge, total;
 };
 
 static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residues, int64_t n_maps) {
@@ -1020,6 +1023,7 @@ static AggLayout agg_layout(int64_t n_atoms, int64_t n_entries, int64_t n_residu
     L.abox = take(n_atoms * 8);
     L.aslot = take((2 * n_atoms + 16 * n_maps) * 16);  // atom grid of the pair path: every structure's region is twice its atoms (+ 16)
     L.anext = take(n_atoms * 4);
+    L.cell_edge = take(n_maps * 4);  // per structure: widest cloud bounding box edge = edge of its atom grid's cells
     L.total = p;
     return L;
 }
@@ -1093,6 +1097,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     unsigned long long *abox = (unsigned long long *)(ws + L.abox);
     AggSlot *aslot = (AggSlot *)(ws + L.aslot);
     uint32_t *anext = (uint32_t *)(ws + L.anext);
+    int *cell_edge = (int *)(ws + L.cell_edge);
     // shared-memory frame of the pair kernel: the largest box grown by one voxel on every side (an atom whose grown box is larger
     // sends the batch down the hash-table path)
     int dil_cap = 5 * max_box_voxels + 64;
@@ -1104,6 +1109,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
         const char *force = getenv("PE_CLOUD_FORCE_HASH");
         if (force && force[0] == '1') PE_CUDA(cudaMemsetAsync(d_bad + 1, 1, 1, st));
     }
+    PE_CUDA(cudaMemsetAsync(cell_edge, 0, (size_t)n_maps * sizeof(int), st));
     PE_CUDA(cudaMemsetAsync(aslot, 0xff, (size_t)(2 * (int64_t)n_atoms + 16 * (int64_t)n_maps) * sizeof(AggSlot), st));
     PE_CUDA(cudaMemsetAsync(elec_dom, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
     PE_CUDA(cudaMemsetAsync(elec_res, 0, (size_t)(n_entries > 0 ? n_entries : 1) * 8, st));
@@ -1120,7 +1126,7 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     PE_CUDA(cudaFuncSetAttribute(cloud_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PE_LAUNCH("cloud_fill_kernel", st, cloud_fill_kernel<<<(n_atoms + warps - 1) / warps, warps * 32, smem, st>>>(
         d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, max_box_voxels, e_key, e_val, e_atom, e_lab, cloud_count, d_atom_out, d_bad,
-        abox, dil_cap, d_box_bits));
+        abox, dil_cap, d_box_bits, cell_edge));
     PE_LAUNCH("cutoff_kernel", st, cutoff_kernel<<<n_maps, kSummaryThreads, 0, st>>>(d_maps, d_atom_out, d_map_out));
     // pass 2: contributing atoms, cloud ids
     PE_LAUNCH("accept_kernel", st, accept_kernel<<<(n_atoms + 1 + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
@@ -1134,12 +1140,12 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
             n_atoms, cloud_start, d_atom_residue, d_atom_local, d_atom_out, info));
         // pair path (atom grid + one warp per atom); the hash-table kernels return at once unless cloud_fill_kernel flagged the batch
         PE_LAUNCH("atom_cell_insert_kernel", st, atom_cell_insert_kernel<<<(n_atoms + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
-            d_maps, n_atoms, d_atom_map, info, abox, aslot, anext, d_bad));
+            d_maps, n_atoms, d_atom_map, info, abox, aslot, anext, d_bad, cell_edge));
         {
             const size_t pair_smem = (size_t)(((dil_cap + 7) & ~7) + 2 * ((dil_cap + 3) & ~3) + 128 + 24 * kPairCand + 8 * kPairList) * kPairWarps;
             PE_CUDA(cudaFuncSetAttribute(cloud_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
             PE_LAUNCH("cloud_pair_kernel", st, cloud_pair_kernel<<<(n_atoms + kPairWarps - 1) / kPairWarps, kPairWarps * 32, pair_smem, st>>>(
-                d_maps, n_atoms, d_atom_map, d_offset, e_key, e_lab, info, abox, aslot, anext, parent_dom, parent_res, adj, first, d_bad, dil_cap));
+                d_maps, n_atoms, d_atom_map, d_offset, e_key, e_lab, info, abox, aslot, anext, parent_dom, parent_res, adj, first, d_bad, dil_cap, cell_edge));
         }
         PE_LAUNCH("slot_clear_kernel", st, slot_clear_kernel<<<grid, kAggThreads, 0, st>>>(t.slot, cap, d_bad));
         PE_LAUNCH("pool_insert_kernel", st, pool_insert_kernel<<<grid, kAggThreads, 0, st>>>(n_entries, e_key, e_atom, d_atom_out, t, d_bad));

@@ -11,6 +11,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pdb_eda_b200 import _device, _lib, ccp4, cloudBatch, multi, synthetic  # noqa: E402
 
+if os.environ.get("PE_LIB"):  # A/B runs of two builds of the library (tuning only)
+    _lib.LIB_PATH = os.path.abspath(os.environ["PE_LIB"])
+
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 maxAtoms = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 21

@@ -445,3 +445,30 @@ def test_voxel_pass_matches_the_individual_calls():
     again = vp.stepFromHost(h_dens, h_diff, h_xyz)
     assert np.array_equal(again["cloud"], want_cloud) and np.array_equal(again["region"], want_region)
     assert np.array_equal(again["green"]["label"], res["green"]["label"]) and np.array_equal(again["red"]["stats"], res["red"]["stats"])
+
+
+@pytest.mark.parametrize("name", ["ortho", "perm"])
+def test_xyz2crs_ties_and_near_ties(name):
+    """xyz2crs rounds (x - origin) / gridLength half to even (pdb_eda/ccp4.py:297-299).  The device forms the quotient with a
+    reciprocal and keeps the exact division for quotients within 1e-9 of a half-integer (round_quotient, pe_common.cuh): exact
+    ties, their neighbours one and a few ulp away, and ordinary points must all land on the reference's index."""
+    dm, cuda, orc = _impls(name)
+    h = dm.header
+    origin = np.asarray(h.origin, dtype=np.float64)
+    gl = np.asarray(h.gridLength, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    k = rng.integers(-40, 200, size=(400, 3)).astype(np.float64)
+    pts = [origin + (k + 0.5) * gl]                                  # ties up to the rounding of the products
+    for steps in (1, 2, 3, 17):
+        pts.append(np.nextafter(pts[0], np.inf) if steps == 1 else pts[0] + steps * np.spacing(pts[0]))
+        pts.append(np.nextafter(pts[0], -np.inf) if steps == 1 else pts[0] - steps * np.spacing(pts[0]))
+    pts.append(origin + (k + rng.uniform(0.4999999, 0.5000001, size=k.shape)) * gl)
+    pts.append(origin + rng.uniform(-40, 200, size=k.shape) * gl)
+    xyz = np.concatenate(pts)
+    got = cuda.xyz2crs(xyz)
+    want = orc.xyz2crs(xyz)
+    assert np.array_equal(got, want)
+    # and against the arithmetic itself: Python's round() of the correctly rounded quotient
+    q = (xyz - origin) / gl
+    ref = np.rint(q).astype(np.int64)[:, [int(a) for a in h.map2crs]]
+    assert np.array_equal(got, ref)
