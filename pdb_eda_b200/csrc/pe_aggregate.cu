@@ -39,6 +39,12 @@ constexpr uint64_t kAggEmpty = ~0ull;
 constexpr uint32_t kAggNil = 0xffffffffu;
 constexpr int kKeyBits = 14;                 // per crs axis, offset 2^13: |index| < 8192
 constexpr int kKeyOff = 1 << (kKeyBits - 1);
+constexpr int kSmallBox = 8;                 // widest box edge of the 8-lanes-per-atom count path
+struct SmallTabB {
+    double sq[3][kSmallBox];  // per crs axis: fl((coord - atom)^2) of the box's indices
+    int off[3][kSmallBox];    // wrapped element offsets, or kInvalidOff
+};
+static_assert(kSmallBox * kSmallBox * kSmallBox <= 1024, "magic division by dim[1]");
 constexpr int kBoxBitWords = 8;              // candidate boxes of up to 256 voxels hand their bitmap from the count pass to the fill pass
 constexpr int kPairClouds = 8;               // clouds per atom the pair kernel's byte masks can name
 constexpr int kPairWarps = 4;
@@ -96,19 +102,14 @@ __device__ __forceinline__ void load_geom(pe_geom *dst, const pe_batch_map *m, i
 }
 
 // ------------------------------------------------------------------------------------------------ pass 1: counts
-__global__ void __launch_bounds__(kSphereWarps * 32)
-    cloud_count_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
-                       const double *__restrict__ xyz, const float *__restrict__ radius, uint32_t *__restrict__ count,
-                       unsigned long long *__restrict__ d_maxbox, uint32_t *__restrict__ box_bits) {
-    __shared__ AxisTab tabs[kSphereWarps][2];
-    __shared__ pe_geom geoms[kSphereWarps];
-    __shared__ uint32_t wbits[kSphereWarps][kBoxBitWords];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * kSphereWarps + warp;
-    if (a >= n_atoms) return;
+// One atom by one warp (boxes wider than 8 voxels, skewed cells): the candidate box in the reference's product order.
+__device__ __forceinline__ void count_one_atom(const pe_batch_map *__restrict__ maps, int a, const int32_t *__restrict__ atom_map,
+                                               const double *__restrict__ xyz, const float *__restrict__ radius, uint32_t *__restrict__ count,
+                                               unsigned long long *__restrict__ d_maxbox, uint32_t *__restrict__ box_bits, AxisTab *tab,
+                                               pe_geom *gs, uint32_t *wb, int lane) {
     const pe_batch_map *m = maps + atom_map[a];
-    load_geom(&geoms[warp], m, lane);
-    const pe_geom &g = geoms[warp];
+    load_geom(gs, m, lane);
+    const pe_geom &g = *gs;
     const float *rho = m->d_rho;
     const float cutoff = m->cutoff;
     const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
@@ -121,26 +122,165 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
     const int D1 = b.dim[1], D2 = b.dim[2];
     const bool keep = box_bits != nullptr && b.dim[0] * D1 * D2 <= 32 * kBoxBitWords;
     if (keep) {
-        if (lane < kBoxBitWords) wbits[warp][lane] = 0u;
+        if (lane < kBoxBitWords) wb[lane] = 0u;
         __syncwarp();
     }
-    for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
+    for_each_inside(g, rho, b, ax, ay, az, T, tab, lane, [&](int ic, int ir, int is, bool, float v) {
         if (passes(v, cutoff)) {
             ++n;
             if (keep) {
                 const int p = (ic * D1 + ir) * D2 + is;
-                atomicOr(&wbits[warp][p >> 5], 1u << (p & 31));
+                atomicOr(&wb[p >> 5], 1u << (p & 31));
             }
         }
     });
     n = warp_sum(n);
     if (keep) {
         __syncwarp();
-        if (lane < kBoxBitWords) box_bits[(int64_t)a * kBoxBitWords + lane] = wbits[warp][lane];
+        if (lane < kBoxBitWords) box_bits[(int64_t)a * kBoxBitWords + lane] = wb[lane];
     }
     if (lane == 0) {
         count[a] = (uint32_t)n;
-        atomicMax(d_maxbox, (unsigned long long)b.dim[0] * (unsigned long long)b.dim[1] * (unsigned long long)b.dim[2]);
+        const unsigned long long vol = (unsigned long long)b.dim[0] * (unsigned long long)b.dim[1] * (unsigned long long)b.dim[2];
+        if (vol > *(volatile unsigned long long *)d_maxbox) atomicMax(d_maxbox, vol);
+    }
+    __syncwarp();  // the scratch is reused by the warp's next atom
+}
+
+// A warp takes kCountAtoms = 4 consecutive atoms.  At the atom-type radii (0.6 - 1.3 A on a 0.5 A grid) a candidate box is 4^3 or
+// 6^3 voxels for ~15 cloud voxels, so when all four boxes are at most 8 wide in an orthogonal cell each atom gets 8 lanes (the
+// layout of sphere_sums_kernel, pe_sphere.cu): a lane walks box rows (row, section), finds the row's in-sphere columns exactly
+// (row_chord) and gathers just those -- a third of the instructions of one warp per atom (ncu: 1,050 warp instructions per atom,
+// issue slots 59 % busy).  Every 8-lane group keeps its own copy of its structure's geometry: a warp's atoms may belong to two
+// structures.  Otherwise the warp handles its atoms one after the other with all 32 lanes (count_one_atom).
+constexpr int kCountAtoms = 4;
+template <int MODE>
+__device__ __forceinline__ int count_small_rows(const pe_geom &g, const float *__restrict__ rho, const SmallTabB &t, const int *lo, const int *dim,
+                                                double ax, double ay, double az, double T, float cutoff, bool keep, uint32_t *wb, int l8) {
+    const int ic = g.map2crs[0];  // xyz axis carried by the columns
+    const float inv_gl = (float)(1.0 / g.grid_length[ic]);
+    const float xc = (float)((sel3(ax, ay, az, ic) - g.origin[ic]) / g.grid_length[ic] - (double)lo[0]);
+    const int nC = dim[0], D1 = dim[1], D2 = dim[2];
+    const double *sqc = t.sq[0];
+    int km = min(max(nC / 2, 0), nC - 1);  // the column nearest the atom: the box's centre column or one of its neighbours
+    if (km > 0 && sqc[km - 1] < sqc[km]) --km;
+    else if (km + 1 < nC && sqc[km + 1] < sqc[km]) ++km;
+    const int rows = D1 * D2;
+    const unsigned div_d1 = (1024u + (unsigned)D1 - 1u) / (unsigned)D1;  // exact for row < 64, D1 <= 8
+    int n = 0;
+    for (int row = l8; row < rows; row += 8) {
+        const int is = (int)(((unsigned)row * div_d1) >> 10), ir = row - is * D1;
+        const double sr = t.sq[1][ir], ss = t.sq[2][is];
+        const double A = (MODE == 0) ? ss : ((MODE == 1) ? sr : __dadd_rn(sr, ss));
+        const double B = (MODE == 0) ? sr : ss;
+        int kl, kh;
+        if (!row_chord<MODE>(sqc, nC, km, xc, inv_gl, A, B, T, kl, kh)) continue;
+        const int o1 = t.off[1][ir], o2 = t.off[2][is];
+        const int orr = o1 | o2;
+        const unsigned osum = (unsigned)o1 + (unsigned)o2;
+        float v[kSmallBox];
+#pragma unroll
+        for (int j = 0; j < kSmallBox; ++j) {  // all loads of the chord first
+            const int k = kl + j;
+            v[j] = 0.f;
+            if (k <= kh) {
+                const int oc = t.off[0][k];
+                if ((orr | oc) >= 0) v[j] = __ldg(rho + (int)(osum + (unsigned)oc));  // a voxel outside the stored map counts as 0
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kSmallBox; ++j) {
+            if (kl + j > kh) break;
+            if (passes(v[j], cutoff)) {
+                ++n;
+                if (keep) {
+                    const int p = ((kl + j) * D1 + ir) * D2 + is;
+                    atomicOr(&wb[p >> 5], 1u << (p & 31));
+                }
+            }
+        }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(kSphereWarps * 32)
+    cloud_count_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
+                       const double *__restrict__ xyz, const float *__restrict__ radius, uint32_t *__restrict__ count,
+                       unsigned long long *__restrict__ d_maxbox, uint32_t *__restrict__ box_bits) {
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    __shared__ pe_geom geoms[kSphereWarps][kCountAtoms];
+    __shared__ SmallTabB stab[kSphereWarps][kCountAtoms];
+    __shared__ uint32_t wbits[kSphereWarps][kCountAtoms][kBoxBitWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a0 = (blockIdx.x * kSphereWarps + warp) * kCountAtoms;
+    if (a0 >= n_atoms) return;
+    const int sub = lane >> 3, l8 = lane & 7;
+    const int a = a0 + sub;
+    const bool live = a < n_atoms;
+    const pe_batch_map *m = maps + (live ? atom_map[a] : 0);
+    if (live) {  // the group's copy of its structure's geometry
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&m->geom);
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(&geoms[warp][sub]);
+        for (int k = l8; k < (int)(sizeof(pe_geom) / 8); k += 8) d[k] = src[k];
+    }
+    __syncwarp();
+    const pe_geom &g = geoms[warp][sub];
+    int lo[3] = {0, 0, 0}, dim[3] = {0, 0, 0};
+    double ax = 0.0, ay = 0.0, az = 0.0, T = -1.0;
+    bool small = true;
+    if (live) {
+        ax = xyz[3 * a];
+        ay = xyz[3 * a + 1];
+        az = xyz[3 * a + 2];
+        AtomBox bb;
+        atom_box(g, ax, ay, az, radius[a], bb, T);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = bb.lo[k];
+            dim[k] = bb.dim[k];
+        }
+        small = g.orthogonal && dim[0] <= kSmallBox && dim[1] <= kSmallBox && dim[2] <= kSmallBox;
+    }
+    if (!__all_sync(kFull, small)) {
+        for (int q = 0; q < kCountAtoms && a0 + q < n_atoms; ++q)
+            count_one_atom(maps, a0 + q, atom_map, xyz, radius, count, d_maxbox, box_bits, tabs[warp], &geoms[warp][0], wbits[warp][0], lane);
+        return;
+    }
+    const int vol = dim[0] * dim[1] * dim[2];
+    const bool keep = box_bits != nullptr && vol <= 32 * kBoxBitWords;
+    uint32_t *wb = wbits[warp][sub];
+    int n = 0;
+    wb[l8] = 0u;  // kBoxBitWords == 8: one word per lane of the group
+    if (live && vol > 0) {
+        SmallTabB &t = stab[warp][sub];
+#pragma unroll
+        for (int axis = 0; axis < 3; ++axis) {
+            if (l8 < dim[axis]) {
+                t.sq[axis][l8] = axis_sq(g, axis, lo[axis] + l8, ax, ay, az);
+                t.off[axis][l8] = axis_off(g, axis, lo[axis] + l8);
+            }
+        }
+        __syncwarp(0xffu << (8 * sub));  // the 8 lanes of this atom (they take this branch together)
+        const float cutoff = m->cutoff;
+        const float *rho = m->d_rho;
+        const int mode = g.map2xyz[2] == 1 ? 0 : (g.map2xyz[2] == 2 ? 1 : 2);  // crs axis that carries z
+        if (mode == 0)
+            n = count_small_rows<0>(g, rho, t, lo, dim, ax, ay, az, T, cutoff, keep, wb, l8);
+        else if (mode == 1)
+            n = count_small_rows<1>(g, rho, t, lo, dim, ax, ay, az, T, cutoff, keep, wb, l8);
+        else
+            n = count_small_rows<2>(g, rho, t, lo, dim, ax, ay, az, T, cutoff, keep, wb, l8);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+    if (live) {
+        if (keep) box_bits[(int64_t)a * kBoxBitWords + l8] = wb[l8];
+        if (l8 == 0) {
+            count[a] = (uint32_t)n;
+            const unsigned long long v = (unsigned long long)(vol > 0 ? vol : 0);
+            if (v > *(volatile unsigned long long *)d_maxbox) atomicMax(d_maxbox, v);
+        }
     }
 }
 
@@ -653,10 +793,9 @@ __global__ void __launch_bounds__(kAggThreads)
     anext[a] = next;
 }
 
-#ifndef PE_PAIR_MINB
-#define PE_PAIR_MINB 1
-#endif
-__global__ void __launch_bounds__(kPairWarps * 32, PE_PAIR_MINB)
+// (56 registers, 9 CTAs per SM.  __launch_bounds__(128, 12) / (128, 16) -- 40 / 32 registers with spills -- ran at 21.2 / 22.4 ms
+// against 14.8 ms, and so did (128, 1), which lets ptxas take more registers: profiles/r02_c3_pool.md.)
+__global__ void __launch_bounds__(kPairWarps * 32)
     cloud_pair_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
                       const uint32_t *__restrict__ offset, const unsigned long long *__restrict__ e_key, const uint16_t *__restrict__ e_lab,
                       const int4 *__restrict__ info, const unsigned long long *__restrict__ abox, const AggSlot *__restrict__ aslot,
@@ -1049,7 +1188,7 @@ int pe_cloud_count(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_atoms, 
     PE_CHECK_ARG(n_maps < (1 << 20), "pe_cloud_count: at most 2^20 structures per batch");
     // counts are written into d_offset and scanned in place (n_atoms + 1 entries, the last one zero)
     PE_CUDA(cudaMemsetAsync(d_offset + n_atoms, 0, sizeof(uint32_t), st));
-    const int blocks = (n_atoms + kSphereWarps - 1) / kSphereWarps;
+    const int blocks = (n_atoms + kSphereWarps * kCountAtoms - 1) / (kSphereWarps * kCountAtoms);
     PE_LAUNCH("cloud_count_kernel", st, cloud_count_kernel<<<blocks, kSphereWarps * 32, 0, st>>>(
         d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, (unsigned long long *)(d_totals + 1), d_box_bits));
     PE_LAUNCH_CHECK();
