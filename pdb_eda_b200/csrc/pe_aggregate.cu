@@ -290,23 +290,58 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
 // DensityBlob.fromCrsList (pdb_eda/ccp4.py:522-545).  Per-atom record (8 doubles): number of clouds, voxels of the best
 // cloud, smallest centroid distance, total density of the best cloud, its centroid xyz, [7] is written by later kernels.
 // Dynamic shared memory per warp: bits[nw] | pref[nw] | pidx[maxbox] lab[maxbox] rnk[maxbox] (u16).
-__global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_atoms, const int32_t *__restrict__ atom_map,
-                                  const double *__restrict__ xyz, const float *__restrict__ radius,
-                                  const uint32_t *__restrict__ offset, int max_box, unsigned long long *__restrict__ e_key,
-                                  float *__restrict__ e_val, uint32_t *__restrict__ e_atom, uint16_t *__restrict__ e_lab,
-                                  uint32_t *__restrict__ n_clouds, double *__restrict__ atom_out, int *__restrict__ d_bad,
-                                  unsigned long long *__restrict__ abox, int dil_cap, const uint32_t *__restrict__ box_bits, int *__restrict__ cell_edge) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ AxisTab tabs[kSphereWarps][2];
-    __shared__ pe_geom geoms[kSphereWarps];
-    const int warps = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * warps + warp;
-    if (a >= n_atoms) return;
+struct FillArgs {
+    const pe_batch_map *maps;
+    int n_atoms;
+    const int32_t *atom_map;
+    const double *xyz;
+    const float *radius;
+    const uint32_t *offset;
+    int max_box;
+    unsigned long long *e_key;
+    float *e_val;
+    uint32_t *e_atom;
+    uint16_t *e_lab;
+    uint32_t *n_clouds;
+    double *atom_out;
+    int *d_bad;
+    unsigned long long *abox;
+    const uint32_t *box_bits;
+    int *cell_edge;
+    int dil_cap;
+};
+
+// the per-atom results every later kernel reads: the atom's record and the bounding box of its cloud voxels
+__device__ __forceinline__ void fill_box_record(const FillArgs &A, int a, int map_id, int n, int lo_c, int lo_r, int lo_s, int hi_c, int hi_r,
+                                                int hi_s) {
+    const int d0 = hi_c - lo_c + 1, d1 = hi_r - lo_r + 1, d2 = hi_s - lo_s + 1;
+    const int dmax = max(d0, max(d1, d2));
+    if (dmax > *(volatile int *)(A.cell_edge + map_id)) atomicMax(A.cell_edge + map_id, dmax);  // hot addresses: only the rare increases go to the atomic unit
+    // a batch with a cloud the pair kernel's shared-memory frame cannot hold takes the hash-table path
+    if (dmax > 15 || n > 1024 || (d0 + 2) * (d1 + 2) * (d2 + 2) > A.dil_cap) A.d_bad[1] = 1;
+    A.abox[a] = ((unsigned long long)(unsigned)(lo_c + kKeyOff) << 40) | ((unsigned long long)(unsigned)(lo_r + kKeyOff) << 26) |
+                ((unsigned long long)(unsigned)(lo_s + kKeyOff) << 12) | ((unsigned long long)(d0 & 15) << 8) |
+                ((unsigned long long)(d1 & 15) << 4) | (unsigned long long)(d2 & 15);
+}
+
+// One atom by one warp (boxes of more than 256 candidates, or no bitmap from the count pass).
+__device__ __forceinline__ void fill_one_atom(const FillArgs &A, int a, unsigned char *base, AxisTab *tab, pe_geom *gs, int lane) {
+    const pe_batch_map *__restrict__ maps = A.maps;
+    const int32_t *__restrict__ atom_map = A.atom_map;
+    const double *__restrict__ xyz = A.xyz;
+    const float *__restrict__ radius = A.radius;
+    const uint32_t *__restrict__ offset = A.offset;
+    const int max_box = A.max_box;
+    unsigned long long *__restrict__ e_key = A.e_key;
+    float *__restrict__ e_val = A.e_val;
+    uint32_t *__restrict__ e_atom = A.e_atom;
+    uint16_t *__restrict__ e_lab = A.e_lab;
+    uint32_t *__restrict__ n_clouds = A.n_clouds;
+    double *__restrict__ atom_out = A.atom_out;
+    int *__restrict__ d_bad = A.d_bad;
+    const uint32_t *__restrict__ box_bits = A.box_bits;
     const int nw_max = (max_box + 31) / 32;
     const int box_pad = (max_box + 1) / 2 * 2;
-    const size_t per_warp = (size_t)nw_max * 8 + (size_t)box_pad * 6;
-    unsigned char *base = dyn_smem + per_warp * warp;
     uint32_t *bits = reinterpret_cast<uint32_t *>(base);
     uint32_t *pref = bits + nw_max;
     uint16_t *pidx = reinterpret_cast<uint16_t *>(pref + nw_max);
@@ -315,8 +350,8 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
 
     const int map_id = atom_map[a];
     const pe_batch_map *m = maps + map_id;
-    load_geom(&geoms[warp], m, lane);
-    const pe_geom &g = geoms[warp];
+    load_geom(gs, m, lane);
+    const pe_geom &g = *gs;
     const float *rho = m->d_rho;
     const float cutoff = m->cutoff;
     const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
@@ -342,7 +377,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         if (lane < nw) bits[lane] = box_bits[(int64_t)a * kBoxBitWords + lane];
         __syncwarp();
     } else {
-        for_each_inside(g, rho, b, ax, ay, az, T, tabs[warp], lane, [&](int ic, int ir, int is, bool, float v) {
+        for_each_inside(g, rho, b, ax, ay, az, T, tab, lane, [&](int ic, int ir, int is, bool, float v) {
             if (passes(v, cutoff)) {
                 const int p = (ic * D1 + ir) * D2 + is;
                 atomicOr(bits + (p >> 5), 1u << (p & 31));
@@ -521,15 +556,7 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
         hi_c = __reduce_max_sync(kFull, hi_c);
         hi_r = __reduce_max_sync(kFull, hi_r);
         hi_s = __reduce_max_sync(kFull, hi_s);
-        if (lane == 0) {
-            const int d0 = hi_c - lo_c + 1, d1 = hi_r - lo_r + 1, d2 = hi_s - lo_s + 1;
-            const int dmax = max(d0, max(d1, d2));
-            if (dmax > *(volatile int *)(cell_edge + map_id)) atomicMax(cell_edge + map_id, dmax);  // hot addresses: only the rare increases go to the atomic unit
-            if (dmax > 15 || n > 1024 || (d0 + 2) * (d1 + 2) * (d2 + 2) > dil_cap) d_bad[1] = 1;
-            abox[a] = ((unsigned long long)(unsigned)(lo_c + kKeyOff) << 40) | ((unsigned long long)(unsigned)(lo_r + kKeyOff) << 26) |
-                      ((unsigned long long)(unsigned)(lo_s + kKeyOff) << 12) | ((unsigned long long)(d0 & 15) << 8) |
-                      ((unsigned long long)(d1 & 15) << 4) | (unsigned long long)(d2 & 15);
-        }
+        if (lane == 0) fill_box_record(A, a, map_id, n, lo_c, lo_r, lo_s, hi_c, hi_r, hi_s);
     }
     // 7. per-cloud sums (fromCrsList) -> centroid distance; the nearest cloud (first minimum, :630-634)
     double best_dist = 0.0, best_sum = 0.0, bcx = 0.0, bcy = 0.0, bcz = 0.0;
@@ -572,6 +599,229 @@ __global__ void cloud_fill_kernel(const pe_batch_map *__restrict__ maps, int n_a
     if (lane == 0) {
         if (nroots > kPairClouds) d_bad[1] = 1;
         n_clouds[a] = (uint32_t)nroots;
+        rec[0] = (double)nroots;
+        rec[1] = (double)best_n;
+        rec[2] = best_dist;
+        rec[3] = best_sum;
+        rec[4] = bcx;
+        rec[5] = bcy;
+        rec[6] = bcz;
+        rec[7] = 0.0;
+    }
+}
+
+// A warp takes kFillAtoms = 4 consecutive atoms.  When the count pass left a bitmap for all four (candidate boxes of at most 256
+// voxels: 8 words) each atom gets 8 lanes, one bitmap word per lane: prefix counts, the bit-parallel flood fill (multi-word
+// shifts across the 8 lanes), the entries and the per-cloud sums all run inside the 8-lane group, four atoms side by side --
+// the one-warp-per-atom form spent ~1,900 warp instructions per atom with a third of the lanes busy (ncu: issue slots 60 % busy).
+// Otherwise the warp handles its atoms one after the other with all 32 lanes (fill_one_atom).
+constexpr int kFillAtoms = 4;
+struct FillGroupShared {
+    pe_geom geom;
+    float val[32 * kBoxBitWords];   // density of the listed voxels
+    uint8_t lab[32 * kBoxBitWords];  // their cluster numbers
+};
+
+__global__ void __launch_bounds__(kSphereWarps * 32) cloud_fill_kernel(const FillArgs A, int warps, size_t per_warp) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ AxisTab tabs[kSphereWarps][2];
+    __shared__ FillGroupShared fgs[kSphereWarps][kFillAtoms];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a0 = (blockIdx.x * warps + warp) * kFillAtoms;
+    if (a0 >= A.n_atoms) return;
+    const int sub = lane >> 3, l8 = lane & 7;
+    const unsigned gmask = 0xffu << (8 * sub);
+    const int a = a0 + sub;
+    const bool live = a < A.n_atoms;
+    const int map_id = live ? A.atom_map[a] : 0;
+    const pe_batch_map *m = A.maps + map_id;
+    FillGroupShared &fg = fgs[warp][sub];
+    if (live) {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&m->geom);
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(&fg.geom);
+        for (int k = l8; k < (int)(sizeof(pe_geom) / 8); k += 8) d[k] = src[k];
+    }
+    __syncwarp();
+    const pe_geom &g = fg.geom;
+    AtomBox b;
+    double T;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    int vol = 0;
+    if (live) {
+        ax = A.xyz[3 * a];
+        ay = A.xyz[3 * a + 1];
+        az = A.xyz[3 * a + 2];
+        atom_box(g, ax, ay, az, A.radius[a], b, T);
+        vol = b.dim[0] * b.dim[1] * b.dim[2];
+    }
+    const bool small = !live || (A.box_bits != nullptr && vol <= 32 * kBoxBitWords);
+    if (!__all_sync(kFull, small)) {
+        for (int q = 0; q < kFillAtoms && a0 + q < A.n_atoms; ++q) {
+            fill_one_atom(A, a0 + q, dyn_smem + per_warp * warp, tabs[warp], &fgs[warp][0].geom, lane);
+            __syncwarp();  // the scratch is reused by the warp's next atom
+        }
+        return;
+    }
+    if (!live) return;  // from here on only the 8 lanes of a group synchronise
+    const float *rho = m->d_rho;
+    const int D1 = b.dim[1], D2 = b.dim[2];
+    const int nw = (vol + 31) / 32;
+    double *rec = A.atom_out + (int64_t)a * 8;
+    // 1 + 2. the bitmap of the count pass, one word per lane; prefix counts
+    const uint32_t mine = l8 < nw ? A.box_bits[(int64_t)a * kBoxBitWords + l8] : 0u;
+    int mybase, n;
+    {
+        const int cnt = __popc(mine);
+        int x = cnt;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int y = __shfl_up_sync(gmask, x, o, 8);
+            if (l8 >= o) x += y;
+        }
+        mybase = x - cnt;
+        n = __shfl_sync(gmask, x, 7, 8);
+    }
+    const uint32_t obase = A.offset[a];
+    if ((uint32_t)n != A.offset[a + 1] - obase) {  // the two passes must agree
+        if (l8 == 0) *A.d_bad = 1;
+        return;
+    }
+    // 4 + 5. 26-connected clusters by bit-parallel flood fill, numbered by their first member (createCrsLists order)
+    // p / D by multiplication: exact for p < 256, D <= 256
+    const uint32_t m2 = (65536u + (uint32_t)max(D2, 1) - 1u) / (uint32_t)max(D2, 1), m1 = (65536u + (uint32_t)max(D1, 1) - 1u) / (uint32_t)max(D1, 1);
+    uint32_t nfs = 0u, nls = 0u, nfr = 0u, nlr = 0u;  // own voxels that may move -1 / +1 along sections, -1 / +1 along rows
+    for (uint32_t c = mine; c; c &= c - 1u) {
+        const int j = __ffs((int)c) - 1;
+        const uint32_t p = 32u * (uint32_t)l8 + (uint32_t)j;
+        const uint32_t q = (p * m2) >> 16;
+        const int is = (int)(p - q * (uint32_t)D2), ir = (int)(q - ((q * m1) >> 16) * (uint32_t)D1);
+        nfs |= (is != 0 ? 1u : 0u) << j;
+        nls |= (is != D2 - 1 ? 1u : 0u) << j;
+        nfr |= (ir != 0 ? 1u : 0u) << j;
+        nlr |= (ir != D1 - 1 ? 1u : 0u) << j;
+    }
+    auto shl = [&](uint32_t v, int k) {  // the group's bit string moved k positions up
+        const int q = k >> 5, r = k & 31;
+        uint32_t x = __shfl_up_sync(gmask, v, q, 8), y = __shfl_up_sync(gmask, v, q + 1, 8);
+        if (l8 < q) x = 0u;
+        if (l8 < q + 1) y = 0u;
+        return r ? ((x << r) | (y >> (32 - r))) : x;
+    };
+    auto shr = [&](uint32_t v, int k) {
+        const int q = k >> 5, r = k & 31;
+        uint32_t x = __shfl_down_sync(gmask, v, q, 8), y = __shfl_down_sync(gmask, v, q + 1, 8);
+        if (l8 + q > 7) x = 0u;
+        if (l8 + q + 1 > 7) y = 0u;
+        return r ? ((x >> r) | (y << (32 - r))) : x;
+    };
+    int nroots = 0;
+    {
+        uint32_t todo = mine;
+        const int plane = D1 * D2;
+        for (;;) {
+            const unsigned has = (__ballot_sync(gmask, todo != 0u) >> (8 * sub)) & 0xffu;
+            if (!has) break;
+            uint32_t comp = (l8 == __ffs((int)has) - 1) ? (todo & (0u - todo)) : 0u;  // the lowest unlabelled voxel
+            for (;;) {
+                const uint32_t x = comp | shl(comp & nls, 1) | shr(comp & nfs, 1);
+                const uint32_t y = x | shl(x & nlr, D2) | shr(x & nfr, D2);
+                const uint32_t z = (y | (plane < 32 * kBoxBitWords ? (shl(y, plane) | shr(y, plane)) : 0u)) & todo;
+                const bool grew = z != comp;
+                comp = z;
+                if (!__any_sync(gmask, grew)) break;
+            }
+            for (uint32_t c = comp; c;) {
+                const int bit = __ffs((int)c) - 1;
+                c &= c - 1u;
+                fg.lab[mybase + __popc(mine & ((1u << bit) - 1u))] = (uint8_t)nroots;
+            }
+            todo &= ~comp;
+            ++nroots;
+        }
+    }
+    __syncwarp(gmask);
+    // 6. entries: packed key (structure, un-wrapped crs), density, owning atom, cloud number inside the atom
+    bool bad = false;
+    int lo_c = INT_MAX, lo_r = INT_MAX, lo_s = INT_MAX, hi_c = INT_MIN, hi_r = INT_MIN, hi_s = INT_MIN;
+    {
+        int jj = mybase;
+        for (uint32_t cb = mine; cb; cb &= cb - 1u, ++jj) {
+            const uint32_t p = 32u * (uint32_t)l8 + (uint32_t)(__ffs((int)cb) - 1);
+            const uint32_t q = (p * m2) >> 16, ic = (q * m1) >> 16;
+            const int c = b.lo[0] + (int)ic, r = b.lo[1] + (int)(q - ic * (uint32_t)D1), s = b.lo[2] + (int)(p - q * (uint32_t)D2);
+            lo_c = min(lo_c, c);
+            hi_c = max(hi_c, c);
+            lo_r = min(lo_r, r);
+            hi_r = max(hi_r, r);
+            lo_s = min(lo_s, s);
+            hi_s = max(hi_s, s);
+            const unsigned uc = (unsigned)(c + kKeyOff), ur = (unsigned)(r + kKeyOff), us = (unsigned)(s + kKeyOff);
+            // neighbours (+-1) must stay inside the field: 1 <= u < 2^14 - 1
+            if (uc - 1u >= (1u << kKeyBits) - 2u || ur - 1u >= (1u << kKeyBits) - 2u || us - 1u >= (1u << kKeyBits) - 2u) bad = true;
+            const int oc = axis_off(g, 0, c), orr = axis_off(g, 1, r), os = axis_off(g, 2, s);
+            const float v = ((oc | orr | os) >= 0) ? __ldg(rho + (oc + orr + os)) : 0.f;
+            fg.val[jj] = v;
+            A.e_key[obase + jj] = ((unsigned long long)(unsigned)map_id << (3 * kKeyBits)) | ((unsigned long long)uc << (2 * kKeyBits)) |
+                                  ((unsigned long long)ur << kKeyBits) | (unsigned long long)us;
+            A.e_val[obase + jj] = v;
+            A.e_atom[obase + jj] = (uint32_t)a;
+            A.e_lab[obase + jj] = (uint16_t)fg.lab[jj];
+        }
+    }
+    if (__any_sync(gmask, bad) && l8 == 0) *A.d_bad = 1;
+    if (n > 0) {
+        lo_c = __reduce_min_sync(gmask, lo_c);
+        lo_r = __reduce_min_sync(gmask, lo_r);
+        lo_s = __reduce_min_sync(gmask, lo_s);
+        hi_c = __reduce_max_sync(gmask, hi_c);
+        hi_r = __reduce_max_sync(gmask, hi_r);
+        hi_s = __reduce_max_sync(gmask, hi_s);
+        if (l8 == 0) fill_box_record(A, a, map_id, n, lo_c, lo_r, lo_s, hi_c, hi_r, hi_s);
+    }
+    // 7. per-cloud sums (fromCrsList) -> centroid distance; the nearest cloud (first minimum, :630-634)
+    double best_dist = 0.0, best_sum = 0.0, bcx = 0.0, bcy = 0.0, bcz = 0.0;
+    int best_n = 0;
+    for (int k = 0; k < nroots; ++k) {
+        double sd = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+        int cn = 0;
+        int jj = mybase;
+        for (uint32_t cb = mine; cb; cb &= cb - 1u, ++jj) {
+            if ((int)fg.lab[jj] != k) continue;
+            const uint32_t p = 32u * (uint32_t)l8 + (uint32_t)(__ffs((int)cb) - 1);
+            const uint32_t q = (p * m2) >> 16, ic = (q * m1) >> 16;
+            const int c = b.lo[0] + (int)ic, r = b.lo[1] + (int)(q - ic * (uint32_t)D1), s = b.lo[2] + (int)(p - q * (uint32_t)D2);
+            const double d = (double)fg.val[jj];
+            double x, y, z;
+            crs2xyz(g, c, r, s, x, y, z);
+            sd += d;
+            sx += __dmul_rn(d, x);
+            sy += __dmul_rn(d, y);
+            sz += __dmul_rn(d, z);
+            ++cn;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            sd += __shfl_xor_sync(gmask, sd, o);
+            sx += __shfl_xor_sync(gmask, sx, o);
+            sy += __shfl_xor_sync(gmask, sy, o);
+            sz += __shfl_xor_sync(gmask, sz, o);
+            cn += __shfl_xor_sync(gmask, cn, o);
+        }
+        const double cx = sx / sd, cy = sy / sd, cz = sz / sd;
+        const double dx = ax - cx, dy = ay - cy, dz = az - cz;
+        const double dist = sqrt(dx * dx + dy * dy + dz * dz);  // np.linalg.norm(atom.coord - cloud.centroid)
+        if (k == 0 || dist < best_dist) {  // Python's min(): a later value replaces only when strictly smaller
+            best_dist = dist;
+            best_sum = sd;
+            best_n = cn;
+            bcx = cx;
+            bcy = cy;
+            bcz = cz;
+        }
+    }
+    if (l8 == 0) {
+        if (nroots > kPairClouds) A.d_bad[1] = 1;
+        A.n_clouds[a] = (uint32_t)nroots;
         rec[0] = (double)nroots;
         rec[1] = (double)best_n;
         rec[2] = best_dist;
@@ -1263,9 +1513,29 @@ int pe_cloud_aggregate(int32_t n_maps, const pe_batch_map *d_maps, int32_t n_ato
     PE_CHECK_ARG(warps >= 1, "pe_cloud_aggregate: a box of %d voxels needs %zu bytes of shared memory", max_box_voxels, per_warp);
     const size_t smem = per_warp * warps;
     PE_CUDA(cudaFuncSetAttribute(cloud_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PE_LAUNCH("cloud_fill_kernel", st, cloud_fill_kernel<<<(n_atoms + warps - 1) / warps, warps * 32, smem, st>>>(
-        d_maps, n_atoms, d_atom_map, d_xyz, d_radius, d_offset, max_box_voxels, e_key, e_val, e_atom, e_lab, cloud_count, d_atom_out, d_bad,
-        abox, dil_cap, d_box_bits, cell_edge));
+    {
+        FillArgs fa;
+        fa.maps = d_maps;
+        fa.n_atoms = n_atoms;
+        fa.atom_map = d_atom_map;
+        fa.xyz = d_xyz;
+        fa.radius = d_radius;
+        fa.offset = d_offset;
+        fa.max_box = max_box_voxels;
+        fa.e_key = e_key;
+        fa.e_val = e_val;
+        fa.e_atom = e_atom;
+        fa.e_lab = e_lab;
+        fa.n_clouds = cloud_count;
+        fa.atom_out = d_atom_out;
+        fa.d_bad = d_bad;
+        fa.abox = abox;
+        fa.box_bits = d_box_bits;
+        fa.cell_edge = cell_edge;
+        fa.dil_cap = dil_cap;
+        const int per_block = warps * kFillAtoms;
+        PE_LAUNCH("cloud_fill_kernel", st, cloud_fill_kernel<<<(n_atoms + per_block - 1) / per_block, warps * 32, smem, st>>>(fa, warps, per_warp));
+    }
     PE_LAUNCH("cutoff_kernel", st, cutoff_kernel<<<n_maps, kSummaryThreads, 0, st>>>(d_maps, d_atom_out, d_map_out));
     // pass 2: contributing atoms, cloud ids
     PE_LAUNCH("accept_kernel", st, accept_kernel<<<(n_atoms + 1 + kAggThreads - 1) / kAggThreads, kAggThreads, 0, st>>>(
