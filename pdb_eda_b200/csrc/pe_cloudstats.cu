@@ -53,7 +53,7 @@ __device__ double beta_inc(double a, double b, double x) {
     return 1.0 - bt * beta_cf(b, a, 1.0 - x) / b;
 }
 
-constexpr int kStatThreads = 256;
+constexpr int kStatThreads = 1024;
 constexpr int kStatCols = 14;  // kept rows, ten statistics, contributing atoms, completely overlapped atoms, spare
 // scratch columns (structure-of-arrays over the permuted atom order, n_atoms doubles each)
 enum { C_DER = 0, C_NV, C_CD, C_BF, C_ADJ, C_DOM, C_COR, C_KEEP, C_FLAGS, kScratchCols };
