@@ -228,3 +228,50 @@ def test_statistics_kernel_matches_the_numpy_statement():
         assert segOut[s_, 0] == (keep & (atomMap[rows] == k) & (typeIndex[rows] == t)).sum()
         for j, column in enumerate(cloudBatch.MEDIAN_COLUMNS):
             gc.close(segOut[s_, 1 + j], med[column][k, t], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radiusScale", [1.0, 1.8, 3.0])
+def test_pair_path_equals_the_hash_table_path(ref, radiusScale, monkeypatch):
+    """pe_cloud_aggregate merges clouds through the atom grid + pair kernel and keeps the voxel hash table as the fallback for
+    batches the pair kernel's frame cannot hold (a DEVICE flag decides; PE_CLOUD_FORCE_HASH=1 forces the fallback).  Both must give
+    the same per-atom records and per-structure totals, bit for bit -- at the atom-type radii (candidate boxes of <= 256 voxels: 8
+    lanes per atom in the count and fill passes), at 1.8 x the radii (boxes beyond 256 voxels: one warp per atom, no bitmap
+    hand-off) and at 3 x (clouds wider than 15 voxels / atoms with more than 8 clouds: the device flag sends the batch to the
+    hash-table kernels by itself), for orthogonal, axis-permuted and hexagonal cells in ONE batch."""
+    import copy
+    import test_analysis_vs_reference as tar
+    from pdb_eda_b200 import cloudBatch, densityAnalysis
+    ref_da = ref[1]
+    params = copy.deepcopy(ref_da.paramsGlobal)
+    params["radii"] = {k: float(np.float32(v * radiusScale)) for k, v in params["radii"].items()}
+    densityAnalysis.setGlobals(params)
+    try:
+        items = []
+        for name in tar.CASES:
+            st, d1, d2, pdb_text = tar._build(name)
+            m = densityAnalysis.fromFile(io.StringIO(pdb_text), io.BytesIO(d1), io.BytesIO(d2))
+            items.append((m.densityObj, cloudBatch.AtomTable.fromStructure(m.biopdbObj, params)))
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("PE_CLOUD_FORCE_HASH", mode)
+            batch = cloudBatch.CloudBatch(items, params)
+            batch.launch()
+            arr = batch.collectArrays()
+            out[mode] = (batch.atomRows().copy(), arr, batch.ws[:16].cpu().numpy().view(np.int32).copy())
+        rows0, arr0, flags0 = out["0"]
+        rows1, arr1, flags1 = out["1"]
+        assert flags0[0] == 0 and flags1[0] == 0 and flags1[1] == 1      # no error; the forced run took the hash-table kernels
+        # the workspace's second flag says which kernels merged the clouds: the pair kernel at the first two scales, the hash
+        # table at the third (the count pass's largest box and the atoms' cloud numbers decide on the device)
+        assert flags0[1] == (1 if radiusScale >= 3.0 else 0), (radiusScale, flags0[:4], int(rows0[:, 0].max()))
+        assert rows0.shape == rows1.shape and rows0.shape[0] > 0
+        assert np.array_equal(rows0, rows1, equal_nan=True)
+        for key in ("ok", "ratio", "numVoxels", "totalDensity", "totalElectrons", "analysed", "domainClouds", "residueClouds",
+                    "centroidCutoff", "present", "complete", "incomplete"):
+            assert np.array_equal(np.asarray(arr0[key]), np.asarray(arr1[key]), equal_nan=True), key
+        for column in arr0["medians"]:
+            assert np.array_equal(arr0["medians"][column], arr1["medians"][column], equal_nan=True), column
+        assert arr0["numVoxels"].sum() > 0
+    finally:
+        densityAnalysis.setGlobals(ref_da.paramsGlobal)
