@@ -1222,7 +1222,6 @@ __global__ void __launch_bounds__(kPairWarps * 32)
                 }
             }
         }
-        drain();
         __syncwarp();
         ncand = 0;
     };
@@ -1258,6 +1257,7 @@ __global__ void __launch_bounds__(kPairWarps * 32)
             if (ncand > kPairCand - 32) flush();
         }
         flush();
+        drain();  // once per atom (or when the pair list fills): every drain is a chain of dependent union-find loads
     }
     __syncwarp();
     if (lane == 0 && adj_j) atomicOr(adj + j, adj_j);

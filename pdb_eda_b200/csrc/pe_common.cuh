@@ -216,6 +216,14 @@ __device__ __forceinline__ uint32_t uf_find_halve(uint32_t *parent, uint32_t x) 
     return x;
 }
 __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b) {
+    {
+        // two nodes with the same parent are in one set already: one round trip instead of two finds (the common case once a
+        // component's nodes point at its root)
+        const uint32_t pa = __ldcg(parent + a), pb = __ldcg(parent + b);
+        if (pa == pb || pa == b || pb == a) return;
+        a = pa;
+        b = pb;
+    }
     for (;;) {
         a = uf_find_halve(parent, a);
         b = uf_find_halve(parent, b);
