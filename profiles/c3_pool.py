@@ -64,3 +64,20 @@ print("launch %.1f ms, pack %.1f ms per pass" % ((t1 - t0) / passes * 1e3, (t2 -
 c = out["cumulative"]
 print("structures ok %d, ratio %.6f, voxels %d" % (c["structures"], c["density_electron_ratio"], c["num_voxels_aggregated"]))
 print("medianDiffs", {k[:6]: round(v, 5) for k, v in out["medianDiffs"].items()})
+if os.environ.get("CHECK_HASH"):
+    # the pair path against the hash-table path over the whole pool: every per-structure number and per-atom flag
+    import ctypes
+    def arrays():
+        outs = []
+        for b in shard.batches:
+            b.launch()
+            arr = b.collectArrays()
+            outs.append((b.atomRows().copy(), {k: np.asarray(v).copy() for k, v in arr.items() if k not in ("medians", "unitVolume")}))
+        return outs
+    a0 = arrays()
+    os.environ["PE_CLOUD_FORCE_HASH"] = "1"
+    a1 = arrays()
+    os.environ["PE_CLOUD_FORCE_HASH"] = "0"
+    same = all(np.array_equal(x[0], y[0], equal_nan=True) and all(np.array_equal(x[1][k], y[1][k], equal_nan=True) for k in x[1])
+               for x, y in zip(a0, a1))
+    print("pair path == hash-table path over the pool (per-atom records and per-structure totals, bit for bit):", same)
