@@ -1139,13 +1139,25 @@ __global__ void __launch_bounds__(kPairWarps * 32)
     // edge list and uniting them in a kernel of their own, one thread per edge, was slower in total: 10.8 + 5.2 ms against 14.9 ms.)
     auto drain = [&]() {
         __syncwarp();
-        for (int t = lane; t < 2 * npair; t += 32) {
+        // The first pair goes ahead of the others: an atom's pairs mostly lead into ONE set (its residue, the chain so far), and
+        // once the first has hooked the atom's cloud under that set's root the others see "same parent" after one round trip
+        // instead of walking both trees and colliding on the same atomicMin.
+        if (lane < 2 && npair > 0) {
+            const uint2 pr = plist[0];
+            const uint32_t ci = pr.x & 0x7fffffffu;
+            if (lane == 0)
+                uf_union_cached(parent_dom, ci, pr.y);
+            else if (pr.x >> 31)
+                uf_union_cached(parent_res, ci, pr.y);
+        }
+        __syncwarp();
+        for (int t = lane + 2; t < 2 * npair; t += 32) {
             const uint2 pr = plist[t >> 1];
             const uint32_t ci = pr.x & 0x7fffffffu;
             if (!(t & 1))
-                uf_union(parent_dom, ci, pr.y);
+                uf_union_cached(parent_dom, ci, pr.y);
             else if (pr.x >> 31)
-                uf_union(parent_res, ci, pr.y);
+                uf_union_cached(parent_res, ci, pr.y);
         }
         __syncwarp();
         npair = 0;

@@ -239,6 +239,43 @@ __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t 
     }
 }
 
+// The same union with L1-CACHED parent loads.  A stale parent is still an ancestor (pointers only ever move to smaller ids of the
+// same set), so finds through stale lines are merely longer, "same ancestor" still proves "same set", and the hook itself is an
+// atomicMin whose return value is fresh: a stale "root" that has been hooked meanwhile is found out there and the loop carries on
+// from its real parent.  What the cache buys: thousands of warps unite into the same few giant sets, and with ld.cg every one of
+// their finds reads the root's line from its one L2 slice.  Only for kernels whose results are read by LATER launches.
+__device__ __forceinline__ uint32_t uf_find_halve_cached(uint32_t *parent, uint32_t x) {
+    uint32_t p = parent[x];
+    while (p != x) {
+        const uint32_t gp = parent[p];
+        if (gp != p) __stcg(parent + x, gp);
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union_cached(uint32_t *parent, uint32_t a, uint32_t b) {
+    {
+        const uint32_t pa = parent[a], pb = parent[b];
+        if (pa == pb || pa == b || pb == a) return;
+        a = pa;
+        b = pb;
+    }
+    for (;;) {
+        a = uf_find_halve_cached(parent, a);
+        b = uf_find_halve_cached(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        const uint32_t old = atomicMin(parent + a, b);  // hook the larger root under the smaller
+        if (old == a) return;
+        a = old;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ scans (pe_scan.cu)
 // Exclusive prefix sum of n uint32 values (n read from d_n when non-null, else n_host) in three launches.
 // d_total (may be null) receives the grand total as int64.  d_block_ws: >= scan_ws_bytes(capacity) bytes.
