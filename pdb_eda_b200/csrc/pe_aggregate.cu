@@ -1094,7 +1094,7 @@ __global__ void __launch_bounds__(kPairWarps * 32)
             atom_region(maps, map_id, rbase, size);
             uint32_t h = agg_start(key, size);
             for (;;) {
-                const uint4 sl = __ldcg(reinterpret_cast<const uint4 *>(aslot + rbase + h));
+                const uint4 sl = __ldg(reinterpret_cast<const uint4 *>(aslot + rbase + h));
                 const unsigned long long k = ((unsigned long long)sl.y << 32) | sl.x;
                 if (k == key) {
                     i = sl.z;
