@@ -142,7 +142,7 @@ __device__ __forceinline__ void count_one_atom(const pe_batch_map *__restrict__ 
     if (lane == 0) {
         count[a] = (uint32_t)n;
         const unsigned long long vol = (unsigned long long)b.dim[0] * (unsigned long long)b.dim[1] * (unsigned long long)b.dim[2];
-        if (vol > *(volatile unsigned long long *)d_maxbox) atomicMax(d_maxbox, vol);
+        if (vol > *d_maxbox) atomicMax(d_maxbox, vol);  // a cached (possibly stale, i.e. smaller) value only costs a redundant atomic
     }
     __syncwarp();  // the scratch is reused by the warp's next atom
 }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kSphereWarps * 32)
         if (l8 == 0) {
             count[a] = (uint32_t)n;
             const unsigned long long v = (unsigned long long)(vol > 0 ? vol : 0);
-            if (v > *(volatile unsigned long long *)d_maxbox) atomicMax(d_maxbox, v);
+            if (v > *d_maxbox) atomicMax(d_maxbox, v);  // L1-cached read of the one hot address: stale values only cost a redundant atomic
         }
     }
 }
@@ -316,7 +316,7 @@ __device__ __forceinline__ void fill_box_record(const FillArgs &A, int a, int ma
                                                 int hi_s) {
     const int d0 = hi_c - lo_c + 1, d1 = hi_r - lo_r + 1, d2 = hi_s - lo_s + 1;
     const int dmax = max(d0, max(d1, d2));
-    if (dmax > *(volatile int *)(A.cell_edge + map_id)) atomicMax(A.cell_edge + map_id, dmax);  // hot addresses: only the rare increases go to the atomic unit
+    if (dmax > A.cell_edge[map_id]) atomicMax(A.cell_edge + map_id, dmax);  // hot addresses, read through L1: only the rare increases go to the atomic unit
     // a batch with a cloud the pair kernel's shared-memory frame cannot hold takes the hash-table path
     if (dmax > 15 || n > 1024 || (d0 + 2) * (d1 + 2) * (d2 + 2) > A.dil_cap) A.d_bad[1] = 1;
     A.abox[a] = ((unsigned long long)(unsigned)(lo_c + kKeyOff) << 40) | ((unsigned long long)(unsigned)(lo_r + kKeyOff) << 26) |
