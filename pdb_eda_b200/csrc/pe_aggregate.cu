@@ -7,6 +7,7 @@
 //   pass 1  every candidate atom's clouds = findAberrantBlobs(atom.coord, radius[type], densityCutoff) (:605):
 //           sphere voxels with rho > cutoff, 26-connected clusters, per cloud sum rho / centroid / size; the atom's
 //           smallest centroid distance (:608)                                   -> cloud_count_kernel, cloud_fill_kernel
+//                                                                                  (8 lanes per atom for boxes of <= 256 voxels)
 //           centroidDistanceCutoff = nanmedian + 2.5 nanstd per structure (:609) -> cutoff_kernel (radix select)
 //   pass 2  an atom contributes unless it has several clouds and even the nearest centroid is beyond the cutoff
 //           (:623-634); all clouds of a contributing atom join its residue's pool (:638-639)   -> accept_kernel
@@ -14,10 +15,14 @@
 //           is "completely overlapped" when it touches every bonded atom of its residue that contributes (:646-659)
 //           domain level: residue clouds that touch are merged (:689-708); a merged cloud is a voxel SET, so the
 //           totals run over each distinct voxel once and over the distinct atoms of the merged cloud (:712-724)
-//                                                      -> one hash table of all pool voxels of the batch (key = structure +
-//                                                         un-wrapped crs), cloud_merge_kernel (two union-finds over cloud
-//                                                         ids + per-atom adjacency bits), cloud_roots_kernel,
-//                                                         cloud_first_kernel, map_summary_kernel
+//                                                      -> pair path: atoms binned into a per-structure cell grid
+//                                                         (atom_cell_insert_kernel), one warp per atom tests its neighbours'
+//                                                         cloud voxels against byte masks of its own clouds in shared memory
+//                                                         (cloud_pair_kernel: two union-finds over cloud ids + per-atom
+//                                                         adjacency bits + first flags), cloud_roots_kernel,
+//                                                         map_summary_kernel; fallback for batches the pair kernel's frame
+//                                                         cannot hold (device flag): one hash table of all pool voxels
+//                                                         (pool_insert / cloud_merge / cloud_first_kernel)
 // The host keeps the per-atom-type statistics (numpy / scipy, pdb_eda/densityAnalysis.py:734-766), vectorised over the
 // batch.  Order-dependent descriptions (which atom names a merged cloud, :717) are not produced here; the single
 // structure API (DensityAnalysis.aggregateCloud) replays those with Python sets.
