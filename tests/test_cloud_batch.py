@@ -275,3 +275,46 @@ def test_pair_path_equals_the_hash_table_path(ref, radiusScale, monkeypatch):
         assert arr0["numVoxels"].sum() > 0
     finally:
         densityAnalysis.setGlobals(ref_da.paramsGlobal)
+
+
+@pytest.mark.gpu
+def test_pair_path_equals_the_hash_table_path_on_a_pool(monkeypatch):
+    """The same comparison over a pool of 24 synthetic structures drawn like bench.py's config-3 pool (64^3-192^3 maps, five space
+    groups incl. the hexagonal cell, ~190,000 atoms, two batches): per-atom records and per-structure totals bit for bit."""
+    import torch
+    from pdb_eda_b200 import _device, ccp4, cloudBatch, multi
+    params = synthetic.defaultParams()
+    electronsOf = np.array([synthetic.ALA_ELECTRONS["ALA_" + a] for a, _, _ in synthetic._ALA_ATOMS])
+    entries = []
+    for sp in synthetic.poolSpec(24, sizes=(64, 96, 128, 192)):
+        n, cell = sp["n"], sp["cell"]
+        coords, bf = synthetic.fastPolyAla(sp["residues"], cell, sp["seed"])
+        table = synthetic.polyAlaTable(coords, bf, params)
+        rho = synthetic.densityMapDevice(coords, np.tile(electronsOf, sp["residues"]), n, cell, sp["seed"] + 1)
+        hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), cell, (n, n, n)))
+        dmap = _device.DeviceMap(_device.geom_from_header(hdr), rho.reshape(-1))
+        m, s = dmap.mean_std()
+        entries.append((sp["index"], cloudBatch.MapRef(dmap, m + 1.5 * s, hdr.unitVolume, "s%05d" % sp["index"]), table))
+    shard = multi.PoolShard(entries, params, 1 << 17)
+    assert len(shard.batches) >= 2
+
+    def arrays():
+        outs = []
+        for b in shard.batches:
+            b.launch()
+            arr = b.collectArrays()
+            outs.append((b.atomRows().copy(), {k: np.asarray(v).copy() for k, v in arr.items() if k not in ("medians", "unitVolume")},
+                         b.ws[:16].cpu().numpy().view(np.int32).copy()))
+        return outs
+
+    monkeypatch.setenv("PE_CLOUD_FORCE_HASH", "0")
+    pair = arrays()
+    monkeypatch.setenv("PE_CLOUD_FORCE_HASH", "1")
+    table = arrays()
+    assert sum(len(x[0]) for x in pair) > 100000
+    for x, y in zip(pair, table):
+        assert x[2][0] == 0 and x[2][1] == 0 and y[2][1] == 1          # the pair kernel ran in the first pass, the hash table in the second
+        assert np.array_equal(x[0], y[0], equal_nan=True)
+        for k in x[1]:
+            assert np.array_equal(x[1][k], y[1][k], equal_nan=True), k
+        assert x[1]["numVoxels"].sum() > 0 and x[1]["ok"].all()
