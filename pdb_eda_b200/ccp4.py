@@ -6,6 +6,7 @@ kernel through :mod:`pdb_eda_b200.cutils`.  Class, method and attribute names ar
 (pdb_eda/ccp4.py:58-594) so that code written against ``pdb_eda.ccp4`` keeps working.
 """
 import struct
+import threading
 import urllib.request
 
 import numpy as np
@@ -55,18 +56,14 @@ def parse(handle, pdbid, verbose=False):
     assert header.xlength != 0.0 or header.ylength != 0.0 or header.zlength != 0.0, \
         "Error: Cell dimensions are all 0, Map file will not align with other structures"
     header.symmetry = handle.read(header.symmetryBytes) if header.symmetryBytes > 0 else b""
-    # page-locking costs a few ms per call: worth it from a few tens of MB up, where the pageable copy would dominate
-    staging = _pinnedBuffer(header.mapSize) if (header.endian == "<" and header.mapSize >= PINNED_MIN_BYTES) else None
-    if staging is not None and hasattr(handle, "readinto"):
-        # the voxels go from the file straight into page-locked memory, from where one DMA takes them to HBM
-        view = staging.numpy()
-        got = handle.readinto(memoryview(view).cast("B"))
-        extra = handle.read(1)
+    if header.endian == "<" and header.mapSize >= PINNED_MIN_BYTES and hasattr(handle, "readinto") and _cudaPresent():
+        # the voxels go from the file through a small page-locked ring straight to HBM (reads overlap the DMAs); the host
+        # copy that ``densityArray`` / ``density`` expose is fetched back only if somebody asks for it
+        rho, got = _streamToDevice(handle, header.mapSize)
+        extra = handle.read(1) if got == header.mapSize else b""
         if got != header.mapSize or extra:
             raise AssertionError("Error: file holds %s map bytes, the header promises %d" % ("more than %d" % got if extra else got, header.mapSize))
-        matrix = DensityMatrix(header, header.origin, view.view(np.float32), pdbid)
-        matrix._pinned = staging
-        return matrix
+        return DensityMatrix._fromDevice(header, header.origin, rho.view(_torch().float32), pdbid)
     payload = handle.read()
     if len(payload) != header.mapSize:
         # the reference's size assertions all fail once the lengths disagree (pdb_eda/ccp4.py:95-100)
@@ -76,15 +73,48 @@ def parse(handle, pdbid, verbose=False):
     return DensityMatrix(header, header.origin, voxels, pdbid)
 
 
-def _pinnedBuffer(nbytes):
-    """A page-locked uint8 staging tensor when a CUDA device is present (else None)."""
+def _torch():
+    import torch
+    return torch
+
+
+def _cudaPresent():
     try:
-        import torch
-        if nbytes > 0 and torch.cuda.is_available():
-            return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        return _torch().cuda.is_available()
     except Exception:
-        pass
-    return None
+        return False
+
+
+RING_SLOT_BYTES = 8 << 20
+_ring = None
+_ringLock = threading.Lock()
+
+
+def _streamToDevice(handle, nbytes):
+    """Reads ``nbytes`` from ``handle`` into a new uint8 tensor in HBM through two page-locked slots that live as long as the
+    process (page-locking a whole 226 MB map costs ~150 ms on first use, the ring ~30 ms once; profiles/r02f_h2d_load.txt): slot k
+    is being filled from the file while slot k-1 is in flight.  Returns (tensor, bytes read)."""
+    global _ring
+    torch = _torch()
+    with _ringLock:
+        if _ring is None:
+            slots = [torch.empty(RING_SLOT_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            _ring = [[slot, memoryview(slot.numpy()).cast("B"), None] for slot in slots]
+        dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        off = k = 0
+        while off < nbytes:
+            entry = _ring[k & 1]
+            if entry[2] is not None:
+                entry[2].synchronize()               # the DMA that last read this slot
+            got = handle.readinto(entry[1][:min(RING_SLOT_BYTES, nbytes - off)])
+            if not got:
+                break
+            dev[off:off + got].copy_(entry[0][:got], non_blocking=True)
+            entry[2] = torch.cuda.Event()
+            entry[2].record()
+            off += got
+            k += 1
+    return dev, off
 
 
 class DensityHeader(object):
@@ -234,14 +264,41 @@ class DensityMatrix:
         flat = np.ascontiguousarray(flat).reshape(-1)
         if flat.size != n:
             raise ValueError("map payload holds %d values, header says %d" % (flat.size, n))
-        self._raw32 = flat
-        self._pinned = None
+        self._host32 = flat
         self._density64 = None
         self._hostDirty = False
         self._device = None
         self._totalAbsDensity = {}
 
+    @classmethod
+    def _fromDevice(cls, header, origin, rho, pdbid):
+        """A map whose voxels are already in HBM (``rho``: flat float32 CUDA tensor, file order) and have no host copy yet."""
+        from ._device import DeviceMap, geom_from_header
+        self = cls.__new__(cls)
+        self.pdbid = pdbid
+        self.header = header
+        self.origin = origin
+        if rho.numel() != header.ncrs[0] * header.ncrs[1] * header.ncrs[2]:
+            raise ValueError("map payload holds %d values, header says %d" % (rho.numel(), header.ncrs[0] * header.ncrs[1] * header.ncrs[2]))
+        self._host32 = None
+        self._density64 = None
+        self._hostDirty = False
+        self._device = DeviceMap(geom_from_header(header, origin), rho)
+        self._totalAbsDensity = {}
+        return self
+
     # ---- host views -----------------------------------------------------------------------------------------
+    @property
+    def _raw32(self):
+        """The flat float32 host copy; read back from HBM on first use when the map was streamed there by ``parse``."""
+        if self._host32 is None:
+            self._host32 = self._device.rho.cpu().numpy()
+        return self._host32
+
+    @_raw32.setter
+    def _raw32(self, value):
+        self._host32 = value
+
     @property
     def densityArray(self):
         """Flat voxel values in file order (the reference keeps a tuple, pdb_eda/ccp4.py:337)."""
@@ -270,7 +327,6 @@ class DensityMatrix:
         if self._hostDirty:
             self._raw32 = np.ascontiguousarray(np.asarray(self._density64), dtype=np.float32).reshape(-1)
             self._hostDirty = False
-            self._pinned = None
             self._device = None
             self._totalAbsDensity = {}
 
@@ -280,7 +336,7 @@ class DensityMatrix:
         self._syncHost()
         if self._device is None:
             from ._device import DeviceMap
-            self._device = DeviceMap.from_host(self.header, self._raw32, self.origin, pinned=self._pinned)
+            self._device = DeviceMap.from_host(self.header, self._raw32, self.origin)
         return self._device
 
     # ---- statistics -----------------------------------------------------------------------------------------

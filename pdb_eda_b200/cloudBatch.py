@@ -28,6 +28,7 @@ from . import _device
 from . import _lib
 from ._device import _ptr, _stream
 from ._lib import PeGeom, check
+from ._gc import pausedGC
 
 MEDIAN_COLUMNS = ("num_voxels", "density_electron_ratio", "centroid_distance", "adj_density_electron_ratio", "volume", "bfactor",
                   "slopes", "domain_fraction", "corrected_fraction", "corrected_density_electron_ratio")
@@ -62,51 +63,70 @@ class AtomTable:
         return len(self.nameIndex)
 
     @classmethod
+    @pausedGC
     def fromStructure(cls, biopdbObj, params):
         """Walks a (duck-typed) Biopython structure once."""
         types = params["full_atom_name_map_atom_type"]
         bondedAtoms = params["bonded_atoms"]
-        coords, nameIdx, occ, bf, res, local, labels = [], [], [], [], [], [], []
+        coords, nameIdx, occ, bf, res, local, labels, bondedList = [], [], [], [], [], [], [], []
         names, nameOf = [], {}
-        residueNames = []                             # per residue: {RES_ATOM: local index}
+        masksOf = {}                                  # RES_ATOM sequence of a residue -> bonded-atom mask of each of its atoms
         supported, reason = True, ""
         ridx = -1
         for residue in biopdbObj.get_residues():
-            if residue.id[0] != ' ':
+            rid = residue.id
+            if rid[0] != ' ':
                 continue
             ridx += 1
-            present = {}
+            resname = residue.resname
+            prefix = resname.strip() + "_"
+            chainId, number = residue.parent.id, rid[1]
+            present = {}                              # RES_ATOM -> local index
+            sequence = []
             for atom in residue.child_list:
-                resAtom = atom.parent.resname.strip() + "_" + atom.name
-                if resAtom not in types or atom.get_occupancy() == 0:
+                owner = atom.parent
+                if owner is residue:
+                    resAtom, ownerName = prefix + atom.name, resname
+                else:
+                    ownerName = owner.resname
+                    resAtom = ownerName.strip() + "_" + atom.name
+                if resAtom not in types:
                     continue
-                if resAtom in present:
-                    supported, reason = False, "residue with a repeated atom name (%s)" % resAtom
+                occupancy = atom.get_occupancy()
+                if occupancy == 0:
+                    continue
                 k = len(present)
-                present.setdefault(resAtom, k)
-                if resAtom not in nameOf:
-                    nameOf[resAtom] = len(names)
+                if present.setdefault(resAtom, k) != k:
+                    supported, reason = False, "residue with a repeated atom name (%s)" % resAtom
+                index = nameOf.get(resAtom)
+                if index is None:
+                    index = nameOf[resAtom] = len(names)
                     names.append(resAtom)
+                sequence.append(resAtom)
                 coords.append(atom.coord)
-                nameIdx.append(nameOf[resAtom])
-                occ.append(atom.get_occupancy())
+                nameIdx.append(index)
+                occ.append(occupancy)
                 bf.append(atom.get_bfactor())
                 res.append(ridx)
                 local.append(k)
-                labels.append((residue.parent.id, residue.id[1], atom.parent.resname, atom.name))
-            residueNames.append(present)
+                labels.append((chainId, number, ownerName, atom.name))
             if len(present) > 64:
                 supported, reason = False, "residue with more than 64 candidate atoms"
+            key = tuple(sequence)
+            masks = masksOf.get(key)
+            if masks is None:
+                masks = []
+                for resAtom in sequence:
+                    mask = 0
+                    for other in bondedAtoms.get(resAtom, ()):
+                        j = present.get(other)
+                        if j is not None and j < 64:
+                            mask |= 1 << j
+                    masks.append(mask)
+                masksOf[key] = masks
+            bondedList.extend(masks)
         n = len(coords)
-        bonded = np.zeros(n, dtype=np.uint64)
-        for k in range(n):
-            present = residueNames[res[k]]
-            mask = 0
-            for other in bondedAtoms.get(names[nameIdx[k]], ()):
-                j = present.get(other)
-                if j is not None and j < 64:
-                    mask |= 1 << j
-            bonded[k] = mask
+        bonded = np.array(bondedList, dtype=np.uint64) if n else np.zeros(0, dtype=np.uint64)
         coords32 = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
         if n and _distinctRows(coords32) < n:
             supported, reason = False, "atoms with identical coordinates share one cloud entry"

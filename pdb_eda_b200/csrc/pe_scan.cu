@@ -4,6 +4,7 @@
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: a no-op unless a profiler injects its library
 #include "pe_common.cuh"
 
 namespace pe {
@@ -36,6 +37,7 @@ static std::vector<ProfTotal> g_prof_totals;
 
 ProfScope::ProfScope(const char *tag, cudaStream_t st) : slot(-1), stream(st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    nvtxRangePushA(tag);  // one NVTX range per launch, named like the kernel (tracing)
     if (!g_profiling.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     ProfEvent ev;
@@ -52,6 +54,7 @@ ProfScope::ProfScope(const char *tag, cudaStream_t st) : slot(-1), stream(st) {
 }
 
 ProfScope::~ProfScope() {
+    nvtxRangePop();
     if (slot < 0) return;
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     if (slot < (int)g_prof_events.size()) cudaEventRecord(g_prof_events[slot].stop, stream);

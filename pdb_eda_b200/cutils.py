@@ -19,6 +19,7 @@ import torch
 from . import _device
 from . import _lib
 from ._device import _ptr, _stream, _as_dev
+from ._gc import pausedGC
 from ._lib import check
 
 dcutoff = np.sqrt(3)  # adjacency radius of createCrsLists (pdb_eda/cutils.pyx:43)
@@ -85,6 +86,7 @@ def sumOfAbs(array, cutoff):
     return out.item()
 
 
+@pausedGC
 def createCrsLists(crsList):
     """Disjoint 26-connected voxel lists, in the reference's creation order (pdb_eda/cutils.pyx:44-70)."""
     crsList = list(crsList)
@@ -110,14 +112,18 @@ class SymAtom:
         return getattr(self.atom, attr)
 
 
+@pausedGC
 def createSymmetryAtoms(atomList, rotationMats, orthoMat, xs, ys, zs):
     """All symmetry images inside the map's circumscribed box +- 5 A (pdb_eda/cutils.pyx:73-103)."""
     atomIndex, image, coords = symmetryImages([atom.coord for atom in atomList], rotationMats, orthoMat, xs, ys, zs)
     nops = len(rotationMats)
+    symmetryOf = {}                                   # image code -> (i, j, k, operator); 27 x nops distinct codes at most
     out = []
     for a, code, xyz in zip(atomIndex.tolist(), image.tolist(), coords):
-        img, op = divmod(code, nops)
-        symmetry = (img // 9 - 1, (img // 3) % 3 - 1, img % 3 - 1, op)
+        symmetry = symmetryOf.get(code)
+        if symmetry is None:
+            img, op = divmod(code, nops)
+            symmetry = symmetryOf[code] = (img // 9 - 1, (img // 3) % 3 - 1, img % 3 - 1, op)
         atom = atomList[a]
         out.append(SymAtom(atom, atom.coord if symmetry == (0, 0, 0, 0) else xyz, symmetry))
     return out
@@ -240,6 +246,7 @@ def _make_blobs(densityMatrix, crs, label, stats):
                         densityMatrix) for b in range(len(stats))]
 
 
+@pausedGC
 def fullBlobs(densityMatrix, positiveCutoff, negativeCutoff):
     """[green, red] = createFullBlobList(+c), createFullBlobList(-c) from one pass over the map
     (pdb_eda/ccp4.py:463-485, pdb_eda/densityAnalysis.py:392-412); None for a zero cutoff."""
@@ -287,6 +294,7 @@ def pairMetrics(foMatrix, diffMatrix, crs, label=None, take=None, nGroups=1):
     return out
 
 
+@pausedGC
 def blobsFromCrsList(densityMatrix, crsList):
     """createBlobList (pdb_eda/ccp4.py:475-485): cluster + per-blob sums on the device."""
     crs = np.asarray(list(crsList), dtype=np.int32).reshape(-1, 3)

@@ -7,20 +7,27 @@ SURVEY.md App. B.3): ``get_residues()``, ``get_atoms()``, ``header['resolution']
 (this image has no Biopython) they fall back on this small PDB-format reader, which yields the same surface.
 Any object with that surface works with :class:`pdb_eda_b200.densityAnalysis.DensityAnalysis`.
 """
+import itertools
+
 import numpy as np
+
+from ._gc import pausedGC
+
+_ATOM_RECORDS = ("ATOM  ", "HETATM")
+_FLOAT32 = np.dtype(np.float32)                       # native float32 arrays carry this very object as their dtype
 
 
 class Atom:
-    def __init__(self, name, coord, bfactor, occupancy, altloc=" ", fullname=None, serial_number=0, element=""):
+    def __init__(self, name, coord, bfactor, occupancy, altloc=" ", fullname=None, serial_number=0, element="", parent=None):
         self.name = name
         self.fullname = fullname if fullname is not None else name
-        self.coord = coord if (type(coord) is np.ndarray and coord.dtype == np.float32) else np.asarray(coord, dtype=np.float32)
+        self.coord = coord if (type(coord) is np.ndarray and coord.dtype is _FLOAT32) else np.asarray(coord, dtype=np.float32)
         self.bfactor = float(bfactor)
         self.occupancy = float(occupancy)
         self.altloc = altloc
         self.serial_number = serial_number
         self.element = element
-        self.parent = None
+        self.parent = parent
 
     def get_occupancy(self):
         return self.occupancy
@@ -122,15 +129,13 @@ def _parsePDBColumns(lines, structureId):
     """Fast path of ``parsePDB`` for the common case -- one model, no alternate locations: the fixed-width columns of all
     ATOM / HETATM records are converted with numpy in one go (coordinates, occupancies, b-factors, residue numbers, names);
     the Python loop that remains only creates the objects.  Returns None when the file needs the general reader."""
-    atomLines = []
+    atomLines = [line for line in lines if line.startswith(_ATOM_RECORDS)]
     resolution = None
-    for line in lines:
+    for line in (lines if len(atomLines) == len(lines) else [line for line in lines if not line.startswith(_ATOM_RECORDS)]):
         rec = line[0:6]
-        if rec == "ATOM  " or rec == "HETATM":
-            atomLines.append(line)
-        elif rec == "MODEL " or rec == "ENDMDL":
+        if rec == "MODEL " or rec == "ENDMDL":
             return None
-        elif rec == "REMARK" and line.startswith("REMARK   2 RESOLUTION."):
+        if rec == "REMARK" and line.startswith("REMARK   2 RESOLUTION."):
             try:
                 resolution = float(line[23:30])
             except ValueError:
@@ -142,7 +147,7 @@ def _parsePDBColumns(lines, structureId):
         return structure
     try:
         width = len(atomLines[0])
-        if width >= 79 and all(len(line) == width for line in atomLines):       # the usual case: every record is 80 columns wide
+        if width >= 79 and set(map(len, atomLines)) == {width}:                 # the usual case: every record is 80 columns wide
             raw = np.frombuffer("".join(atomLines).encode("ascii"), dtype="S1").reshape(n, width)
             if width < 80:
                 raw = np.concatenate((raw, np.full((n, 80 - width), b" ", dtype="S1")), axis=1)
@@ -171,7 +176,13 @@ def _parsePDBColumns(lines, structureId):
     except ValueError:
         return None
     fullnames = text(12, 16).tolist()
-    names = text(12, 16, str.strip).tolist()
+    nameValues, nameInverse = np.unique(col(12, 16), return_inverse=True)
+    strippedTable = [v.decode("ascii").strip() for v in nameValues.tolist()]
+    idOfName = {}
+    nameIds = np.array([idOfName.setdefault(name, len(idOfName)) for name in strippedTable], dtype=np.int64)[np.asarray(nameInverse).reshape(-1)]
+    nameTable = np.empty(len(strippedTable), dtype=object)
+    nameTable[:] = strippedTable
+    names = nameTable[np.asarray(nameInverse).reshape(-1)].tolist()
     resnames = text(17, 20, str.strip)
     chainIds = text(21, 22)
     icodes = text(26, 27)
@@ -191,24 +202,30 @@ def _parsePDBColumns(lines, structureId):
         if key in keys:
             return None
         keys.add(key)
+    # a repeated atom name inside a residue: general reader
+    if len(np.unique((np.cumsum(change) - 1) * len(idOfName) + nameIds)) < n:
+        return None
     model = structure.add(Model(0))
     chains = {}
     resnameList, chainList, hetList, icodeList, resseqList = resnames.tolist(), chainIds.tolist(), hetflags.tolist(), icodes.tolist(), resseq.tolist()
     bounds = starts.tolist() + [n]
-    for a, b in zip(bounds[:-1], bounds[1:]):
+    residues = []
+    for a in bounds[:-1]:
         chain = chains.get(chainList[a])
         if chain is None:
             chain = chains[chainList[a]] = model.add(Chain(chainList[a]))
-        residue = chain.add(Residue((hetList[a], resseqList[a], icodeList[a]), resnameList[a]))
-        seen = set()
-        for k in range(a, b):
-            if names[k] in seen:
-                return None                           # a repeated atom name inside a residue: general reader
-            seen.add(names[k])
-            residue.add(Atom(names[k], coords[k], bfac[k], occ[k], " ", fullnames[k], serial[k], elements[k]))
+        residues.append(chain.add(Residue((hetList[a], resseqList[a], icodeList[a]), resnameList[a])))
+    # the atoms in one C-level sweep (map over the prepared columns), their residue handed to the constructor
+    owners = np.empty(len(residues), dtype=object)
+    owners[:] = residues
+    owners = np.repeat(owners, np.diff(bounds)).tolist()
+    atoms = list(map(Atom, names, list(coords), bfac, occ, itertools.repeat(" "), fullnames, serial, elements, owners))
+    for residue, a, b in zip(residues, bounds[:-1], bounds[1:]):
+        residue.child_list = atoms[a:b]
     return structure
 
 
+@pausedGC
 def parsePDB(handle, structureId="xxxx"):
     """Reads ATOM / HETATM / MODEL records of a PDB-format text handle (or file name) into a Structure.
 

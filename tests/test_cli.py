@@ -82,10 +82,17 @@ def test_optimize_service_and_pinned_loader(tmp_path):
     ids = ["1aaa", "2bbb"]
     for k, pdbid in enumerate(ids):
         _write_entry(folder, pdbid, 20 + 3 * k)
+    threshold = ccp4.PINNED_MIN_BYTES
     ccp4.PINNED_MIN_BYTES = 1024
-    dm = ccp4.read(os.path.join(folder, "1aaa.ccp4"))
-    assert dm._pinned is not None and dm._pinned.is_pinned()                 # file -> page-locked memory -> one DMA
+    try:
+        dm = ccp4.read(os.path.join(folder, "1aaa.ccp4"))
+        assert dm._host32 is None and ccp4._ring[0][0].is_pinned()           # file -> page-locked ring -> HBM, no host copy
+        with pytest.raises(AssertionError):
+            ccp4.parse(io.BytesIO(open(os.path.join(folder, "1aaa.ccp4"), "rb").read()[:-8]), "x")
+    finally:
+        ccp4.PINNED_MIN_BYTES = threshold
     ref = ccp4.parse(io.BytesIO(open(os.path.join(folder, "1aaa.ccp4"), "rb").read()), "x")
+    assert ref._host32 is not None                                           # small maps: host array, uploaded on first use
     assert np.array_equal(dm.densityArray, ref.densityArray) and dm.meanDensity == ref.meanDensity
     with pytest.raises(AssertionError):
         ccp4.parse(io.BytesIO(open(os.path.join(folder, "1aaa.ccp4"), "rb").read()[:-8]), "x")
