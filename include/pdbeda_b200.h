@@ -195,7 +195,10 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
  *                     pe_blob_label's d_stats, cap_merged rows per sign) with the whole map's geometry; the caller
  *                     all-reduces the table.
  * d_ws: >= pe_slab_workspace_bytes(world, cap_blobs, u0, u1), shared by the three calls; pe_slab_status reads its overflow
- * flag (synchronises). */
+ * flag (synchronises).
+ * Size limits: one SLAB holds fewer than 2^31 stored voxels (32-bit element offsets and keys inside a call); the WHOLE map may
+ * be larger -- its keys are 64-bit and g_whole is used for index -> coordinate arithmetic only -- so maps beyond the 1290^3 that
+ * one pe_blob_label call takes (1536^3, 2048^3 ...) are labelled slab by slab, on several GPUs or one after another on one. */
 int64_t pe_slab_exchange_bytes(int64_t cap_blobs, int64_t cap_plane);
 int64_t pe_slab_workspace_bytes(int32_t world, int64_t cap_blobs, int32_t u0, int32_t u1);
 int pe_slab_boundary(const pe_geom *g_slab, int32_t u2_whole, int32_t s0, int32_t last_is_cut, const int64_t *d_counts,

@@ -58,6 +58,7 @@ struct ProfScope {
 
 int sm_count();  // cached SM count of the current device (148 on B200)
 int check_geom(const pe_geom *g);  // host-side validation shared by the entry points (pe_map.cu)
+int check_geom_shape(const pe_geom *g, int64_t *nvox_out);  // the same without the 2^31-voxel limit of one call
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

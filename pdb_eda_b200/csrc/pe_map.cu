@@ -137,7 +137,10 @@ __global__ void crs2xyz_kernel(pe_geom g, int64_t n, const int32_t *__restrict__
     xyz[3 * i + 2] = z;
 }
 
-int check_geom(const pe_geom *g) {
+// check_geom_shape: the header fields alone -- for entry points that use a geometry only for index <-> coordinate arithmetic
+// (pe_slab_relabel takes the WHOLE map's geometry while its voxels live in slabs on several GPUs); check_geom adds the limit of
+// the entry points that address the stored voxels with 32-bit element offsets.
+int check_geom_shape(const pe_geom *g, int64_t *nvox_out) {
     PE_CHECK_ARG(g != nullptr, "geometry pointer is null");
     int64_t nvox = 1;
     for (int a = 0; a < 3; ++a) {
@@ -151,7 +154,15 @@ int check_geom(const pe_geom *g) {
     }
     PE_CHECK_ARG(g->map2crs[g->map2xyz[0]] == 0 && g->map2crs[g->map2xyz[1]] == 1 && g->map2crs[g->map2xyz[2]] == 2,
                  "map2xyz / map2crs are not inverse permutations");
-    PE_CHECK_ARG(nvox < (1ll << 31), "maps with 2^31 or more stored voxels are not supported (%lld)", (long long)nvox);
+    if (nvox_out) *nvox_out = nvox;
+    return PE_OK;
+}
+
+int check_geom(const pe_geom *g) {
+    int64_t nvox = 0;
+    if (int rc = check_geom_shape(g, &nvox)) return rc;
+    PE_CHECK_ARG(nvox < (1ll << 31),
+                 "maps with 2^31 or more stored voxels are not supported in one call (%lld): label them in slabs (pe_slab_*)", (long long)nvox);
     return PE_OK;
 }
 

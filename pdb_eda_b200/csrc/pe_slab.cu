@@ -413,7 +413,7 @@ int pe_slab_status(const void *d_ws, void *stream, int32_t *bad) {
 int pe_slab_relabel(const pe_geom *g_whole, int32_t u2_slab, int32_t s0, const int64_t *d_counts, int64_t cap_voxels, const uint32_t *d_key,
                     const float *d_value, int32_t *d_label, int64_t cap_blobs, const int32_t *d_new_number, const int64_t *d_n_merged,
                     int64_t cap_merged, double *d_stats, void *d_ws, void *stream) {
-    if (int rc = check_geom(g_whole)) return rc;
+    if (int rc = check_geom_shape(g_whole, nullptr)) return rc;  // only crs -> xyz of the whole map: no 2^31-voxel limit here
     PE_CHECK_ARG(d_counts && d_key && d_value && d_label && d_new_number && d_n_merged && d_stats && d_ws, "pe_slab_relabel: null pointer");
     PE_CHECK_ARG(cap_voxels > 0 && cap_blobs > 0 && cap_merged > 0 && u2_slab > 0, "pe_slab_relabel: capacities must be positive");
     cudaStream_t st = (cudaStream_t)stream;

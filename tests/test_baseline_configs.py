@@ -191,3 +191,34 @@ def test_c4_1024_cubed_labelling_and_slabs():
     crs = part["crs"].cpu().numpy().astype(np.int64)
     assert np.array_equal((crs[:, 0] * n + crs[:, 1]) * n + crs[:, 2], key)
     assert np.array_equal(np.bincount(remap[flat], minlength=nlab), part["stats"][:, 0].cpu().numpy().astype(np.int64))
+
+
+@pytest.mark.gpu
+def test_beyond_2_31_voxels_in_slabs():
+    """A 1536^3 map (3.6e9 voxels, above the 2^31 of one pe_blob_label call) labelled slab by slab through pe_slab_boundary /
+    merge / relabel: 4 slabs and 2 slabs give the same voxels, blob numbers and sums; the numbering is the canonical one (a
+    blob's number = how many blobs start before its first voxel in createFullCrsList order); the foreground equals a plain
+    threshold of the volume.  VERDICT r1 item 7: maps beyond one call's reach across slabs."""
+    import torch
+    from pdb_eda_b200 import _device, ccp4, slab
+    from pdb_eda_b200._lib import PdbEdaLibError
+    n = 1536
+    vol = synthetic.smoothNoiseMapDevice(n, seed=4)
+    hdr = ccp4.DensityHeader.fromFileHeader(synthetic.ccp4Header((n, n, n), (n * 0.5,) * 3 + (90, 90, 90), (n, n, n)))
+    with pytest.raises(PdbEdaLibError, match="slabs"):
+        _device.DeviceMap(_device.geom_from_header(hdr), vol.reshape(-1)).blob_label(3.0, -3.0)
+    four = slab.labelSlabsEmulated(hdr, vol, 4, 3.0, -3.0)
+    two = slab.labelSlabsEmulated(hdr, vol, 2, 3.0, -3.0)
+    expected = (int((vol >= 3.0).sum().item()), int((vol <= -3.0).sum().item()))
+    for k, (a, b) in enumerate(zip(four, two)):
+        assert a["n_blobs"] == b["n_blobs"] > 1000000 and a["n_pairs"] > b["n_pairs"] > 0
+        assert a["crs"].shape[0] == expected[k]
+        assert torch.equal(a["crs"], b["crs"]) and torch.equal(a["label"], b["label"]) and torch.equal(a["value"], b["value"])
+        gc.close(a["stats"].cpu().numpy(), b["stats"].cpu().numpy(), rtol=1e-9, atol=1e-9)
+        # canonical numbering: first occurrences of the labels, in list order, are 0, 1, 2, ...
+        label = a["label"]
+        firstSeen = torch.full((a["n_blobs"],), label.numel(), dtype=torch.long, device=label.device)
+        firstSeen.scatter_reduce_(0, label, torch.arange(label.numel(), device=label.device), reduce="amin")
+        assert bool((firstSeen[1:] > firstSeen[:-1]).all()) and int(firstSeen[0]) == 0
+        counts = torch.bincount(label, minlength=a["n_blobs"])
+        assert torch.equal(counts.double(), a["stats"][:, 0])
