@@ -62,3 +62,51 @@ def test_fast_reader_steps_aside():
     assert structure._parsePDBColumns(["MODEL        1\n"] + lines, "x") is None
     short = [l[:60].rstrip() + "\n" if l.startswith("ATOM") else l for l in lines]
     _same(structure.parsePDB(io.StringIO("".join(short))), _general("".join(short)))
+
+
+def test_repeated_atom_name_goes_to_the_general_reader():
+    """A residue that lists an atom name twice (no altloc flag) is the general reader's business: it keeps ONE atom per name."""
+    st = synthetic.polyAlaStructure(6, (0, 0, 0), (30.0,) * 3, seed=6)
+    lines = structure.formatPDB(st, cell=(30.0, 30.0, 30.0, 90, 90, 90)).splitlines(True)
+    first = next(i for i, l in enumerate(lines) if l.startswith("ATOM"))
+    twice = lines[:first + 1] + [lines[first]] + lines[first + 1:]
+    assert structure._parsePDBColumns(twice, "x") is None
+    assert structure._parsePDBColumns(lines, "x") is not None
+    # the same NAME in two different residues is the usual case and stays on the fast path
+    _same(structure.parsePDB(io.StringIO("".join(lines))), _general("".join(lines)))
+    # names that differ only in their padding ("CA  " / " CA ") are one name to Biopython
+    padded = lines[:first + 1] + [lines[first][:12] + (lines[first][13:16] + " " if lines[first][12] == " " else " " + lines[first][12:15])
+                                  + lines[first][16:]] + lines[first + 1:]
+    if padded[first + 1][12:16].strip() == lines[first][12:16].strip() and padded[first + 1][12:16] != lines[first][12:16]:
+        assert structure._parsePDBColumns(padded, "x") is None
+
+
+def test_paused_gc_restores_the_collector():
+    import gc
+    from pdb_eda_b200._gc import pausedGC
+
+    @pausedGC
+    def inner():
+        assert not gc.isenabled()
+        return 7
+
+    @pausedGC
+    def outer(fail):
+        assert not gc.isenabled()
+        assert inner() == 7 and not gc.isenabled()     # nested: the inner call leaves the outer pause alone
+        if fail:
+            raise ValueError("x")
+        return 1
+
+    assert gc.isenabled()
+    assert outer(False) == 1 and gc.isenabled()
+    try:
+        outer(True)
+    except ValueError:
+        pass
+    assert gc.isenabled()                               # switched back on when the call raises
+    gc.disable()
+    try:
+        assert outer(False) == 1 and not gc.isenabled()  # a caller that runs without the collector keeps it off
+    finally:
+        gc.enable()
