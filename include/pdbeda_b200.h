@@ -163,7 +163,8 @@ int pe_sphere_fill(const pe_geom *g, const float *d_rho, int32_t n_atoms, const 
  *
  * Outputs, per class k (all device pointers; capacity `cap_voxels` foreground voxels and `cap_blobs` blobs per class):
  *   d_counts[k*2+0] = number of foreground voxels, d_counts[k*2+1] = number of blobs   (int64, 4 entries)
- *   d_counts[4]     = overflow flag (non-zero: a capacity was exceeded; results are invalid)
+ *   d_counts[4]     = failure flag (1: a capacity was exceeded -- call again with larger ones; 2: the labelling kernel's blocks
+ *                     were not spread evenly over the SMs, part of the map was not scanned; either way results are invalid)
  *   d_key  [k*cap_voxels + p] = canonical index (c*U1 + r)*U2 + s of the p-th foreground voxel, ascending:
  *                               exactly createFullCrsList's list
  *   d_value[k*cap_voxels + p] = its density

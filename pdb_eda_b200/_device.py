@@ -273,6 +273,8 @@ class DeviceMap:
             c = counts.tolist()
             if c[4] == 0:
                 break
+            if c[4] == 2:
+                raise PdbEdaLibError("pe_blob_label: the sparse kernel's blocks were not spread evenly over the SMs; no result")
             need_v = max(c[0], c[2])
             need_b = max(c[1], c[3], 1)
             if need_v > cap_voxels:

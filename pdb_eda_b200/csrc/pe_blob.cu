@@ -35,6 +35,7 @@ constexpr int kSegShift = 9;       // words per counting segment of the bit plan
 constexpr int kSegWords = 1 << kSegShift;
 constexpr int kChunkShift = 9;     // voxels per root-ranking chunk: 512 (= kSparseThreads)
 constexpr int kChunkSmem = 4096;   // chunks whose prefix fits the shared-memory table (2 M voxels)
+constexpr int kScanBlocksPerSm = 2;  // blocks per SM that scan the bit planes in P1 (of the 3 resident ones)
 constexpr int kQueueCap = 160;     // non-empty words a warp collects before it drains them (P1)
 constexpr int kPoolWords = (kSparseThreads / 32) * 3 * kQueueCap > kChunkSmem ? (kSparseThreads / 32) * 3 * kQueueCap : kChunkSmem;
 static_assert((1 << kChunkShift) == kSparseThreads, "a ranking chunk is one block of voxels");
@@ -73,7 +74,7 @@ static BlobPlan make_plan(const pe_geom *g, int64_t cap) {
     p.off_coarse = o;  // per chunk: roots; then (maps beyond kChunkSmem chunks) their exclusive prefix
     o += align_up(2 * p.nchunk_cap * 4, 256);
     p.off_seg = o;
-    o += align_up(p.nseg * 4, 256);
+    o += align_up(p.nseg * 4, 256) + 1024;  // + per-SM block ranks and the count of scanning blocks (zeroed with the counts)
     p.total = o;
     return p;
 }
@@ -208,6 +209,9 @@ struct SparseArgs {
     int NC, NR, U1, U2, W;
     int64_t nwords_pad, cap, cap_blobs;
     int nseg;
+    int p1_blocks;             // blocks that take part in P1 (the others go straight to the first barrier)
+    int p1_per_sm;             // ... = this many per SM
+    int *sm_rank;              // [256] blocks seen per SM, [255] scanning blocks so far (zeroed per launch)
     const uint32_t *bmp;       // two planes, nwords_pad apart
     const uint32_t *segcount;  // foreground voxels per segment (K1)
     uint32_t *base;            // per non-empty word: position of its first set bit in the concatenated voxel list
@@ -267,11 +271,28 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
     stamp(0);
 
     // ---- P1: positions, keys, densities, initial parents
-    // contiguous run of segments per warp; the voxels before it are the segment counts before it
-    const int nwarps = nb * warps_per_block;
+    // contiguous run of segments per warp; the voxels before it are the segment counts before it.  Only the first p1_blocks blocks
+    // scan (two per SM: with a third one the same words take longer -- three copies of the count prefix per SM and 48 warps on the
+    // ballots and shuffles of the scan, profiles/r01_blob_sizes.md); the others wait at the barrier and read the totals after it.
+    uint32_t n0 = 0, n_all = 0;
+    // which blocks scan: the first p1_per_sm to arrive on each SM (block indices say nothing about placement); they number
+    // themselves densely in arrival order
+    __shared__ int scan_index;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int idx = -1;
+        if (a.p1_blocks >= nb) idx = b;  // every block scans
+        else if (atomicAdd(a.sm_rank + (smid < 254u ? smid : 254u), 1) < a.p1_per_sm) idx = atomicAdd(a.sm_rank + 255, 1);
+        scan_index = idx;
+    }
+    __syncthreads();
+    const int bi = scan_index;
+    if (bi >= 0 && bi < a.p1_blocks) {
+    const int nwarps = a.p1_blocks * warps_per_block;
     const int spw = (a.nseg + nwarps - 1) / nwarps;  // segments per warp
     const int seg_class1 = (int)(a.nwords_pad >> kSegShift);
-    const int sb = min(b * warps_per_block * spw, a.nseg);  // first segment of this block
+    const int sb = min(bi * warps_per_block * spw, a.nseg);  // first segment of this block
     {
         // this warp's words are requested into L2 now (K1 streamed the whole map through L2 after writing them), so the
         // loads below, behind the prefix computation, find them there
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
         for (int64_t i = ((int64_t)seg_begin << kSegShift) + 32 * lane; i < ((int64_t)seg_end << kSegShift); i += 32 * 32)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a.bmp + i));
     }
-    uint32_t before, n0, n_all;
+    uint32_t before;
     {
         uint32_t s_before = 0, s0 = 0, s_all = 0;
         constexpr int kBatch = 8;  // independent loads in flight per thread (one L2 round trip per batch, not per count)
@@ -302,17 +323,13 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
         n0 = block_sum_u32(s0, smem);
         n_all = block_sum_u32(s_all, smem);
     }
-    const int64_t n = (int64_t)n_all;
-    const uint32_t n1 = n_all - n0;
-    if (b == 0 && threadIdx.x == 0) {
+    const bool overflow = (int64_t)n0 > a.cap || (int64_t)(n_all - n0) > a.cap;  // the same in every scanning block
+    if (bi == 0 && threadIdx.x == 0) {
         a.counts[0] = (int64_t)n0;
-        a.counts[2] = (int64_t)n1;
+        a.counts[2] = (int64_t)(n_all - n0);
+        if (overflow) a.counts[4] = 1;
     }
-    if ((int64_t)n0 > a.cap || (int64_t)n1 > a.cap) {  // grid-uniform: nothing has been written yet
-        if (b == 0 && threadIdx.x == 0) a.counts[4] = 1;
-        return;
-    }
-    {
+    if (!overflow) {
         const int seg_begin = min(sb + warp * spw, a.nseg), seg_end = min(seg_begin + spw, a.nseg);
         uint32_t mine = 0;
         for (int i = sb + lane; i < seg_begin; i += 32) mine += a.segcount[i];
@@ -393,8 +410,22 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
             __syncwarp();
         }
     }
+    }  // scanning blocks
     grid.sync();
     stamp(1);
+    if (!(bi >= 0 && bi < a.p1_blocks)) {  // the totals the first scanning block left before the barrier
+        n0 = (uint32_t)__ldcg(a.counts + 0);
+        n_all = n0 + (uint32_t)__ldcg(a.counts + 2);
+    }
+    if (a.p1_blocks < nb && __ldcg(a.sm_rank + 255) != a.p1_blocks) {
+        // not every SM held its share of the scanning blocks (cannot happen while 3 blocks fill an SM; checked, not assumed):
+        // part of the planes was never scanned -- fail loudly instead of returning a partial list
+        if (b == 0 && threadIdx.x == 0) a.counts[4] = 2;
+        return;
+    }
+    if (__ldcg(a.counts + 4) != 0) return;  // a class overflows its capacity: grid-uniform, nothing has been written
+    const int64_t n = (int64_t)n_all;
+    const uint32_t n1 = n_all - n0;
 
     // ---- P2: hook the 12 predecessor neighbours outside the voxel's own column; zero the per-blob sums
     const int64_t gstride = (int64_t)nb * kSparseThreads;
@@ -694,7 +725,7 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
 
     PE_CUDA(cudaMemsetAsync(d_counts, 0, 5 * sizeof(int64_t), st));
     uint32_t *segcount = (uint32_t *)(ws + p.off_seg);
-    PE_CUDA(cudaMemsetAsync(segcount, 0, (size_t)p.nseg * sizeof(uint32_t), st));
+    PE_CUDA(cudaMemsetAsync(segcount, 0, (size_t)align_up(p.nseg * 4, 256) + 1024, st));
     // K1: the only pass over the map
     {
         const bool vec4 = (NC % 4 == 0) && (((uintptr_t)d_rho & 15u) == 0);
@@ -741,6 +772,11 @@ int pe_blob_label(const pe_geom *g, const float *d_rho, float cut_pos, float cut
         PE_CHECK_ARG(blocks_per_sm > 0, "pe_blob_label: the sparse kernel does not fit an SM");
     }
     const int nblocks = sm_count() * (blocks_per_sm < 3 ? blocks_per_sm : 3);
+    // P1 runs on two blocks per SM (384^3: 13.7 us against 16.7 us with all three scanning; 768^3 / 1024^3: no difference)
+    // -- only when exactly 3 blocks fill an SM, so that every SM is known to hold 3 of the grid's blocks; otherwise every block scans
+    a.p1_per_sm = blocks_per_sm == 3 ? kScanBlocksPerSm : (blocks_per_sm < 3 ? blocks_per_sm : 3);
+    a.p1_blocks = sm_count() * a.p1_per_sm;
+    a.sm_rank = (int *)(ws + p.off_seg + align_up(p.nseg * 4, 256));
     pe_geom geom = *g;
     void *args[] = {(void *)&geom, (void *)&a};
     PE_LAUNCH("blob_sparse_kernel", st,
