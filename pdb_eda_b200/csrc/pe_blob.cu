@@ -289,127 +289,127 @@ __global__ void __launch_bounds__(kSparseThreads, 3) blob_sparse_kernel(const __
     __syncthreads();
     const int bi = scan_index;
     if (bi >= 0 && bi < a.p1_blocks) {
-    const int nwarps = a.p1_blocks * warps_per_block;
-    const int spw = (a.nseg + nwarps - 1) / nwarps;  // segments per warp
-    const int seg_class1 = (int)(a.nwords_pad >> kSegShift);
-    const int sb = min(bi * warps_per_block * spw, a.nseg);  // first segment of this block
-    {
-        // this warp's words are requested into L2 now (K1 streamed the whole map through L2 after writing them), so the
-        // loads below, behind the prefix computation, find them there
-        const int seg_begin = min(sb + warp * spw, a.nseg), seg_end = min(seg_begin + spw, a.nseg);
-        for (int64_t i = ((int64_t)seg_begin << kSegShift) + 32 * lane; i < ((int64_t)seg_end << kSegShift); i += 32 * 32)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.bmp + i));
-    }
-    uint32_t before;
-    {
-        uint32_t s_before = 0, s0 = 0, s_all = 0;
-        constexpr int kBatch = 8;  // independent loads in flight per thread (one L2 round trip per batch, not per count)
-        for (int i0 = threadIdx.x; i0 < a.nseg; i0 += kSparseThreads * kBatch) {
-            uint32_t v[kBatch];
-#pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const int i = i0 + j * kSparseThreads;
-                v[j] = i < a.nseg ? __ldg(a.segcount + i) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const int i = i0 + j * kSparseThreads;
-                s_all += v[j];
-                if (i < sb) s_before += v[j];
-                if (i < seg_class1) s0 += v[j];
-            }
+        const int nwarps = a.p1_blocks * warps_per_block;
+        const int spw = (a.nseg + nwarps - 1) / nwarps;  // segments per warp
+        const int seg_class1 = (int)(a.nwords_pad >> kSegShift);
+        const int sb = min(bi * warps_per_block * spw, a.nseg);  // first segment of this block
+        {
+            // this warp's words are requested into L2 now (K1 streamed the whole map through L2 after writing them), so the
+            // loads below, behind the prefix computation, find them there
+            const int seg_begin = min(sb + warp * spw, a.nseg), seg_end = min(seg_begin + spw, a.nseg);
+            for (int64_t i = ((int64_t)seg_begin << kSegShift) + 32 * lane; i < ((int64_t)seg_end << kSegShift); i += 32 * 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.bmp + i));
         }
-        before = block_sum_u32(s_before, smem);
-        n0 = block_sum_u32(s0, smem);
-        n_all = block_sum_u32(s_all, smem);
-    }
-    const bool overflow = (int64_t)n0 > a.cap || (int64_t)(n_all - n0) > a.cap;  // the same in every scanning block
-    if (bi == 0 && threadIdx.x == 0) {
-        a.counts[0] = (int64_t)n0;
-        a.counts[2] = (int64_t)(n_all - n0);
-        if (overflow) a.counts[4] = 1;
-    }
-    if (!overflow) {
-        const int seg_begin = min(sb + warp * spw, a.nseg), seg_end = min(seg_begin + spw, a.nseg);
-        uint32_t mine = 0;
-        for (int i = sb + lane; i < seg_begin; i += 32) mine += a.segcount[i];
-        uint32_t run = before + (uint32_t)warp_sum((int)mine);
-        uint32_t carry = 0u;  // the word before the current one
-        if (seg_begin < seg_end && seg_begin > 0) carry = a.bmp[((int64_t)seg_begin << kSegShift) - 1];
-        const int64_t w_end = (int64_t)seg_end << kSegShift;
-        uint32_t *queue = pool + warp * (3 * kQueueCap);
-        int qn = 0;
-        uint4 next = make_uint4(0u, 0u, 0u, 0u);
-        if (seg_begin < seg_end) next = __ldcg(reinterpret_cast<const uint4 *>(a.bmp + ((int64_t)seg_begin << kSegShift) + 4 * lane));
-        for (int64_t i0 = (int64_t)seg_begin << kSegShift; i0 < w_end; i0 += 128) {
-            const int64_t widx0 = i0 + 4 * lane;
-            const uint4 wv = next;
-            if (i0 + 128 < w_end) next = __ldcg(reinterpret_cast<const uint4 *>(a.bmp + widx0 + 128));  // in flight during this iteration
-            const int c4 = __popc(wv.x) + __popc(wv.y) + __popc(wv.z) + __popc(wv.w);
-            const int excl = warp_excl_scan(c4, lane);
-            uint32_t p = run + (uint32_t)excl;
-            run += (uint32_t)__shfl_sync(kFull, excl + c4, 31);
-            uint32_t prevw = __shfl_up_sync(kFull, wv.w, 1);
-            if (lane == 0) prevw = carry;
-            carry = __shfl_sync(kFull, wv.w, 31);
-            // non-empty words go to the warp's queue: (word index, position of the word's first voxel | "the word before
-            // ends in a set bit" << 31, bits)
-            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint32_t before;
+        {
+            uint32_t s_before = 0, s0 = 0, s_all = 0;
+            constexpr int kBatch = 8;  // independent loads in flight per thread (one L2 round trip per batch, not per count)
+            for (int i0 = threadIdx.x; i0 < a.nseg; i0 += kSparseThreads * kBatch) {
+                uint32_t v[kBatch];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t word = words[q];
-                const unsigned act = __ballot_sync(kFull, word != 0u);
-                if (word) {
-                    const int slot = qn + __popc(act & ((1u << lane) - 1u));
-                    const uint32_t pw = q == 0 ? prevw : words[q > 0 ? q - 1 : 0];
-                    queue[slot] = (uint32_t)(widx0 + q);
-                    queue[kQueueCap + slot] = p | (pw & 0x80000000u);
-                    queue[2 * kQueueCap + slot] = word;
-                    p += (uint32_t)__popc(word);
+                for (int j = 0; j < kBatch; ++j) {
+                    const int i = i0 + j * kSparseThreads;
+                    v[j] = i < a.nseg ? __ldg(a.segcount + i) : 0u;
                 }
-                qn += __popc(act);
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int i = i0 + j * kSparseThreads;
+                    s_all += v[j];
+                    if (i < sb) s_before += v[j];
+                    if (i < seg_class1) s0 += v[j];
+                }
             }
-            const bool last = i0 + 128 >= w_end;
-            if (qn <= kQueueCap - 128 && !last) continue;  // room for another 128 words
-            // ---- drain: one lane per non-empty word (at +/-3 sigma one word in twenty: draining them as they come would
-            // leave two lanes of the warp busy)
-            __syncwarp();
-            for (int e = lane; e < qn; e += 32) {
-                const uint32_t widx = queue[e], pp = queue[kQueueCap + e], word = queue[2 * kQueueCap + e];
-                const uint32_t p_first = pp & 0x7fffffffu;
-                const int k = (int64_t)widx >= a.nwords_pad ? 1 : 0;
-                const uint32_t local = widx - (k ? (uint32_t)a.nwords_pad : 0u);
-                const uint32_t colrow = local / (uint32_t)a.W;
-                const int w = (int)(local - colrow * (uint32_t)a.W);
-                const int64_t out0 = (int64_t)k * a.cap - (k ? (int64_t)n0 : 0);  // output index = out0 + position
-                const bool prev_last = (w > 0) && (pp >> 31);
-                a.base[widx] = p_first;
-                // bits that start a run of consecutive sections inside this word (a run entering from the previous word
-                // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
-                const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
-                const uint32_t keybase = colrow * (uint32_t)a.U2 + (uint32_t)w * 32u;
-                uint32_t rest = word, pv = p_first;
-                while (rest) {
-                    const int bit = __ffs(rest) - 1;
-                    rest &= rest - 1;
-                    // parent = first voxel of the run (finds stay O(1) instead of O(run length))
-                    const uint32_t below = starts & ((2u << bit) - 1u);
-                    uint32_t par;
-                    if (below) {
-                        const int sbit = 31 - __clz(below);
-                        par = p_first + (uint32_t)__popc(word & ((1u << sbit) - 1u));
-                    } else {
-                        par = p_first - 1;  // the run continues from the previous word (prev_last is set)
+            before = block_sum_u32(s_before, smem);
+            n0 = block_sum_u32(s0, smem);
+            n_all = block_sum_u32(s_all, smem);
+        }
+        const bool overflow = (int64_t)n0 > a.cap || (int64_t)(n_all - n0) > a.cap;  // the same in every scanning block
+        if (bi == 0 && threadIdx.x == 0) {
+            a.counts[0] = (int64_t)n0;
+            a.counts[2] = (int64_t)(n_all - n0);
+            if (overflow) a.counts[4] = 1;
+        }
+        if (!overflow) {
+            const int seg_begin = min(sb + warp * spw, a.nseg), seg_end = min(seg_begin + spw, a.nseg);
+            uint32_t mine = 0;
+            for (int i = sb + lane; i < seg_begin; i += 32) mine += a.segcount[i];
+            uint32_t run = before + (uint32_t)warp_sum((int)mine);
+            uint32_t carry = 0u;  // the word before the current one
+            if (seg_begin < seg_end && seg_begin > 0) carry = a.bmp[((int64_t)seg_begin << kSegShift) - 1];
+            const int64_t w_end = (int64_t)seg_end << kSegShift;
+            uint32_t *queue = pool + warp * (3 * kQueueCap);
+            int qn = 0;
+            uint4 next = make_uint4(0u, 0u, 0u, 0u);
+            if (seg_begin < seg_end) next = __ldcg(reinterpret_cast<const uint4 *>(a.bmp + ((int64_t)seg_begin << kSegShift) + 4 * lane));
+            for (int64_t i0 = (int64_t)seg_begin << kSegShift; i0 < w_end; i0 += 128) {
+                const int64_t widx0 = i0 + 4 * lane;
+                const uint4 wv = next;
+                if (i0 + 128 < w_end) next = __ldcg(reinterpret_cast<const uint4 *>(a.bmp + widx0 + 128));  // in flight during this iteration
+                const int c4 = __popc(wv.x) + __popc(wv.y) + __popc(wv.z) + __popc(wv.w);
+                const int excl = warp_excl_scan(c4, lane);
+                uint32_t p = run + (uint32_t)excl;
+                run += (uint32_t)__shfl_sync(kFull, excl + c4, 31);
+                uint32_t prevw = __shfl_up_sync(kFull, wv.w, 1);
+                if (lane == 0) prevw = carry;
+                carry = __shfl_sync(kFull, wv.w, 31);
+                // non-empty words go to the warp's queue: (word index, position of the word's first voxel | "the word before
+                // ends in a set bit" << 31, bits)
+                const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t word = words[q];
+                    const unsigned act = __ballot_sync(kFull, word != 0u);
+                    if (word) {
+                        const int slot = qn + __popc(act & ((1u << lane) - 1u));
+                        const uint32_t pw = q == 0 ? prevw : words[q > 0 ? q - 1 : 0];
+                        queue[slot] = (uint32_t)(widx0 + q);
+                        queue[kQueueCap + slot] = p | (pw & 0x80000000u);
+                        queue[2 * kQueueCap + slot] = word;
+                        p += (uint32_t)__popc(word);
                     }
-                    a.key[out0 + pv] = keybase + (uint32_t)bit;
-                    a.parent[pv] = par;
-                    ++pv;
+                    qn += __popc(act);
                 }
+                const bool last = i0 + 128 >= w_end;
+                if (qn <= kQueueCap - 128 && !last) continue;  // room for another 128 words
+                // ---- drain: one lane per non-empty word (at +/-3 sigma one word in twenty: draining them as they come would
+                // leave two lanes of the warp busy)
+                __syncwarp();
+                for (int e = lane; e < qn; e += 32) {
+                    const uint32_t widx = queue[e], pp = queue[kQueueCap + e], word = queue[2 * kQueueCap + e];
+                    const uint32_t p_first = pp & 0x7fffffffu;
+                    const int k = (int64_t)widx >= a.nwords_pad ? 1 : 0;
+                    const uint32_t local = widx - (k ? (uint32_t)a.nwords_pad : 0u);
+                    const uint32_t colrow = local / (uint32_t)a.W;
+                    const int w = (int)(local - colrow * (uint32_t)a.W);
+                    const int64_t out0 = (int64_t)k * a.cap - (k ? (int64_t)n0 : 0);  // output index = out0 + position
+                    const bool prev_last = (w > 0) && (pp >> 31);
+                    a.base[widx] = p_first;
+                    // bits that start a run of consecutive sections inside this word (a run entering from the previous word
+                    // has no start bit here: its voxels point at the previous word's last voxel, one hop from that run's start)
+                    const uint32_t starts = word & ~((word << 1) | (prev_last ? 1u : 0u));
+                    const uint32_t keybase = colrow * (uint32_t)a.U2 + (uint32_t)w * 32u;
+                    uint32_t rest = word, pv = p_first;
+                    while (rest) {
+                        const int bit = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        // parent = first voxel of the run (finds stay O(1) instead of O(run length))
+                        const uint32_t below = starts & ((2u << bit) - 1u);
+                        uint32_t par;
+                        if (below) {
+                            const int sbit = 31 - __clz(below);
+                            par = p_first + (uint32_t)__popc(word & ((1u << sbit) - 1u));
+                        } else {
+                            par = p_first - 1;  // the run continues from the previous word (prev_last is set)
+                        }
+                        a.key[out0 + pv] = keybase + (uint32_t)bit;
+                        a.parent[pv] = par;
+                        ++pv;
+                    }
+                }
+                qn = 0;
+                __syncwarp();
             }
-            qn = 0;
-            __syncwarp();
         }
-    }
     }  // scanning blocks
     grid.sync();
     stamp(1);
